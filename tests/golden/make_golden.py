@@ -1,0 +1,167 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.json|*.npz by running the UNMODIFIED reference code.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+What is pinned
+  * analysis_synth.json : reference ``analyse_predictions`` / ``disparate_impact_analysis`` /
+                          ``confusion_matrix`` outputs (result dict + captured stdout) on the seeded
+                          instance dicts of tests/helpers.py (tone_bias_test.py:240-561).
+  * model_<kind>.npz    : reference ``SkinCancerListModel`` / ``SkinCancerModel`` (tone_bias_model.py)
+                          log-probabilities + a slice of every block output for the seeded weights of
+                          oracle.model.synthetic_state_dict and the seeded input batch.
+  * transform.npz       : reference ``Rescale`` + ``ToTensor`` (tone_bias_dataset.py:397-473) on seeded
+                          u8 images, with ``skimage.transform.resize`` bound to the scipy restatement
+                          (scikit-image itself is not installable here -- see oracle/__init__.py).
+  * notebook_di.json    : hand-transcribed from the reference's saved notebook outputs
+                          (notebooks/jgi_hiba_2022_torch.ipynb raw 3591-3617, 3643-3669, 3318-3322,
+                          3433-3434, 3178); written by this script so the provenance is in one place.
+"""
+import contextlib
+import io
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import model as omodel          # noqa: E402
+from oracle import ref_import               # noqa: E402
+from tests import helpers                   # noqa: E402
+
+
+def _jsonable(o):
+    if isinstance(o, dict):
+        return {str(k): _jsonable(v) for k, v in o.items()}
+    if isinstance(o, (list, tuple)):
+        return [_jsonable(v) for v in o]
+    if isinstance(o, (np.integer,)):
+        return int(o)
+    if isinstance(o, (np.floating,)):
+        return float(o)
+    return o
+
+
+def gen_analysis(ref):
+    cases = {}
+    for name, n, seed, odd in [("n500", 500, 11, True), ("n64", 64, 12, False), ("n1087", 1087, 13, True)]:
+        inst = helpers.synthetic_instances(n, seed, odd)
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            res = ref.test.analyse_predictions(inst)
+        tp, tn, fp, fn = ref.test.confusion_matrix(inst)
+        cases[name] = {
+            "n": n, "seed": seed, "with_oddities": odd, "result": _jsonable(res), "stdout": buf.getvalue(),
+            "cells": [len(tp), len(tn), len(fp), len(fn)],
+            "dark_count": ref.test.values_counts(inst, "skin_tone", "dark"),
+        }
+    with open(os.path.join(HERE, "analysis_synth.json"), "w") as f:
+        json.dump(cases, f, indent=1, sort_keys=True)
+
+
+def gen_model(ref):
+    torch.manual_seed(0)
+    for kind, cls in [(omodel.LIST_MODEL, ref.model.SkinCancerListModel),
+                      (omodel.FOUR_CONV_MODEL, ref.hiba.SkinCancerModel)]:
+        state = omodel.synthetic_state_dict(kind, seed=7)
+        m = cls(helpers.CLASS_NAMES).eval()
+        missing = m.load_state_dict(state, strict=True)
+        assert not missing.missing_keys and not missing.unexpected_keys
+        x = helpers.synthetic_batch_f32(4, 224, seed=21)
+        with torch.no_grad():
+            logp = m(x)
+            # block outputs through the reference's own submodules
+            feats = {}
+            if kind == omodel.LIST_MODEL:
+                h = x
+                for i, layer in enumerate(m.layers):
+                    h = layer(h)
+                    if i in (2, 5, 8, 11, 14):
+                        feats[f"after_{i}"] = h
+            else:
+                h = m.pool1(m.act1(m.conv1(x))); feats["conv1"] = h
+                h = m.pool2(m.act2(m.conv2(h))); feats["conv2"] = h
+                h = m.pool3(m.act3(m.conv3(h))); feats["conv3"] = h
+                h = m.pool4(m.act4(m.conv4(h))); feats["conv4"] = h
+        arrays = {"logp": logp.numpy(), "pred": torch.max(logp, 1)[1].numpy()}
+        for k, v in feats.items():
+            v = v.numpy()
+            arrays["feat_" + k + "_sum"] = np.array([v.astype(np.float64).sum(), np.abs(v).astype(np.float64).sum()])
+            arrays["feat_" + k + "_slice"] = v.reshape(v.shape[0], -1)[:, ::max(1, v[0].size // 64)][:, :64].copy()
+        np.savez_compressed(os.path.join(HERE, f"model_{kind}.npz"), **arrays)
+
+
+def gen_transform(ref):
+    arrays = {}
+    tf_tuple = [ref.dataset.Rescale((224, 224)), ref.dataset.ToTensor()]
+    cases = [("noise_450x600_224", 450, 600, 31, "noise", (224, 224)),
+             ("smooth_450x600_224", 450, 600, 32, "smooth", (224, 224)),
+             ("extremes_450x600_224", 450, 600, 33, "extremes", (224, 224)),
+             ("noise_450x600_512", 450, 600, 34, "noise", (512, 512)),
+             ("noise_97x131_int64", 97, 131, 35, "noise", 64),
+             ("noise_131x97_int48", 131, 97, 36, "noise", 48)]
+    for name, h, w, seed, kind, size in cases:
+        u8 = helpers.synthetic_u8_image(h, w, seed, kind)
+        image = np.float32(u8) / 255.0             # tone_bias_dataset.py:335
+        sample = (image, 1, 42)
+        sample = ref.dataset.Rescale(size)(sample)
+        t, label, idx = ref.dataset.ToTensor()(sample)
+        assert (label, idx) == (1, 42)
+        t = t.contiguous().numpy()
+        arrays[name + "_shape"] = np.array(t.shape)
+        arrays[name + "_sum"] = np.array([t.astype(np.float64).sum()])
+        if t.size <= 40000:
+            arrays[name + "_full"] = t
+        else:
+            arrays[name + "_sub"] = t[:, ::7, ::5].copy()
+    del tf_tuple
+    np.savez_compressed(os.path.join(HERE, "transform.npz"), **arrays)
+
+
+def gen_notebook():
+    nb = {
+        "source": "notebooks/jgi_hiba_2022_torch.ipynb (saved cell outputs)",
+        "tone": {"raw_lines": "3591-3617",
+                 "cells": {"tp_min": 6, "tn_min": 150, "fp_min": 11, "fn_min": 17,
+                           "tp_maj": 113, "tn_maj": 606, "fp_maj": 48, "fn_maj": 136},
+                 "printed": {"min_prevalence": 0.125, "maj_prevalence": 0.276, "min_precision": 0.353,
+                             "min_recall": 0.261, "min_f1": 0.300, "maj_precision": 0.702, "maj_recall": 0.454,
+                             "maj_f1": 0.551, "f1": 0.529, "min_group_accuracy": 0.848,
+                             "maj_group_accuracy": 0.796, "min_selected": 17, "min_count": 184,
+                             "maj_selected": 161, "maj_count": 903, "selection_rate_min": 0.092,
+                             "selection_rate_maj": 0.178, "di": 0.518, "di_inverse": 1.930}},
+        "sex": {"raw_lines": "3643-3669",
+                "cells": {"tp_min": 48, "tn_min": 414, "fp_min": 33, "fn_min": 75,
+                          "tp_maj": 70, "tn_maj": 342, "fp_maj": 26, "fn_maj": 78},
+                "printed": {"min_prevalence": 0.216, "maj_prevalence": 0.287, "min_precision": 0.593,
+                            "min_recall": 0.390, "min_f1": 0.471, "maj_precision": 0.729, "maj_recall": 0.473,
+                            "maj_f1": 0.574, "f1": 0.527, "min_group_accuracy": 0.811,
+                            "maj_group_accuracy": 0.798, "min_selected": 81, "min_count": 570,
+                            "maj_selected": 96, "maj_count": 516, "selection_rate_min": 0.142,
+                            "selection_rate_maj": 0.186, "di": 0.764, "di_inverse": 1.309}},
+        "sizes": {"raw_lines": "3318-3322", "dark": 184, "light": 903, "male": 516, "female": 570, "total": 1087},
+        "prevalence": {"raw_lines": "3433-3434", "dark_pos": 23, "light_pos": 249},
+        "overall": {"raw_lines": "3178", "correct": 875, "total": 1087, "accuracy": 0.805},
+    }
+    with open(os.path.join(HERE, "notebook_di.json"), "w") as f:
+        json.dump(nb, f, indent=1, sort_keys=True)
+
+
+def main():
+    ref = ref_import.load()
+    gen_notebook()
+    gen_analysis(ref)
+    gen_transform(ref)
+    gen_model(ref)
+    print("golden fixtures written to", HERE)
+
+
+if __name__ == "__main__":
+    main()
