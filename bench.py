@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""Benchmark of the batched-evaluation hot path (BASELINE.json metric: eval images/s at 224x224).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+
+A "step" is one batch through the whole path: fused resize/normalise of ``batch`` ISIC-shaped
+600x450 uint8 images -> SkinCancerListModel forward (bf16 tensor cores, fp32 accumulate) -> per-group
+confusion counts.  N=1 workload = BASELINE configs[1] (batch 256, bf16, 1 x B200).  For N>1 the driver
+launches one rank per GPU with torchrun; every rank evaluates its own batches (weak scaling) and the
+only collective is ONE all-reduce of the 576-byte count tensor at the end of the timed region.
+
+Prints one JSON line (rank 0).  ``value`` = whole-job images/s with inputs resident in HBM,
+CUDA-event timed, max over ranks.  ``e2e`` = same metric through the public ``EvalEngine.step`` call
+from pinned HOST buffers (H2D of every batch and D2H of the counts inside the timed region).
+``--impl reference`` times the reference's own CPU path (the oracle port of it: scipy/numpy resize +
+fp32 torch model + dict-based analysis) on this box's host cores with the same JSON schema.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+SRC_H, SRC_W, OUT = 450, 600, 224
+METRIC, UNIT = "eval_images_per_sec_224", "images/s"
+WORKLOAD = ("configs[1]: SkinCancerListModel eval, batch 256 per GPU, bf16, fused resize+normalise from synthetic "
+            "600x450 uint8 ISIC-shaped images, per-Fitzpatrick-group confusion counts")
+FLOPS_PER_IMAGE = {"conv1": 2 * 224 * 224 * 32 * 147, "conv2": 2 * 112 * 112 * 64 * 288,
+                   "conv3": 2 * 56 * 56 * 128 * 576, "fc1": 2 * 100352 * 512}
+PRE_BYTES_PER_IMAGE = SRC_H * SRC_W * 3 + 3 * OUT * OUT * 2          # algorithmic: u8 in + 3-channel bf16 out
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle port of the reference path on the host cores
+# ---------------------------------------------------------------------------------------------------
+def _resize_one(im):
+    from oracle import resize as R
+    return R.transform_u8(im, (OUT, OUT), R.resize_scipy)
+
+
+def cpu_reference_step(n_images: int, seed: int, state, pool):
+    """The reference's path for n_images on the host: transform in worker PROCESSES (the reference uses
+    DataLoader workers, tone_bias_test.py:637; scipy.ndimage holds the GIL so threads do not scale), fp32
+    torch forward on all cores, dict-based analysis."""
+    from oracle import analysis as oa
+    from oracle import model as om
+    from skin_image_analysis_b200.synthetic import counter_metadata
+    rng = np.random.default_rng(seed)
+    imgs = rng.integers(0, 256, (n_images, SRC_H, SRC_W, 3), dtype=np.uint8)
+    label, ftype, sex, control = counter_metadata(np.arange(n_images) + seed * n_images, 1)
+    t0 = time.perf_counter()
+    x = torch.from_numpy(np.stack(pool.map(_resize_one, list(imgs))))
+    logp = om.forward(om.LIST_MODEL, state, x)
+    pred = om.predict(logp).numpy()
+    names, fitz = ["benign", "malignant"], ["I", "II", "III", "IV", "V", "VI"]
+    inst = {i: {"benign_malignant": names[label[i]], "prediction": names[pred[i]], "skin_type": fitz[ftype[i]],
+                "skin_tone": "light" if ftype[i] < 2 else "dark", "sex": ["male", "female"][sex[i]],
+                "control": ["rich", "poor"][control[i]], "age": 50.0} for i in range(n_images)}
+    try:
+        oa.analyse_predictions(inst, out=lambda *a: None)
+    except ZeroDivisionError:
+        pass                                       # a tiny sample may leave a group empty, as in the reference
+    return time.perf_counter() - t0
+
+
+def cpu_baseline():
+    """Runs the reference arm in a fresh process (no CUDA context there, so worker processes can fork)."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3", "--warmup", "1"]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    try:
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+        line = json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1])
+        return line["cpu_baseline"]
+    except Exception as exc:                                        # never let the baseline kill the bench line
+        return {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {exc}"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    workers = min(cores, 32)
+    pool = mp.get_context("fork").Pool(workers)         # before any torch op starts its thread pool
+    pool.map(_resize_one, [np.zeros((SRC_H, SRC_W, 3), np.uint8)] * workers)
+    from oracle import model as om
+    torch.set_num_threads(cores)
+    state = om.synthetic_state_dict(om.LIST_MODEL, seed=0)
+    sample = args.ref_sample
+    for w in range(max(1, args.warmup)):
+        cpu_reference_step(sample, 100 + w, state, pool)
+    t = sum(cpu_reference_step(sample, 200 + s, state, pool) for s in range(args.steps))
+    pool.close()
+    value = sample * args.steps / t
+    desc = (f"{sample} synthetic 600x450 images per step x {args.steps} steps: scipy.ndimage resize in {workers} "
+            f"worker processes + fp32 torch CPU forward on {cores} threads + dict-based analysis")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": f"reference CPU path (oracle port), bounded sample of {sample} "
+                   "images per step"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+def build_state(device):
+    """Random-init weights of the reference architecture (xavier-normal weights, default biases) with the
+    head centred so both classes occur (un-centred random init predicts one class)."""
+    from skin_image_analysis_b200.tone_bias_model import SkinCancerListModel
+    torch.manual_seed(0)
+    model = SkinCancerListModel(["benign", "malignant"])
+    state = {k: v.clone() for k, v in model.state_dict().items()}
+    model = model.to(device).eval()
+    g = torch.Generator(device=device).manual_seed(1)
+    logp = model(torch.rand(64, 3, OUT, OUT, device=device, generator=g))
+    state["layers.16.bias"][1] -= float((logp[:, 1] - logp[:, 0]).median())
+    del model
+    return state
+
+
+def time_kernel(fn, stream, iters=20):
+    for _ in range(3):
+        fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stream.synchronize()
+    a.record(stream)
+    for _ in range(iters):
+        fn()
+    b.record(stream)
+    stream.synchronize()
+    return a.elapsed_time(b) / iters * 1e-3
+
+
+def stage_breakdown(eng, batch, peaks):
+    """Per-kernel average launch duration (CUDA events on the engine stream) -> roofline fractions."""
+    from skin_image_analysis_b200 import ops
+    plan, ws = eng.plan, eng.plan.workspace(batch)
+    acts = ws["acts"]
+    out = {}
+    with torch.cuda.stream(eng.stream):
+        t = time_kernel(lambda: ops.preprocess_u8hwc(eng.u8[0], (OUT, OUT), ops.LAYOUT_NHWC4_BF16, out=eng.x4),
+                        eng.stream)
+        gbs = PRE_BYTES_PER_IMAGE * batch / t / 1e9
+        out["preprocess"] = {"ms": t * 1e3, "bound": "hbm", "achieved": gbs, "unit": "GB/s", "peak": peaks["hbm_gbs"],
+                             "frac": gbs / peaks["hbm_gbs"]}
+        ins = [eng.x4] + acts[:-1]
+        for i, name in enumerate(["conv1", "conv2", "conv3"]):
+            packed, bias, _cin, cout = plan.convs[i]
+            if i == 0:
+                fn = lambda: ops.conv7x7_c3_relu_pool2(ins[0], packed, bias, out=acts[0])           # noqa: E731
+            else:
+                fn = (lambda i=i, packed=packed, bias=bias, cout=cout:
+                      ops.conv3x3_relu_pool2(ins[i], packed, bias, cout, out=acts[i]))
+            t = time_kernel(fn, eng.stream)
+            tf = FLOPS_PER_IMAGE[name] * batch / t / 1e12
+            out[name] = {"ms": t * 1e3, "bound": "tensor", "achieved": tf, "unit": "TFLOP/s",
+                         "peak": peaks["bf16_tflops_sustained"], "frac": tf / peaks["bf16_tflops_sustained"]}
+        a = acts[-1].view(batch, -1)
+        t = time_kernel(lambda: ops.linear_splitk(a, plan.w1, ws["splits"], out=ws["partial"]), eng.stream)
+        tf = FLOPS_PER_IMAGE["fc1"] * batch / t / 1e12
+        out["fc1"] = {"ms": t * 1e3, "bound": "tensor", "achieved": tf, "unit": "TFLOP/s",
+                      "peak": peaks["bf16_tflops_sustained"], "frac": tf / peaks["bf16_tflops_sustained"]}
+        t = time_kernel(lambda: ops.head_tail(ws["partial"], plan.b1, plan.w2t, plan.b2, plan.w3, plan.b3,
+                                              logp=ws["logp"], pred=ws["pred"]), eng.stream)
+        out["tail"] = {"ms": t * 1e3}
+    return out
+
+
+def run_ours(args):
+    from skin_image_analysis_b200 import distributed as D
+    from skin_image_analysis_b200 import tone_bias_test as tt
+    from skin_image_analysis_b200.engine import EvalEngine, N_ATTR
+    from skin_image_analysis_b200.synthetic import counter_metadata, device_u8_batches
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    rank, world, local = D.init_from_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    batch, steps, warmup = args.batch, args.steps, args.warmup
+    peaks = measured_peaks()
+
+    state = build_state(dev)
+    n_slots = 4
+    eng = EvalEngine(state, batch, (SRC_H, SRC_W), OUT, device=dev, n_slots=n_slots)
+    # ---- device-resident inputs: n_slots distinct batches (4 x 207 MB > 126 MB L2), unique metadata per
+    #      logical image index; rank r owns the contiguous index range [r*steps*batch, (r+1)*steps*batch)
+    ring = device_u8_batches(n_slots, batch, SRC_H, SRC_W, seed=100 + rank, device=dev)
+    for s in range(n_slots):
+        eng.u8[s].copy_(ring[s])
+    del ring
+    total_steps = warmup + steps
+    base_index = rank * steps * batch
+    meta = [counter_metadata(np.arange(batch, dtype=np.int64) + base_index + max(0, s - warmup) * batch, seed=7)
+            for s in range(total_steps)]
+    lab_dev = [torch.from_numpy(m[0]).to(dev) for m in meta]
+    grp_dev = [torch.from_numpy(np.stack(m[1:])).to(dev) for m in meta]
+
+    def resident_step(s):
+        slot = s % n_slots
+        with torch.cuda.stream(eng.stream):
+            eng.label[slot].copy_(lab_dev[s], non_blocking=True)
+            eng.groups[slot].copy_(grp_dev[s], non_blocking=True)
+        eng.step_resident(slot)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # ------------------------------------ value: inputs resident in HBM ------------------------------
+    for s in range(warmup):
+        resident_step(s)
+    eng.synchronize()
+    eng.reset_counts()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with ClockSampler(local) as clocks:
+        e0.record(eng.stream)
+        for s in range(warmup, total_steps):
+            resident_step(s)
+        with torch.cuda.stream(eng.stream):
+            D.allreduce_counts(eng.counts)              # the job's single collective (576 bytes)
+        e1.record(eng.stream)
+        barrier()
+    dt = D.max_over_ranks(e0.elapsed_time(e1) * 1e-3, device=dev)
+    value = world * steps * batch / dt
+    counts_resident = eng.read_counts()
+
+    # ------------------------------------ e2e: pinned host buffers, public API ------------------------
+    host_u8 = [torch.empty((batch, SRC_H, SRC_W, 3), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    for i, h in enumerate(host_u8):
+        h.copy_(eng.u8[i].cpu())
+    host_lab = [torch.from_numpy(m[0]).pin_memory() for m in meta]
+    host_grp = [torch.from_numpy(np.stack(m[1:])).pin_memory() for m in meta]
+    host_counts = torch.zeros_like(eng.counts, device="cpu").pin_memory()
+    e2e_steps = steps
+    for s in range(min(warmup, 3)):
+        eng.step(host_u8[s % 2], host_lab[s], host_grp[s], slot=s % n_slots)
+    eng.synchronize()
+    eng.reset_counts()
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(warmup, warmup + e2e_steps):
+        eng.step(host_u8[s % 2], host_lab[s], host_grp[s], slot=s % n_slots)
+        with torch.cuda.stream(eng.stream):
+            host_counts.copy_(eng.counts, non_blocking=True)       # the step's metric, D2H
+    with torch.cuda.stream(eng.stream):
+        D.allreduce_counts(eng.counts)
+    barrier()
+    dt_e2e = D.max_over_ranks(time.perf_counter() - t0, device=dev)
+    e2e_value = world * e2e_steps * batch / dt_e2e
+    counts_e2e = eng.read_counts()
+    h2d = batch * SRC_H * SRC_W * 3 + batch + N_ATTR * batch
+    d2h = host_counts.numel() * 8
+
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+
+    # ------------------------------------ rank 0: roofline, CPU baseline, report ----------------------
+    stages = stage_breakdown(eng, batch, peaks)
+    dominant = max((k for k in stages if "bound" in stages[k]), key=lambda k: stages[k]["ms"])
+    d = stages[dominant]
+    roofline = {"kernel": dominant, "bound": d["bound"], "achieved": d["achieved"], "peak": d["peak"],
+                "unit": d["unit"], "frac": d["frac"], "traffic": None,
+                "peak_source": peaks["source"] + (" (sustained bf16 GEMM)" if d["bound"] == "tensor" else " (copy)"),
+                "kernel_share_of_step": d["ms"] / (1e3 * dt / steps)}
+    cpu = cpu_baseline() if (world == 1 and not args.no_cpu_baseline) else None
+    summary = tt.results_from_type_counts(counts_resident, out=lambda *a: None)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": batch * world, "batch_per_gpu": batch,
+                   "parallelism": f"dp{world}", "l2": f"inputs larger than L2: ring of {n_slots} distinct "
+                   f"{batch * SRC_H * SRC_W * 3 / 1e6:.0f} MB batches per GPU", "cuda_graph": True},
+        "clocks": clocks.summary(),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": 1e3 * dt_e2e / e2e_steps},
+        "gpu_launches": steps * eng.launches_per_batch,
+        "roofline": roofline, "stages": stages, "cpu_baseline": cpu,
+        "check": {"images_counted": int(counts_resident[0].sum()), "expected": world * steps * batch,
+                  "e2e_images_counted": int(counts_e2e[0].sum()), "accuracy": summary["accuracy"],
+                  "tone_di": summary["tone_di_results"]["di"]},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--ref-sample", type=int, default=32, help="images per step of the reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

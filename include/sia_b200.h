@@ -1,0 +1,148 @@
+/*
+ * sia_b200.h -- C ABI of the B200-native batched-evaluation path of skin-image-analysis.
+ *
+ * One shared library (libsia_b200.so, built from skin_image_analysis_b200/csrc with nvcc for
+ * sm_100a).  Plain pointers, sizes and a cudaStream_t (passed as void*): no torch / C++ types cross
+ * this boundary and no C++ exception leaves it.  Every pointer is a DEVICE pointer unless the
+ * parameter name ends in `_host`.  Kernels never allocate; the caller owns every buffer.
+ *
+ * Each entry point replaces one library call site of the reference's evaluation path (the
+ * reference is pure Python, so "the FFI it would bind" is the ctypes stub shown in INTEGRATION.md):
+ *
+ *   sia_preprocess_u8hwc        np.float32(img)/255            src/tone_bias_dataset.py:335
+ *                               skimage.transform.resize       src/tone_bias_dataset.py:425
+ *                               image.transpose((2,0,1))       src/tone_bias_dataset.py:470
+ *   sia_conv7x7_c3_relu_pool2   Conv2d(3,32,7,'same')+ReLU+MaxPool2d   src/tone_bias_model.py:83-92, :169-172
+ *   sia_conv3x3_relu_pool2      Conv2d(C,2C,3,'same')+ReLU+MaxPool2d   src/tone_bias_model.py:83-92, :174-184
+ *   sia_linear_splitk           Flatten + Linear(100352,512)           src/tone_bias_model.py:100,111
+ *   sia_head_tail               ReLU, Linear(512,256)+ReLU, Linear(256,2), LogSoftmax, torch.max(.,1)
+ *                                                                      src/tone_bias_model.py:111-129,
+ *                                                                      src/tone_bias_test.py:199
+ *   sia_confusion_counts        the per-instance Python loops of predict_with_instance /
+ *                               confusion_matrix / filter / values_counts
+ *                                                                      src/tone_bias_test.py:207-234, 240-289
+ *
+ * Return value: 0 on success; > 0 a cudaError_t; < 0 one of SIA_E_*.
+ */
+#ifndef SIA_B200_H
+#define SIA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SIA_VERSION 100
+
+#define SIA_E_INVALID (-1)     /* bad argument (null pointer, non-positive size, misaligned pointer)  */
+#define SIA_E_UNSUPPORTED (-2) /* shape outside what the kernels were built for                       */
+#define SIA_E_DRIVER (-3)      /* could not resolve / call cuTensorMapEncodeTiled                     */
+#define SIA_E_WATCHDOG (-4)    /* a kernel's mbarrier watchdog fired (see sia_debug_watchdog)          */
+
+/* Output layouts of sia_preprocess_u8hwc */
+#define SIA_LAYOUT_NCHW_F32 0   /* [B,3,S,S] float32  -- what ToTensor + default collate produce        */
+#define SIA_LAYOUT_NCHW_BF16 1  /* [B,3,S,S] bfloat16                                                    */
+#define SIA_LAYOUT_NHWC4_BF16 2 /* [B,S,S,4] bfloat16, channel 3 = 0 -- the layout conv7x7_c3 consumes   */
+
+int sia_version(void);
+const char* sia_error_string(int code);
+/* Fills SM count and compute capability of the current device. */
+int sia_device_info(int* sm_count_host, int* cc_major_host, int* cc_minor_host);
+/* Returns the watchdog word of the current device (0 = never fired); reset != 0 clears it. */
+unsigned int sia_debug_watchdog(int reset);
+
+/* ------------------------------------------------------------------------------------------
+ * K1-K3  fused  u8 HWC -> (x/255) -> anti-aliased bilinear resize -> (v-mean)/std -> layout.
+ *
+ * The resize is the separable operator  out = Wy * img * Wx^T  where Wy/Wx are the banded
+ * matrices of (ndimage.zoom order 1, grid_mode, 'mirror') o (ndimage.gaussian_filter 'mirror'),
+ * i.e. skimage.transform.resize with the reference's defaults.  The caller passes the bands:
+ *   x_off[out_w]            first source column of output column j's window
+ *   x_w  [out_w * x_taps]   its x_taps weights (zero padded); x_taps is 8 or 16
+ *   row_w   [src_h * 4]     per SOURCE row r: weight of row r in each of the 4 accumulator slots
+ *   row_emit[src_h * 4]     per SOURCE row r: output row completed in that slot after r, or -1
+ *   y_first_last[out_h * 2] first and last source row that contribute to each output row
+ * (skin_image_analysis_b200/resize_weights.py builds them; 1/255 is folded into row_w).
+ * out = acc * out_scale[c] + out_bias[c]  (1/std and -mean/std; identity for the reference path).
+ * rows_per_cta output rows are produced per thread block.
+ * ------------------------------------------------------------------------------------------ */
+int sia_preprocess_u8hwc(const uint8_t* src, int batch, int src_h, int src_w, const int32_t* x_off,
+                         const float* x_w, int x_taps, const float* row_w, const int32_t* row_emit,
+                         const int32_t* y_first_last, int out_h, int out_w, const float* out_scale_host,
+                         const float* out_bias_host, int layout, int rows_per_cta, void* dst, void* stream);
+
+/* Model boundary: NCHW fp32 [B,3,h,w] (the tensor the reference DataLoader feeds to model(images),
+ * src/tone_bias_test.py:190-196) -> NHWC4 bf16 [B,h,w,4] (channel 3 = 0), the conv7x7_c3 input. */
+int sia_nchw_f32_to_nhwc4_bf16(const float* src, int batch, int h, int w, void* dst, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Weight packing (one-off, at model load).  Inputs are the reference's state_dict tensors
+ * (fp32, OIHW conv weights / [out,in] linear weights).
+ * ------------------------------------------------------------------------------------------ */
+/* conv1 [32,3,7,7] -> the 64 x 224 bf16 "two output pixels per GEMM row" operand (28672 bytes). */
+int sia_pack_conv7x7_c3(const float* w_oihw, void* packed, void* stream);
+size_t sia_pack_conv7x7_c3_bytes(void);
+/* conv [cout,cin,3,3] -> 9 taps x (cin/64 or 1) chunks of [cout][<=64] bf16, pre-swizzled. */
+int sia_pack_conv3x3(const float* w_oihw, int cin, int cout, void* packed, void* stream);
+size_t sia_pack_conv3x3_bytes(int cin, int cout);
+/* fc1 [n, c*h*w] (CHW-flattened columns) -> bf16 [n, h*w*c] (HWC-flattened columns). */
+int sia_pack_linear_chw_to_hwc(const float* w, int n, int c, int hw, void* packed_bf16, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K4  convolution blocks: conv + bias + ReLU + 2x2/2 max-pool, bf16 in / fp32 accumulate / bf16 out.
+ *   in  : NHWC4 bf16 [B,h,w,4] (conv7x7_c3)  or NHWC bf16 [B,h,w,cin] (conv3x3)
+ *   out : NHWC bf16 [B,h/2,w/2,cout]
+ * h and w must be even; conv7x7_c3 needs h%16==0 and w%16==0; conv3x3 needs w%8==0.
+ * Supported (cin,cout): (32,64), (64,128), (128,256).
+ * ------------------------------------------------------------------------------------------ */
+int sia_conv7x7_c3_relu_pool2(const void* in_nhwc4, int batch, int h, int w, const void* w_packed,
+                              const float* bias, void* out_nhwc, void* stream);
+int sia_conv3x3_relu_pool2(const void* in_nhwc, int batch, int h, int w, int cin, int cout, const void* w_packed,
+                           const float* bias, void* out_nhwc, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K5  split-K linear:  partial[s][m][n] = sum_{k in slice s} a[m][k] * w[n][k]   (fp32)
+ *   a : bf16 [m,k] row-major (the NHWC-flattened last conv output), w : bf16 [n,k] row-major.
+ *   n % 128 == 0, k % 64 == 0, 1 <= splits <= k/64.
+ * ------------------------------------------------------------------------------------------ */
+int sia_linear_splitk(const void* a_bf16, const void* w_bf16, int m, int n, int k, int splits, float* partial,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K6 (+K7)  tail:  h1 = relu(sum_s partial + b1); h2 = relu(W2 h1 + b2); z = W3 h2 + b3;
+ *           logp = log_softmax(z); pred = argmax (first maximum on ties).
+ *   w2t : fp32 [n1, n2] (TRANSPOSED Linear weight), w3 : fp32 [2, n2].   n1 <= 512, n2 <= 256.
+ *   If counts != NULL the per-group confusion counts of this batch are accumulated as by
+ *   sia_confusion_counts (label / groups must then be non-NULL).
+ * ------------------------------------------------------------------------------------------ */
+int sia_head_tail(const float* partial, int splits, int m, int n1, int n2, const float* b1, const float* w2t,
+                  const float* b2, const float* w3, const float* b3, float* logp, uint8_t* pred,
+                  const uint8_t* label, const uint8_t* groups, int groups_stride, int n_attr, int n_groups,
+                  long long* counts, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K7  counts[a][g][label][pred] += 1 for every instance i and attribute a with
+ *     g = groups[a*groups_stride + i] < n_groups  (any other value: the instance is in no group of
+ *     that attribute -- the reference's filter() semantics).  pred/label in {0,1}; 1 = 'malignant'.
+ *     counts: int64 [n_attr][n_groups][2][2], accumulated (caller zeroes).  n_attr*n_groups <= 256.
+ * ------------------------------------------------------------------------------------------ */
+int sia_confusion_counts(const uint8_t* pred, const uint8_t* label, const uint8_t* groups, long long n,
+                         long long groups_stride, int n_attr, int n_groups, long long* counts, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Debug / bring-up: run a list of tcgen05.mma (kind::f16, bf16 inputs) over a caller-supplied
+ * shared-memory image and return the 128 x n fp32 accumulator.  Descriptor start addresses are
+ * relative to the (1024-byte aligned) image base.  Used by tests/test_umma_probe.py to pin the
+ * descriptor conventions the conv kernels rely on; cycles_host (optional) gets the SM-clock
+ * cycles of `repeat` back-to-back issues of the list.
+ * ------------------------------------------------------------------------------------------ */
+int sia_debug_umma_probe(const void* smem_image, int image_bytes, const uint64_t* a_desc_host,
+                         const uint64_t* b_desc_host, int n_mma, int n, float* out_128xn, int repeat,
+                         long long* cycles_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIA_B200_H */

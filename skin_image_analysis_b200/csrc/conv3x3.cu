@@ -1,0 +1,292 @@
+// K4 (3x3 blocks): Conv2d(cin, cout, 3, stride 1, 'same') + bias + ReLU + MaxPool2d(2,2) as an
+// implicit GEMM on the 5th-gen tensor cores.  Replaces the ATen conv / relu / max_pool2d calls of
+// tone_bias_model.py:83-92 (layers.3, layers.6) and :174-184 (conv2..conv4).
+//
+//   D[128 pixels, cout] = sum over 9 taps (r,s), cin:  X[pixel + (r-1, s-1), cin] * W[cout, cin, r, s]
+//
+// * M-tile  = 16 rows x 8 columns of output pixels (row m = y*8 + x); N = cout; K = 9*cin.
+// * A operand: for each horizontal tap s the producer TMA-loads ONE x-shifted halo copy of the
+//   input patch, box [<=64 ch, 8 x, 18 y] (zero fill outside the image = 'same' padding).  In the
+//   swizzled K-major layout that box is 144 consecutive smem "rows" of one pixel each, so the three
+//   vertical taps r are simply the same buffer advanced by r*8 rows (= whole swizzle atoms): each
+//   loaded byte feeds 3 taps, every descriptor is canonical.  A ring of such buffers decouples TMA
+//   from the MMA issue.
+// * B operand: all 9 taps of the packed weights stay resident in shared memory (loaded once per
+//   persistent CTA with bulk copies).
+// * Accumulators: two 128 x cout fp32 tiles in TMEM, so the epilogue of tile i overlaps the MMAs
+//   of tile i+1.
+// * Epilogue (4 warps): tcgen05.ld -> +bias -> ReLU -> bf16 -> 2x2 max-pool across lanes with a
+//   shuffle reduce-scatter (x-neighbour = lane^1, y-neighbour = lane^8) -> 16-byte NHWC stores.
+//   The un-pooled activation never leaves the SM.
+//
+// Tensor-core bound; algorithmic FLOPs = 2 * H*W * 9*cin * cout per image.
+#include "sia_host.cuh"
+#include "sia_ptx.cuh"
+
+namespace sia {
+
+constexpr int CV_TILE_Y = 16;
+constexpr int CV_TILE_X = 8;
+constexpr int CV_HALO_ROWS = CV_TILE_Y + 2;
+constexpr int CV_THREADS = 256;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-7 epilogue
+
+template <int CIN, int COUT>
+struct ConvCfg {
+  static constexpr int CK = CIN < 64 ? CIN : 64;       // channels per smem row
+  static constexpr int NCHUNK = CIN / CK;
+  static constexpr int ROWB = CK * 2;                   // bytes per smem row (one pixel)
+  static constexpr uint32_t SWZ = ROWB == 128 ? SW_128B : SW_64B;
+  static constexpr int ATOM = 8 * ROWB;                 // 8-row swizzle atom = SBO
+  static constexpr int STAGE_BYTES = CV_HALO_ROWS * CV_TILE_X * ROWB;
+  static constexpr int B_TAP_BYTES = COUT * ROWB;       // one (tap, chunk) weight block
+  static constexpr int B_BYTES = 9 * NCHUNK * B_TAP_BYTES;
+  static constexpr int STEPS = 3 * NCHUNK;              // (s, chunk) buffers per tile
+  static constexpr int TMEM_COLS = 2 * COUT;
+};
+
+template <int CIN, int COUT, int NSTAGE>
+__global__ void __launch_bounds__(CV_THREADS, 1)
+conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restrict__ w_packed,
+               const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int H, int W, int tiles_y,
+               int tiles_x, int total_tiles) {
+  using C = ConvCfg<CIN, COUT>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_b = smem;                               // B_BYTES (multiple of 1024)
+  uint8_t* smem_a = smem + C::B_BYTES;                  // NSTAGE * STAGE_BYTES
+  float* smem_bias = reinterpret_cast<float*>(smem_a + NSTAGE * C::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_bias + COUT);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + NSTAGE;
+  uint64_t* tfull_bar = bars + 2 * NSTAGE;
+  uint64_t* tempty_bar = bars + 2 * NSTAGE + 2;
+  uint64_t* wload_bar = bars + 2 * NSTAGE + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 5);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSTAGE; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    mbar_init(wload_bar, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmap_in);
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) smem_bias[i] = bias[i];
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ==========================================
+    if (lane == 0) {
+      // resident weights: one expect_tx, a few bulk copies
+      mbar_arrive_expect_tx(wload_bar, C::B_BYTES);
+      constexpr int PIECE = 16384;
+      for (int off = 0; off < C::B_BYTES; off += PIECE) {
+        const int n = C::B_BYTES - off < PIECE ? C::B_BYTES - off : PIECE;
+        bulk_load_1d(smem_b + off, w_packed + off, n, wload_bar);
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int tx = tile % tiles_x;
+        const int ty = (tile / tiles_x) % tiles_y;
+        const int n = tile / (tiles_x * tiles_y);
+        for (int s = 0; s < 3; ++s) {
+          for (int kc = 0; kc < C::NCHUNK; ++kc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1, 20);
+            mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+            tma_load_4d(smem_a + stage * C::STAGE_BYTES, &tmap_in, &full_bar[stage], kc * C::CK,
+                        tx * CV_TILE_X + s - 1, ty * CV_TILE_Y - 1, n);
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ============================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, COUT);
+      const uint32_t a_base = smem_u32(smem_a);
+      const uint32_t b_base = smem_u32(smem_b);
+      mbar_wait(wload_bar, 0, 21);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 22);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * COUT;
+        uint32_t first = 1;
+        for (int s = 0; s < 3; ++s) {
+          for (int kc = 0; kc < C::NCHUNK; ++kc) {
+            mbar_wait(&full_bar[stage], phase, 23);
+            tc_fence_after_sync();
+            const uint32_t a_stage = a_base + stage * C::STAGE_BYTES;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+              const uint32_t b_tap = b_base + ((r * 3 + s) * C::NCHUNK + kc) * C::B_TAP_BYTES;
+#pragma unroll
+              for (int kk = 0; kk < C::CK / 16; ++kk) {
+                const uint64_t a_desc = make_smem_desc(a_stage + r * C::ATOM + kk * 32, 0, C::ATOM, C::SWZ);
+                const uint64_t b_desc = make_smem_desc(b_tap + kk * 32, 0, C::ATOM, C::SWZ);
+                umma_bf16_ss(d_tmem, a_desc, b_desc, idesc, first ? 0u : 1u);
+                first = 0;
+              }
+            }
+            umma_commit(&empty_bar[stage]);  // buffer reusable once these MMAs have read it
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+          }
+        }
+        umma_commit(&tfull_bar[acc]);        // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue ==============================================
+    const int e = warp - 4;                   // TMEM lanes 32e .. 32e+31
+    const int Ho = H >> 1, Wo = W >> 1;
+    const int ly = lane >> 3;                 // 0..3  (tile row 4e + ly)
+    const int lx = lane & 7;                  // tile column
+    const bool odd_x = lane & 1;
+    const bool odd_y = (lane >> 3) & 1;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int tx = tile % tiles_x;
+      const int ty = (tile / tiles_x) % tiles_y;
+      const int n = tile / (tiles_x * tiles_y);
+      const int py = ((ty * CV_TILE_Y + 4 * e + ly) >> 1);
+      const int px = ((tx * CV_TILE_X + lx) >> 1);
+      const bool in_range = py < Ho && px < Wo;
+      __nv_bfloat16* orow = out + (((size_t)n * Ho + py) * Wo + px) * COUT;
+      mbar_wait(&tfull_bar[acc], acc_phase, 24);
+      tc_fence_after_sync();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(32 * e) << 16) + acc * COUT;
+#pragma unroll 1
+      for (int cb = 0; cb < COUT; cb += 32) {
+        uint32_t v[32];
+        tmem_ld32(t_addr + cb, v);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float a = fmaxf(__uint_as_float(v[2 * j]) + smem_bias[cb + 2 * j], 0.f);
+          const float b = fmaxf(__uint_as_float(v[2 * j + 1]) + smem_bias[cb + 2 * j + 1], 0.f);
+          pk[j] = pack_bf16x2(a, b);
+        }
+        // reduce-scatter over the 2x2 window: x partner keeps/sends 8 of 16 regs, y partner 4 of 8
+        uint32_t h8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t keep = odd_x ? pk[8 + j] : pk[j];
+          const uint32_t send = odd_x ? pk[j] : pk[8 + j];
+          h8[j] = max_bf16x2(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+        }
+        uint32_t q4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t keep = odd_y ? h8[4 + j] : h8[j];
+          const uint32_t send = odd_y ? h8[j] : h8[4 + j];
+          q4[j] = max_bf16x2(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+        }
+        if (in_range) {
+          const int ch = cb + (odd_x ? 16 : 0) + (odd_y ? 8 : 0);
+          *reinterpret_cast<uint4*>(orow + ch) = make_uint4(q4[0], q4[1], q4[2], q4[3]);
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tmem_free(tmem_base, C::TMEM_COLS);
+}
+
+// ------------------------------- weight packing ----------------------------------------------
+// [cout][cin][3][3] fp32 -> for tap (r,s), chunk kc: [cout rows][CK channels] bf16, K-major, with the
+// 16-byte units of each row XOR-swizzled by the row index exactly as TMA / UMMA swizzle modes do
+// (128B rows: unit ^= row%8 ; 64B rows: unit ^= (row/2)%4).
+__global__ void pack_conv3x3_kernel(const float* __restrict__ w, int cin, int cout, __nv_bfloat16* __restrict__ dst) {
+  const int ck = cin < 64 ? cin : 64;
+  const int nchunk = cin / ck;
+  const int total = 9 * cin * cout;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c_in_chunk = i % ck;
+    const int row = (i / ck) % cout;
+    const int kc = (i / (ck * cout)) % nchunk;
+    const int tap = i / (ck * cout * nchunk);
+    const int r = tap / 3, s = tap % 3;
+    const int c = kc * ck + c_in_chunk;
+    const float v = w[(((size_t)row * cin + c) * 3 + r) * 3 + s];
+    const int unit = c_in_chunk / 8;
+    const int swz = ck == 64 ? (unit ^ (row & 7)) : (unit ^ ((row >> 1) & 3));
+    const size_t block = ((size_t)tap * nchunk + kc) * cout * ck;
+    dst[block + (size_t)row * ck + swz * 8 + (c_in_chunk & 7)] = __float2bfloat16_rn(v);
+  }
+}
+
+template <int CIN, int COUT, int NSTAGE>
+static int launch_conv3x3(const void* in, int batch, int h, int w, const void* w_packed, const float* bias, void* out,
+                          cudaStream_t st) {
+  using C = ConvCfg<CIN, COUT>;
+  CUtensorMap tmap;
+  const uint64_t dims[4] = {(uint64_t)CIN, (uint64_t)w, (uint64_t)h, (uint64_t)batch};
+  const uint64_t strides[3] = {(uint64_t)CIN * 2, (uint64_t)w * CIN * 2, (uint64_t)h * w * CIN * 2};
+  const uint32_t box[4] = {(uint32_t)C::CK, CV_TILE_X, CV_HALO_ROWS, 1};
+  int rc = encode_tmap_bf16(&tmap, in, 4, dims, strides, box,
+                            C::ROWB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+  if (rc != 0) return rc;
+  const int tiles_y = (h + CV_TILE_Y - 1) / CV_TILE_Y;
+  const int tiles_x = w / CV_TILE_X;
+  const int total = tiles_y * tiles_x * batch;
+  const int smem = 1024 + C::B_BYTES + NSTAGE * C::STAGE_BYTES + COUT * 4 + (2 * NSTAGE + 6) * 8;
+  auto kern = conv3x3_kernel<CIN, COUT, NSTAGE>;
+  static int configured = 0;
+  if (int rc2 = ensure_dynamic_smem(kern, smem, &configured)) return rc2;
+  const int grid = total < sm_count() ? total : sm_count();
+  kern<<<grid, CV_THREADS, smem, st>>>(tmap, static_cast<const uint8_t*>(w_packed), bias,
+                                       static_cast<__nv_bfloat16*>(out), h, w, tiles_y, tiles_x, total);
+  return launch_status();
+}
+
+}  // namespace sia
+
+extern "C" size_t sia_pack_conv3x3_bytes(int cin, int cout) { return (size_t)9 * cin * cout * 2; }
+
+extern "C" int sia_pack_conv3x3(const float* w_oihw, int cin, int cout, void* packed, void* stream) {
+  using namespace sia;
+  SIA_REQUIRE(w_oihw && packed && cin >= 32 && cout >= 8);
+  if (!((cin == 32) || (cin % 64 == 0))) return SIA_E_UNSUPPORTED;
+  const int total = 9 * cin * cout;
+  pack_conv3x3_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w_oihw, cin, cout, static_cast<__nv_bfloat16*>(packed));
+  return launch_status();
+}
+
+extern "C" int sia_conv3x3_relu_pool2(const void* in_nhwc, int batch, int h, int w, int cin, int cout,
+                                      const void* w_packed, const float* bias, void* out_nhwc, void* stream) {
+  using namespace sia;
+  SIA_REQUIRE(in_nhwc && w_packed && bias && out_nhwc && batch >= 1 && h >= 2 && w >= 8);
+  SIA_REQUIRE(aligned(in_nhwc, 16) && aligned(w_packed, 16) && aligned(out_nhwc, 16));
+  if (h % 2 != 0 || w % CV_TILE_X != 0) return SIA_E_UNSUPPORTED;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (cin == 32 && cout == 64) return launch_conv3x3<32, 64, 8>(in_nhwc, batch, h, w, w_packed, bias, out_nhwc, st);
+  if (cin == 64 && cout == 128) return launch_conv3x3<64, 128, 4>(in_nhwc, batch, h, w, w_packed, bias, out_nhwc, st);
+  return SIA_E_UNSUPPORTED;
+}

@@ -1,0 +1,40 @@
+// Library-wide state and the small informational entry points of the C ABI.
+#include "sia_host.cuh"
+#include "sia_ptx.cuh"
+
+extern "C" {
+
+int sia_version(void) { return SIA_VERSION; }
+
+const char* sia_error_string(int code) {
+  if (code == 0) return "ok";
+  if (code > 0) return cudaGetErrorString((cudaError_t)code);
+  switch (code) {
+    case SIA_E_INVALID: return "sia: invalid argument";
+    case SIA_E_UNSUPPORTED: return "sia: unsupported shape";
+    case SIA_E_DRIVER: return "sia: cuTensorMapEncodeTiled unavailable or failed";
+    case SIA_E_WATCHDOG: return "sia: kernel watchdog fired (mbarrier wait timed out)";
+    default: return "sia: unknown error";
+  }
+}
+
+int sia_device_info(int* sm_count_host, int* cc_major_host, int* cc_minor_host) {
+  int dev = 0;
+  SIA_CUDA_OK(cudaGetDevice(&dev));
+  if (sm_count_host) SIA_CUDA_OK(cudaDeviceGetAttribute(sm_count_host, cudaDevAttrMultiProcessorCount, dev));
+  if (cc_major_host) SIA_CUDA_OK(cudaDeviceGetAttribute(cc_major_host, cudaDevAttrComputeCapabilityMajor, dev));
+  if (cc_minor_host) SIA_CUDA_OK(cudaDeviceGetAttribute(cc_minor_host, cudaDevAttrComputeCapabilityMinor, dev));
+  return 0;
+}
+
+unsigned int sia_debug_watchdog(int reset) {
+  unsigned int v = 0;
+  if (cudaMemcpyFromSymbol(&v, sia::g_watchdog_code, sizeof(v)) != cudaSuccess) return 0xffffffffu;
+  if (reset) {
+    unsigned int z = 0;
+    cudaMemcpyToSymbol(sia::g_watchdog_code, &z, sizeof(z));
+  }
+  return v;
+}
+
+}  // extern "C"

@@ -1,0 +1,10 @@
+// The whole library is ONE translation unit: a single copy of the device-side watchdog word, no
+// relocatable device code, one nvcc invocation (see skin_image_analysis_b200/build.py).
+#include "core.cu"
+#include "tmap.cu"
+#include "probe.cu"
+#include "counts.cu"
+#include "preprocess.cu"
+#include "conv1.cu"
+#include "conv3x3.cu"
+#include "linear.cu"

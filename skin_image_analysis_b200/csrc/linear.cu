@@ -1,0 +1,261 @@
+// K5 / K6: the fully connected part of the network.
+//
+//   sia_linear_splitk : Flatten + Linear(K -> N) as a split-K tcgen05 GEMM           tone_bias_model.py:100,111
+//   sia_head_tail     : split-K reduce + bias + ReLU, Linear(512,256)+ReLU, Linear(256,2),
+//                       LogSoftmax, argmax (+ optional fused confusion counts)        tone_bias_model.py:111-129,
+//                                                                                    tone_bias_test.py:199
+//
+// fc1 is skinny (M = batch, N = 512, K = 100352): only (M/128)*(N/128) output tiles exist, so K is
+// split across CTAs until the grid fills the GPU; each CTA streams its K-slice of A (activations,
+// NHWC-flattened) and W (columns pre-permuted CHW->HWC at load) through a TMA/mbarrier ring in the
+// canonical 128B-swizzled K-major layout and leaves an fp32 partial tile.  The partials are summed
+// in a fixed order by the tail kernel, so the result is deterministic.
+#include <math.h>
+
+#include "sia_host.cuh"
+#include "sia_ptx.cuh"
+
+namespace sia {
+
+constexpr int LN_BM = 128, LN_BN = 128, LN_BK = 64;
+constexpr int LN_STAGE_BYTES = (LN_BM + LN_BN) * LN_BK * 2;  // 32 KB
+constexpr int LN_NSTAGE = 6;
+constexpr int LN_THREADS = 192;  // warp0 TMA, warp1 MMA (+TMEM alloc), warps2-5 epilogue
+
+__global__ void __launch_bounds__(LN_THREADS, 1)
+linear_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                     float* __restrict__ partial, int M, int N, int kblocks_total, int splits) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + LN_NSTAGE * LN_STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + LN_NSTAGE;
+  uint64_t* done_bar = bars + 2 * LN_NSTAGE;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * LN_NSTAGE + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_blk = blockIdx.x, n_blk = blockIdx.y, split = blockIdx.z;
+  // contiguous, near-equal K slices
+  const int kb_lo = (int)((long long)kblocks_total * split / splits);
+  const int kb_hi = (int)((long long)kblocks_total * (split + 1) / splits);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < LN_NSTAGE; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(done_bar, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_w);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, LN_BN);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb_lo; kb < kb_hi; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1, 40);
+        uint8_t* sa = smem + stage * LN_STAGE_BYTES;
+        uint8_t* sw = sa + LN_BM * LN_BK * 2;
+        mbar_arrive_expect_tx(&full_bar[stage], LN_STAGE_BYTES);
+        tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * LN_BK, m_blk * LN_BM);
+        tma_load_2d(sw, &tmap_w, &full_bar[stage], kb * LN_BK, n_blk * LN_BN);
+        if (++stage == LN_NSTAGE) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(LN_BM, LN_BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb_lo; kb < kb_hi; ++kb) {
+        mbar_wait(&full_bar[stage], phase, 41);
+        tc_fence_after_sync();
+        const uint32_t sa = smem_u32(smem + stage * LN_STAGE_BYTES);
+        const uint32_t sw = sa + LN_BM * LN_BK * 2;
+#pragma unroll
+        for (int kk = 0; kk < LN_BK / 16; ++kk) {
+          const uint64_t a_desc = make_smem_desc(sa + kk * 32, 0, 1024, SW_128B);
+          const uint64_t b_desc = make_smem_desc(sw + kk * 32, 0, 1024, SW_128B);
+          umma_bf16_ss(tmem_base, a_desc, b_desc, idesc, (kb > kb_lo || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == LN_NSTAGE) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(done_bar);
+    }
+  } else {
+    // epilogue: warp w may only touch TMEM lanes 32*(w%4) ..
+    const int e = warp & 3;
+    const int row = m_blk * LN_BM + e * 32 + lane;
+    mbar_wait(done_bar, 0, 42);
+    tc_fence_after_sync();
+    float* dst = partial + ((size_t)split * M + row) * N + n_blk * LN_BN;
+#pragma unroll 1
+    for (int cb = 0; cb < LN_BN; cb += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(32 * e) << 16) + cb, v);
+      tmem_ld_wait();
+      if (row < M) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          *reinterpret_cast<float4*>(dst + cb + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                 __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_free(tmem_base, LN_BN);
+}
+
+// ------------------------------------- tail --------------------------------------------------
+constexpr int TAIL_THREADS = 256;
+constexpr int TAIL_IMGS = 4;     // images per CTA (amortises the W2 read)
+constexpr int TAIL_MAX_N1 = 512;
+constexpr int TAIL_MAX_N2 = 256;
+
+__global__ void __launch_bounds__(TAIL_THREADS)
+head_tail_kernel(const float* __restrict__ partial, int splits, int M, int n1, int n2, const float* __restrict__ b1,
+                 const float* __restrict__ w2t, const float* __restrict__ b2, const float* __restrict__ w3,
+                 const float* __restrict__ b3, float* __restrict__ logp, uint8_t* __restrict__ pred,
+                 const uint8_t* __restrict__ label, const uint8_t* __restrict__ groups, int groups_stride, int n_attr,
+                 int n_groups, unsigned long long* __restrict__ counts) {
+  __shared__ float h1[TAIL_IMGS][TAIL_MAX_N1];
+  __shared__ float h2[TAIL_IMGS][TAIL_MAX_N2];
+  __shared__ float z[TAIL_IMGS][2];
+  const int m0 = blockIdx.x * TAIL_IMGS;
+
+  // h1 = relu(b1 + sum over splits, in split order)
+  for (int i = threadIdx.x; i < TAIL_IMGS * n1; i += blockDim.x) {
+    const int img = i / n1, k = i % n1;
+    float s = 0.f;
+    if (m0 + img < M) {
+      for (int sp = 0; sp < splits; ++sp) s += partial[((size_t)sp * M + m0 + img) * n1 + k];
+      s = fmaxf(s + b1[k], 0.f);
+    }
+    h1[img][k] = s;
+  }
+  __syncthreads();
+
+  // h2 = relu(W2 h1 + b2): thread j owns output j for all images; w2t is [n1][n2] so reads coalesce
+  for (int j = threadIdx.x; j < n2; j += blockDim.x) {
+    float a[TAIL_IMGS];
+#pragma unroll
+    for (int img = 0; img < TAIL_IMGS; ++img) a[img] = 0.f;
+    for (int k = 0; k < n1; ++k) {
+      const float w = w2t[(size_t)k * n2 + j];
+#pragma unroll
+      for (int img = 0; img < TAIL_IMGS; ++img) a[img] = fmaf(w, h1[img][k], a[img]);
+    }
+#pragma unroll
+    for (int img = 0; img < TAIL_IMGS; ++img) h2[img][j] = fmaxf(a[img] + b2[j], 0.f);
+  }
+  __syncthreads();
+
+  // z = W3 h2 + b3: one warp per (image, class)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp < TAIL_IMGS * 2) {
+    const int img = warp >> 1, cls = warp & 1;
+    float s = 0.f;
+    for (int j = lane; j < n2; j += 32) s = fmaf(w3[cls * n2 + j], h2[img][j], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) z[img][cls] = s + b3[cls];
+  }
+  __syncthreads();
+
+  if (threadIdx.x < TAIL_IMGS && m0 + threadIdx.x < M) {
+    const int img = threadIdx.x, m = m0 + img;
+    const float z0 = z[img][0], z1 = z[img][1];
+    const float mx = fmaxf(z0, z1);
+    const float lse = mx + logf(expf(z0 - mx) + expf(z1 - mx));
+    logp[2 * m] = z0 - lse;
+    logp[2 * m + 1] = z1 - lse;
+    const int pr = (z1 > z0) ? 1 : 0;   // torch.max: first maximal index on ties
+    pred[m] = (uint8_t)pr;
+    if (counts != nullptr) {
+      const int cell = ((label[m] != 0) ? 2 : 0) | pr;
+      for (int a = 0; a < n_attr; ++a) {
+        const int g = groups[(size_t)a * groups_stride + m];
+        if (g < n_groups) atomicAdd(&counts[(a * n_groups + g) * 4 + cell], 1ull);
+      }
+    }
+  }
+}
+
+// fc1 weight [n][c*hw] (column = c*hw + p) -> bf16 [n][hw*c] (column = p*c_total + c)
+__global__ void pack_linear_kernel(const float* __restrict__ w, int n, int c, int hw, __nv_bfloat16* __restrict__ dst) {
+  const size_t total = (size_t)n * c * hw;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % c);
+    const size_t rest = i / c;
+    const int p = (int)(rest % hw);
+    const size_t row = rest / hw;
+    dst[i] = __float2bfloat16_rn(w[(row * c + ch) * hw + p]);
+  }
+}
+
+}  // namespace sia
+
+extern "C" int sia_pack_linear_chw_to_hwc(const float* w, int n, int c, int hw, void* packed_bf16, void* stream) {
+  using namespace sia;
+  SIA_REQUIRE(w && packed_bf16 && n >= 1 && c >= 1 && hw >= 1);
+  pack_linear_kernel<<<sm_count() * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, n, c, hw, static_cast<__nv_bfloat16*>(packed_bf16));
+  return launch_status();
+}
+
+extern "C" int sia_linear_splitk(const void* a_bf16, const void* w_bf16, int m, int n, int k, int splits,
+                                 float* partial, void* stream) {
+  using namespace sia;
+  SIA_REQUIRE(a_bf16 && w_bf16 && partial && m >= 1 && n >= 1 && k >= 1 && splits >= 1);
+  SIA_REQUIRE(aligned(a_bf16, 16) && aligned(w_bf16, 16) && aligned(partial, 16));
+  if (n % LN_BN != 0 || k % LN_BK != 0 || splits > k / LN_BK || splits > 65535) return SIA_E_UNSUPPORTED;
+  CUtensorMap ta, tw;
+  {
+    const uint64_t dims[2] = {(uint64_t)k, (uint64_t)m};
+    const uint64_t strides[1] = {(uint64_t)k * 2};
+    const uint32_t box[2] = {LN_BK, LN_BM};
+    int rc = encode_tmap_bf16(&ta, a_bf16, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != 0) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)k, (uint64_t)n};
+    const uint64_t strides[1] = {(uint64_t)k * 2};
+    const uint32_t box[2] = {LN_BK, LN_BN};
+    int rc = encode_tmap_bf16(&tw, w_bf16, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != 0) return rc;
+  }
+  const int smem = 1024 + LN_NSTAGE * LN_STAGE_BYTES + (2 * LN_NSTAGE + 2) * 8;
+  static int configured = 0;
+  if (int rc2 = ensure_dynamic_smem(linear_splitk_kernel, smem, &configured)) return rc2;
+  dim3 grid((m + LN_BM - 1) / LN_BM, n / LN_BN, splits);
+  linear_splitk_kernel<<<grid, LN_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(ta, tw, partial, m, n,
+                                                                                     k / LN_BK, splits);
+  return launch_status();
+}
+
+extern "C" int sia_head_tail(const float* partial, int splits, int m, int n1, int n2, const float* b1,
+                             const float* w2t, const float* b2, const float* w3, const float* b3, float* logp,
+                             uint8_t* pred, const uint8_t* label, const uint8_t* groups, int groups_stride, int n_attr,
+                             int n_groups, long long* counts, void* stream) {
+  using namespace sia;
+  SIA_REQUIRE(partial && b1 && w2t && b2 && w3 && b3 && logp && pred && splits >= 1 && m >= 1);
+  if (n1 < 1 || n1 > TAIL_MAX_N1 || n2 < 1 || n2 > TAIL_MAX_N2) return SIA_E_UNSUPPORTED;
+  if (counts != nullptr) {
+    SIA_REQUIRE(label && groups && n_attr >= 1 && n_groups >= 1 && groups_stride >= m);
+  }
+  head_tail_kernel<<<(m + TAIL_IMGS - 1) / TAIL_IMGS, TAIL_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      partial, splits, m, n1, n2, b1, w2t, b2, w3, b3, logp, pred, label, groups, groups_stride, n_attr, n_groups,
+      reinterpret_cast<unsigned long long*>(counts));
+  return launch_status();
+}

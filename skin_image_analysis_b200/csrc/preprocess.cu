@@ -1,0 +1,269 @@
+// K1-K3: fused  u8 HWC -> /255 -> anti-aliased bilinear resize -> normalise -> output layout.
+//
+// Replaces, for a whole batch resident in HBM, the per-image CPU chain of the reference:
+//   np.float32(img)/255.0                      tone_bias_dataset.py:335
+//   skimage.transform.resize(img, (h, w))      tone_bias_dataset.py:425   (gaussian_filter + zoom, 'mirror')
+//   img.transpose((2,0,1)) + collate           tone_bias_dataset.py:470
+//
+// The resize is a separable banded operator out = Wy * img * Wx^T (boundary folding already in the
+// bands, built on the host in float64 by resize_weights.py).  One thread owns one output column
+// and streams DOWN the source rows:
+//   horizontal pass  h[c]      = sum_t x_w[t] * u8[row][x_off + t][c]          (weights in registers)
+//   vertical pass    acc[s][c] += row_w[row][s] * h[c]   for the <=4 output rows in flight
+//   emit             when a source row completes an output row, scale/bias it and store it.
+// Nothing intermediate touches shared or global memory; source rows are staged once per CTA in a
+// 3-deep ring of shared-memory chunks by a producer warp using 1-D bulk async copies
+// (cp.async.bulk + mbarrier complete_tx), so every HBM byte is read once per row band.
+//
+// HBM-bound: algorithmic traffic = src_h*src_w*3 bytes in + out_h*out_w*3*sizeof(out) bytes out.
+#include "sia_host.cuh"
+#include "sia_ptx.cuh"
+
+namespace sia {
+
+constexpr int PRE_CONSUMERS = 224;                 // one output column each (7 warps)
+constexpr int PRE_THREADS = PRE_CONSUMERS + 32;    // + producer warp
+constexpr int PRE_RING = 3;
+constexpr int PRE_SLOTS = 4;
+
+struct PreParams {
+  const uint8_t* src;
+  const int32_t* x_off;
+  const float* x_w;
+  const float4* row_w;
+  const int4* row_emit;
+  const int32_t* y_first_last;
+  void* dst;
+  int batch, src_h, src_w, out_h, out_w;
+  int layout, rows_per_cta, rows_per_chunk, chunk_stride;  // chunk_stride: bytes between ring buffers
+  int bulk_ok;                                              // every chunk start is 16-byte aligned
+  float scale[3], bias[3];
+};
+
+template <int TX>
+__global__ void __launch_bounds__(PRE_THREADS)
+preprocess_kernel(const __grid_constant__ PreParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t full_bar[PRE_RING];
+  __shared__ uint64_t empty_bar[PRE_RING];
+
+  const int n = blockIdx.z;
+  const int i0 = blockIdx.x * p.rows_per_cta;
+  const int i1 = min(i0 + p.rows_per_cta, p.out_h);
+  const int row_bytes = p.src_w * 3;
+  const int r_lo = p.y_first_last[2 * i0];
+  const int r_hi = p.y_first_last[2 * (i1 - 1) + 1] + 1;  // exclusive
+  const int c_lo = r_lo / p.rows_per_chunk;
+  const int c_hi = (r_hi - 1) / p.rows_per_chunk;          // inclusive
+  const uint8_t* img = p.src + (size_t)n * p.src_h * row_bytes;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < PRE_RING; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], PRE_CONSUMERS / 32);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (threadIdx.x >= PRE_CONSUMERS) {
+    // ------------------------------ producer warp ------------------------------------------
+    const int lane = threadIdx.x - PRE_CONSUMERS;
+    int slot = 0;
+    uint32_t phase = 0;
+    for (int c = c_lo; c <= c_hi; ++c) {
+      const int row0 = c * p.rows_per_chunk;
+      const int rows = min(p.rows_per_chunk, p.src_h - row0);
+      const uint32_t bytes = (uint32_t)rows * row_bytes;
+      const uint8_t* g = img + (size_t)row0 * row_bytes;
+      uint8_t* s = smem + (size_t)slot * p.chunk_stride;
+      mbar_wait(&empty_bar[slot], phase ^ 1, 10);
+      if (p.bulk_ok) {
+        const uint32_t main_bytes = bytes & ~15u;
+        for (uint32_t b = main_bytes + lane; b < bytes; b += 32) s[b] = g[b];   // < 16 tail bytes
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive_expect_tx(&full_bar[slot], main_bytes);
+          if (main_bytes) bulk_load_1d(s, g, main_bytes, &full_bar[slot]);
+        }
+      } else {
+        // odd image sizes: plain byte copy by the producer warp (correct, not fast)
+        for (uint32_t b = lane; b < bytes; b += 32) s[b] = g[b];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[slot]);
+      }
+      if (++slot == PRE_RING) { slot = 0; phase ^= 1; }
+    }
+    return;
+  }
+
+  // -------------------------------- consumers ------------------------------------------------
+  const int x = blockIdx.y * PRE_CONSUMERS + threadIdx.x;
+  const bool active = x < p.out_w;
+  const int xc = active ? x : p.out_w - 1;
+  float xw[TX];
+#pragma unroll
+  for (int t = 0; t < TX; ++t) xw[t] = p.x_w[(size_t)xc * TX + t];
+  const int b0 = p.x_off[xc] * 3;
+
+  float acc[PRE_SLOTS][3];
+#pragma unroll
+  for (int s = 0; s < PRE_SLOTS; ++s) acc[s][0] = acc[s][1] = acc[s][2] = 0.f;
+
+  int slot = 0;
+  uint32_t phase = 0;
+  for (int c = c_lo; c <= c_hi; ++c) {
+    const int row0 = c * p.rows_per_chunk;
+    const int ra = max(row0, r_lo);
+    const int rb = min(min(row0 + p.rows_per_chunk, p.src_h), r_hi);
+    const uint8_t* cbuf = smem + (size_t)slot * p.chunk_stride;
+    mbar_wait(&full_bar[slot], phase, 11);
+    for (int r = ra; r < rb; ++r) {
+      // ---- horizontal pass over TX source pixels x 3 channels ------------------------------
+      const uint32_t a = smem_u32(cbuf) + (uint32_t)(r - row0) * row_bytes + b0;
+      const uint32_t a4 = a & ~3u;
+      const uint32_t sh = (a & 3u) * 8u;
+      constexpr int NW = (TX * 3 + 3) / 4;  // aligned words holding the window
+      uint32_t w[NW + 1];
+#pragma unroll
+      for (int k = 0; k <= NW; ++k) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[k]) : "r"(a4 + 4u * k));
+      float h0 = 0.f, h1 = 0.f, h2 = 0.f;
+#pragma unroll
+      for (int t = 0; t < TX; ++t) {
+        float v[3];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          const int j = t * 3 + ch;
+          const uint32_t q = __funnelshift_r(w[j / 4], w[j / 4 + 1], sh);
+          v[ch] = (float)((q >> (8 * (j % 4))) & 0xffu);
+        }
+        h0 = fmaf(xw[t], v[0], h0);
+        h1 = fmaf(xw[t], v[1], h1);
+        h2 = fmaf(xw[t], v[2], h2);
+      }
+      // ---- vertical pass: scatter into the output rows in flight ----------------------------
+      const float4 rw = p.row_w[r];
+      const int4 em = p.row_emit[r];
+      const float rws[PRE_SLOTS] = {rw.x, rw.y, rw.z, rw.w};
+      const int ems[PRE_SLOTS] = {em.x, em.y, em.z, em.w};
+#pragma unroll
+      for (int s = 0; s < PRE_SLOTS; ++s) {
+        acc[s][0] = fmaf(rws[s], h0, acc[s][0]);
+        acc[s][1] = fmaf(rws[s], h1, acc[s][1]);
+        acc[s][2] = fmaf(rws[s], h2, acc[s][2]);
+        const int e = ems[s];
+        if (e >= 0) {  // uniform across the CTA
+          if (e >= i0 && e < i1 && active) {
+            const float v0 = fmaf(acc[s][0], p.scale[0], p.bias[0]);
+            const float v1 = fmaf(acc[s][1], p.scale[1], p.bias[1]);
+            const float v2 = fmaf(acc[s][2], p.scale[2], p.bias[2]);
+            if (p.layout == SIA_LAYOUT_NHWC4_BF16) {
+              uint2 o;
+              o.x = pack_bf16x2(v0, v1);
+              o.y = pack_bf16x2(v2, 0.f);
+              reinterpret_cast<uint2*>(p.dst)[((size_t)n * p.out_h + e) * p.out_w + x] = o;
+            } else {
+              const size_t plane = (size_t)p.out_h * p.out_w;
+              const size_t o = (size_t)n * 3 * plane + (size_t)e * p.out_w + x;
+              if (p.layout == SIA_LAYOUT_NCHW_F32) {
+                float* d = reinterpret_cast<float*>(p.dst);
+                d[o] = v0; d[o + plane] = v1; d[o + 2 * plane] = v2;
+              } else {
+                __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.dst);
+                d[o] = __float2bfloat16_rn(v0);
+                d[o + plane] = __float2bfloat16_rn(v1);
+                d[o + 2 * plane] = __float2bfloat16_rn(v2);
+              }
+            }
+          }
+          acc[s][0] = acc[s][1] = acc[s][2] = 0.f;
+        }
+      }
+    }
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(&empty_bar[slot]);
+    if (++slot == PRE_RING) { slot = 0; phase ^= 1; }
+  }
+}
+
+}  // namespace sia
+
+extern "C" int sia_preprocess_u8hwc(const uint8_t* src, int batch, int src_h, int src_w, const int32_t* x_off,
+                                    const float* x_w, int x_taps, const float* row_w, const int32_t* row_emit,
+                                    const int32_t* y_first_last, int out_h, int out_w,
+                                    const float* out_scale_host, const float* out_bias_host, int layout,
+                                    int rows_per_cta, void* dst, void* stream) {
+  using namespace sia;
+  SIA_REQUIRE(src && x_off && x_w && row_w && row_emit && y_first_last && dst && out_scale_host && out_bias_host);
+  SIA_REQUIRE(batch >= 1 && src_h >= 1 && src_w >= 1 && out_h >= 1 && out_w >= 1 && rows_per_cta >= 1);
+  SIA_REQUIRE(layout >= SIA_LAYOUT_NCHW_F32 && layout <= SIA_LAYOUT_NHWC4_BF16);
+  SIA_REQUIRE(aligned(row_w, 16) && aligned(row_emit, 16) && aligned(dst, 16));
+  if (x_taps != 8 && x_taps != 16) return SIA_E_UNSUPPORTED;
+  if (batch > 65535) return SIA_E_UNSUPPORTED;
+
+  PreParams p;
+  p.src = src; p.x_off = x_off; p.x_w = x_w;
+  p.row_w = reinterpret_cast<const float4*>(row_w);
+  p.row_emit = reinterpret_cast<const int4*>(row_emit);
+  p.y_first_last = y_first_last;
+  p.dst = dst;
+  p.batch = batch; p.src_h = src_h; p.src_w = src_w; p.out_h = out_h; p.out_w = out_w;
+  p.layout = layout; p.rows_per_cta = rows_per_cta;
+  for (int c = 0; c < 3; ++c) { p.scale[c] = out_scale_host[c]; p.bias[c] = out_bias_host[c]; }
+
+  const long long row_bytes = (long long)src_w * 3;
+  // source rows per chunk: a multiple that keeps chunk starts 16-byte aligned, about 14 KB
+  int unit = 1;
+  while ((unit * row_bytes) % 16 != 0) ++unit;  // <= 16
+  int rows_per_chunk = unit;
+  while ((long long)(rows_per_chunk + unit) * row_bytes <= 16 * 1024) rows_per_chunk += unit;
+  if ((long long)rows_per_chunk * row_bytes > 64 * 1024) return SIA_E_UNSUPPORTED;
+  p.rows_per_chunk = rows_per_chunk;
+  p.chunk_stride = (int)(((long long)rows_per_chunk * row_bytes + 64 + 127) / 128 * 128);  // + over-read pad
+  p.bulk_ok = (aligned(src, 16) && ((long long)src_h * row_bytes) % 16 == 0) ? 1 : 0;
+
+  const int smem = PRE_RING * p.chunk_stride;
+  dim3 grid((out_h + rows_per_cta - 1) / rows_per_cta, (out_w + PRE_CONSUMERS - 1) / PRE_CONSUMERS, batch);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (x_taps == 8) {
+    static int configured = 0;
+    if (int rc2 = ensure_dynamic_smem(preprocess_kernel<8>, smem, &configured)) return rc2;
+    preprocess_kernel<8><<<grid, PRE_THREADS, smem, st>>>(p);
+  } else {
+    static int configured = 0;
+    if (int rc2 = ensure_dynamic_smem(preprocess_kernel<16>, smem, &configured)) return rc2;
+    preprocess_kernel<16><<<grid, PRE_THREADS, smem, st>>>(p);
+  }
+  return launch_status();
+}
+
+// ----------------------------------------------------------------------------------------------
+// Model-boundary layout change: NCHW fp32 [B,3,H,W] (what the reference DataLoader hands to
+// model(images), tone_bias_test.py:190-196) -> NHWC4 bf16 [B,H,W,4], the layout conv7x7_c3 reads.
+// ----------------------------------------------------------------------------------------------
+namespace sia {
+__global__ void nchw_f32_to_nhwc4_kernel(const float* __restrict__ src, uint2* __restrict__ dst, size_t pixels_per_image,
+                                         size_t total_pixels) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_pixels;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const size_t n = i / pixels_per_image, p = i % pixels_per_image;
+    const float* s = src + n * 3 * pixels_per_image + p;
+    uint2 o;
+    o.x = pack_bf16x2(s[0], s[pixels_per_image]);
+    o.y = pack_bf16x2(s[2 * pixels_per_image], 0.f);
+    dst[i] = o;
+  }
+}
+}  // namespace sia
+
+extern "C" int sia_nchw_f32_to_nhwc4_bf16(const float* src, int batch, int h, int w, void* dst, void* stream) {
+  using namespace sia;
+  SIA_REQUIRE(src && dst && batch >= 1 && h >= 1 && w >= 1 && aligned(dst, 8));
+  const size_t ppi = (size_t)h * w, total = ppi * batch;
+  size_t blocks = (total + 255) / 256;
+  const size_t cap = (size_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  nchw_f32_to_nhwc4_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, static_cast<uint2*>(dst), ppi, total);
+  return launch_status();
+}

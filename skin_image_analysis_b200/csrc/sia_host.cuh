@@ -1,0 +1,58 @@
+// Host-side helpers shared by the C-ABI entry points: error plumbing and TMA tensor-map encoding
+// (cuTensorMapEncodeTiled resolved at run time through the CUDA runtime, so the library has no
+// link-time dependency on libcuda and loads on a box without a driver).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/sia_b200.h"
+
+namespace sia {
+
+#define SIA_CUDA_OK(expr)                      \
+  do {                                         \
+    cudaError_t _e = (expr);                   \
+    if (_e != cudaSuccess) return (int)_e;     \
+  } while (0)
+
+#define SIA_REQUIRE(cond) \
+  do {                    \
+    if (!(cond)) return SIA_E_INVALID; \
+  } while (0)
+
+inline int launch_status() {
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+inline int sm_count() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) cached = 148;
+  }
+  return cached;
+}
+
+// Raises the dynamic shared-memory limit of a kernel once (per process, i.e. per GPU): keeps
+// cudaFuncSetAttribute out of CUDA-graph capture after the first, un-captured, warm-up launch.
+template <typename Kernel>
+inline int ensure_dynamic_smem(Kernel kern, int bytes, int* configured) {
+  if (*configured < bytes) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return (int)e;
+    *configured = bytes;
+  }
+  return 0;
+}
+
+// rank <= 5.  dims / box in elements (innermost first); strides in BYTES for dims 1..rank-1.
+int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle);
+
+}  // namespace sia

@@ -1,0 +1,246 @@
+"""Tensor-level wrappers over the C ABI (include/sia_b200.h).
+
+Every function takes / returns CUDA tensors, checks dtype / contiguity / device on the host and
+launches on the current torch stream.  PyTorch is used for allocation and streams only.
+"""
+from __future__ import annotations
+
+import ctypes
+from functools import lru_cache
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import resize_weights as _rw
+from ._lib import LAYOUT_NCHW_BF16, LAYOUT_NCHW_F32, LAYOUT_NHWC4_BF16, SiaError, check, ptr, stream_ptr
+
+__all__ = [
+    "preprocess_u8hwc", "nchw_f32_to_nhwc4", "pack_conv7x7_c3", "pack_conv3x3", "pack_linear_chw_to_hwc",
+    "conv7x7_c3_relu_pool2", "conv3x3_relu_pool2", "linear_splitk", "head_tail", "confusion_counts",
+    "umma_probe", "LAYOUT_NCHW_F32", "LAYOUT_NCHW_BF16", "LAYOUT_NHWC4_BF16",
+]
+
+
+def _need(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise SiaError(f"{name}: expected a CUDA tensor (there is no CPU fallback)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: expected a contiguous tensor")
+    return t
+
+
+# -------------------------------------------------------------------------------------------------
+# K1-K3 preprocess
+# -------------------------------------------------------------------------------------------------
+class _DeviceTables:
+    def __init__(self, t: _rw.ResizeTables, device):
+        self.host = t
+        self.x_off = torch.from_numpy(t.x_off).to(device)
+        self.x_w = torch.from_numpy(np.ascontiguousarray(t.x_w)).to(device)
+        self.row_w = torch.from_numpy(np.ascontiguousarray(t.row_w)).to(device)
+        self.row_emit = torch.from_numpy(np.ascontiguousarray(t.row_emit)).to(device)
+        self.y_first_last = torch.from_numpy(np.ascontiguousarray(t.y_first_last)).to(device)
+
+
+@lru_cache(maxsize=64)
+def _tables(device_index: int, src_h: int, src_w: int, out_h: int, out_w: int, scale: float, antialias):
+    t = _rw.build_tables(src_h, src_w, out_h, out_w, scale=scale, antialias=antialias)
+    return _DeviceTables(t, torch.device("cuda", device_index))
+
+
+_LAYOUT_DTYPE = {LAYOUT_NCHW_F32: torch.float32, LAYOUT_NCHW_BF16: torch.bfloat16, LAYOUT_NHWC4_BF16: torch.bfloat16}
+
+
+def preprocess_u8hwc(src: torch.Tensor, size, layout: int = LAYOUT_NCHW_F32, mean=(0.0, 0.0, 0.0),
+                     std=(1.0, 1.0, 1.0), scale: float = 1.0 / 255.0, antialias="skimage",
+                     rows_per_cta: int = 32, out: torch.Tensor | None = None) -> torch.Tensor:
+    """[B,H,W,3] uint8 -> resized / scaled / normalised batch in ``layout``.
+
+    Defaults reproduce the reference transform exactly: ``float32(u8)/255`` (tone_bias_dataset.py:335),
+    ``skimage.transform.resize`` (:425), no mean/std, CHW (:470).
+    """
+    _need(src, torch.uint8, "src")
+    if src.dim() != 4 or src.shape[3] != 3:
+        raise ValueError("src must be [B,H,W,3] uint8")
+    b, sh, sw, _ = src.shape
+    oh, ow = int(size[0]), int(size[1])
+    tab = _tables(src.device.index, sh, sw, oh, ow, float(scale), antialias)
+    shape = (b, oh, ow, 4) if layout == LAYOUT_NHWC4_BF16 else (b, 3, oh, ow)
+    if out is None:
+        out = torch.empty(shape, dtype=_LAYOUT_DTYPE[layout], device=src.device)
+    else:
+        _need(out, _LAYOUT_DTYPE[layout], "out")
+        if tuple(out.shape) != shape:
+            raise ValueError(f"out must have shape {shape}")
+    osc = (ctypes.c_float * 3)(*[1.0 / float(s) for s in std])
+    obi = (ctypes.c_float * 3)(*[-float(m) / float(s) for m, s in zip(mean, std)])
+    check(_lib.load().sia_preprocess_u8hwc(
+        ptr(src), b, sh, sw, ptr(tab.x_off), ptr(tab.x_w), tab.host.x_taps, ptr(tab.row_w), ptr(tab.row_emit),
+        ptr(tab.y_first_last), oh, ow, osc, obi, layout, int(rows_per_cta), ptr(out), stream_ptr()),
+        "sia_preprocess_u8hwc")
+    return out
+
+
+def nchw_f32_to_nhwc4(x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    _need(x, torch.float32, "x")
+    b, c, h, w = x.shape
+    if c != 3:
+        raise ValueError("expected [B,3,H,W]")
+    if out is None:
+        out = torch.empty((b, h, w, 4), dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().sia_nchw_f32_to_nhwc4_bf16(ptr(x), b, h, w, ptr(out), stream_ptr()), "sia_nchw_f32_to_nhwc4_bf16")
+    return out
+
+
+# -------------------------------------------------------------------------------------------------
+# weight packing
+# -------------------------------------------------------------------------------------------------
+def pack_conv7x7_c3(w: torch.Tensor) -> torch.Tensor:
+    _need(w, torch.float32, "w")
+    if tuple(w.shape) != (32, 3, 7, 7):
+        raise ValueError("conv1 weight must be [32,3,7,7]")
+    lib = _lib.load()
+    out = torch.empty(lib.sia_pack_conv7x7_c3_bytes(), dtype=torch.uint8, device=w.device)
+    check(lib.sia_pack_conv7x7_c3(ptr(w), ptr(out), stream_ptr()), "sia_pack_conv7x7_c3")
+    return out
+
+
+def pack_conv3x3(w: torch.Tensor) -> torch.Tensor:
+    _need(w, torch.float32, "w")
+    cout, cin, kh, kw = w.shape
+    if (kh, kw) != (3, 3):
+        raise ValueError("expected a 3x3 kernel")
+    lib = _lib.load()
+    out = torch.empty(lib.sia_pack_conv3x3_bytes(cin, cout), dtype=torch.uint8, device=w.device)
+    check(lib.sia_pack_conv3x3(ptr(w), cin, cout, ptr(out), stream_ptr()), "sia_pack_conv3x3")
+    return out
+
+
+def pack_linear_chw_to_hwc(w: torch.Tensor, c: int, hw: int) -> torch.Tensor:
+    _need(w, torch.float32, "w")
+    n, k = w.shape
+    if k != c * hw:
+        raise ValueError("in_features != c*hw")
+    out = torch.empty((n, k), dtype=torch.bfloat16, device=w.device)
+    check(_lib.load().sia_pack_linear_chw_to_hwc(ptr(w), n, c, hw, ptr(out), stream_ptr()), "sia_pack_linear_chw_to_hwc")
+    return out
+
+
+# -------------------------------------------------------------------------------------------------
+# K4 conv blocks
+# -------------------------------------------------------------------------------------------------
+def conv7x7_c3_relu_pool2(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor,
+                          out: torch.Tensor | None = None) -> torch.Tensor:
+    _need(x, torch.bfloat16, "x")
+    _need(w_packed, torch.uint8, "w_packed")
+    _need(bias, torch.float32, "bias")
+    b, h, w, c = x.shape
+    if c != 4:
+        raise ValueError("expected NHWC4 input")
+    if out is None:
+        out = torch.empty((b, h // 2, w // 2, 32), dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().sia_conv7x7_c3_relu_pool2(ptr(x), b, h, w, ptr(w_packed), ptr(bias), ptr(out), stream_ptr()),
+          "sia_conv7x7_c3_relu_pool2")
+    return out
+
+
+def conv3x3_relu_pool2(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, cout: int,
+                       out: torch.Tensor | None = None) -> torch.Tensor:
+    _need(x, torch.bfloat16, "x")
+    _need(w_packed, torch.uint8, "w_packed")
+    _need(bias, torch.float32, "bias")
+    b, h, w, cin = x.shape
+    if out is None:
+        out = torch.empty((b, h // 2, w // 2, cout), dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().sia_conv3x3_relu_pool2(ptr(x), b, h, w, cin, cout, ptr(w_packed), ptr(bias), ptr(out),
+                                             stream_ptr()), "sia_conv3x3_relu_pool2")
+    return out
+
+
+# -------------------------------------------------------------------------------------------------
+# K5 / K6 linear part
+# -------------------------------------------------------------------------------------------------
+def linear_splitk(a: torch.Tensor, w: torch.Tensor, splits: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    _need(a, torch.bfloat16, "a")
+    _need(w, torch.bfloat16, "w")
+    m, k = a.shape
+    n, k2 = w.shape
+    if k != k2:
+        raise ValueError("inner dimensions differ")
+    if out is None:
+        out = torch.empty((splits, m, n), dtype=torch.float32, device=a.device)
+    check(_lib.load().sia_linear_splitk(ptr(a), ptr(w), m, n, k, splits, ptr(out), stream_ptr()), "sia_linear_splitk")
+    return out
+
+
+def head_tail(partial, b1, w2t, b2, w3, b3, label=None, groups=None, n_groups: int = 0, counts=None,
+              logp=None, pred=None):
+    """Returns (logp [M,2] f32, pred [M] u8); accumulates into ``counts`` when given."""
+    _need(partial, torch.float32, "partial")
+    splits, m, n1 = partial.shape
+    n2 = w2t.shape[1]
+    for t, nm in ((b1, "b1"), (w2t, "w2t"), (b2, "b2"), (w3, "w3"), (b3, "b3")):
+        _need(t, torch.float32, nm)
+    if logp is None:
+        logp = torch.empty((m, 2), dtype=torch.float32, device=partial.device)
+    if pred is None:
+        pred = torch.empty((m,), dtype=torch.uint8, device=partial.device)
+    n_attr, stride = 0, 0
+    if counts is not None:
+        _need(counts, torch.int64, "counts")
+        _need(label, torch.uint8, "label")
+        _need(groups, torch.uint8, "groups")
+        n_attr, stride = groups.shape
+        if tuple(counts.shape) != (n_attr, n_groups, 2, 2):
+            raise ValueError("counts must be [n_attr, n_groups, 2, 2]")
+    check(_lib.load().sia_head_tail(ptr(partial), splits, m, n1, n2, ptr(b1), ptr(w2t), ptr(b2), ptr(w3), ptr(b3),
+                                    ptr(logp), ptr(pred), ptr(label), ptr(groups), stride, n_attr, n_groups,
+                                    ptr(counts), stream_ptr()), "sia_head_tail")
+    return logp, pred
+
+
+# -------------------------------------------------------------------------------------------------
+# K7 confusion counts
+# -------------------------------------------------------------------------------------------------
+def confusion_counts(pred: torch.Tensor, label: torch.Tensor, groups: torch.Tensor, n_groups: int,
+                     counts: torch.Tensor | None = None) -> torch.Tensor:
+    """counts[a][g][label][pred] (int64), accumulated into ``counts`` if given.
+
+    pred, label: uint8 [N] in {0,1} (1 = 'malignant'); groups: uint8 [A,N], values >= n_groups mean
+    "in no group of this attribute" (the reference's filter() semantics, tone_bias_test.py:283-289).
+    """
+    _need(pred, torch.uint8, "pred")
+    _need(label, torch.uint8, "label")
+    _need(groups, torch.uint8, "groups")
+    if groups.dim() != 2 or pred.dim() != 1 or label.shape != pred.shape or groups.shape[1] != pred.shape[0]:
+        raise ValueError("expected pred [N], label [N], groups [A,N]")
+    n_attr, n = groups.shape
+    if counts is None:
+        counts = torch.zeros((n_attr, n_groups, 2, 2), dtype=torch.int64, device=pred.device)
+    else:
+        _need(counts, torch.int64, "counts")
+        if tuple(counts.shape) != (n_attr, n_groups, 2, 2):
+            raise ValueError("counts must be [n_attr, n_groups, 2, 2]")
+    check(_lib.load().sia_confusion_counts(ptr(pred), ptr(label), ptr(groups), n, n, n_attr, n_groups, ptr(counts),
+                                           stream_ptr()), "sia_confusion_counts")
+    return counts
+
+
+# -------------------------------------------------------------------------------------------------
+# bring-up probe
+# -------------------------------------------------------------------------------------------------
+def umma_probe(image: torch.Tensor, a_descs, b_descs, n: int, repeat: int = 1, want_cycles: bool = False):
+    _need(image, torch.uint8, "image")
+    k = len(a_descs)
+    a = (ctypes.c_uint64 * k)(*[int(d) for d in a_descs])
+    b = (ctypes.c_uint64 * k)(*[int(d) for d in b_descs])
+    out = torch.zeros((128, n), dtype=torch.float32, device=image.device)
+    cyc = ctypes.c_longlong(0)
+    check(_lib.load().sia_debug_umma_probe(ptr(image), image.numel(), a, b, k, n, ptr(out), repeat,
+                                           ctypes.byref(cyc) if want_cycles else None, stream_ptr()),
+          "sia_debug_umma_probe")
+    torch.cuda.synchronize()
+    return (out, cyc.value) if want_cycles else out

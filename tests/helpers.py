@@ -81,21 +81,10 @@ def synthetic_batch_f32(batch: int, size: int, seed: int):
 
 
 def counter_metadata(index: np.ndarray, seed: int):
-    """Counter-based per-logical-index metadata: label, Fitzpatrick type,
-    sex, control as small ints from a splitmix64 hash of (seed, index) -- identical on every
-    rank and for any partition of the index space."""
-    x = (index.astype(np.uint64) + np.uint64(0x9E3779B97F4A7C15) * np.uint64(seed + 1))
-    with np.errstate(over="ignore"):
-        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
-        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
-        x = x ^ (x >> np.uint64(31))
-    label = (x & np.uint64(1)).astype(np.uint8)
-    u = ((x >> np.uint64(8)) & np.uint64(0xFFFF)).astype(np.float64) / 65536.0
-    cdf = np.cumsum([0.35, 0.45, 0.10, 0.05, 0.03, 0.02])
-    ftype = np.searchsorted(cdf, u, side="right").clip(0, 5).astype(np.uint8)
-    sex = ((x >> np.uint64(32)) & np.uint64(1)).astype(np.uint8)
-    control = ((x >> np.uint64(40)) & np.uint64(1)).astype(np.uint8)
-    return label, ftype, sex, control
+    """Counter-based per-logical-index metadata -- the recipe lives in the package so bench.py and
+    the tests share it (skin_image_analysis_b200/synthetic.py)."""
+    from skin_image_analysis_b200.synthetic import counter_metadata as _cm
+    return _cm(index, seed)
 
 
 def close(a, b, rel=1e-12):

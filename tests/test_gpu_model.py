@@ -1,0 +1,194 @@
+"""K4-K6 parity: conv / linear / tail kernels and the nn.Module drop-ins vs the fp32 oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import model as om
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+LOGP_TOL = 1e-2           # bf16 weights + activations, fp32 accumulate, vs the fp32 reference
+
+
+def _bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+def _ref_block(x_nchw, w, b):
+    """fp64 conv + bias + relu + pool on bf16-rounded inputs -> what the kernel should round to bf16."""
+    y = F.conv2d(x_nchw.double(), w.double(), b.double(), padding="same")
+    return F.max_pool2d(F.relu(y), 2).float()
+
+
+def _close_bf16(got, want, extra_atol=1e-3):
+    err = (got.float() - want).abs()
+    tol = want.abs() * 2.0 ** -7 + extra_atol
+    assert bool((err <= tol).all()), f"max err {err.max().item()} at {int(err.argmax())}"
+
+
+@pytest.mark.parametrize("batch,h,w", [(1, 16, 16), (2, 32, 48), (2, 224, 224)])
+def test_conv7x7_block(batch, h, w):
+    from skin_image_analysis_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(h * w)
+    x = _bf(torch.rand(batch, 3, h, w, device="cuda", generator=g))
+    wt = _bf(torch.randn(32, 3, 7, 7, device="cuda", generator=g) * 0.1)
+    b = torch.randn(32, device="cuda", generator=g) * 0.1
+    x4 = ops.nchw_f32_to_nhwc4(x)
+    assert torch.equal(x4[..., :3].float(), x.permute(0, 2, 3, 1)) and bool((x4[..., 3] == 0).all())
+    out = ops.conv7x7_c3_relu_pool2(x4, ops.pack_conv7x7_c3(wt), b)
+    assert out.shape == (batch, h // 2, w // 2, 32)
+    _close_bf16(out.permute(0, 3, 1, 2), _ref_block(x, wt, b))
+
+
+@pytest.mark.parametrize("cin,cout,batch,h,w", [(32, 64, 1, 16, 8), (32, 64, 2, 112, 112), (64, 128, 3, 56, 56),
+                                                (64, 128, 1, 30, 24), (32, 64, 1, 18, 40)])
+def test_conv3x3_block(cin, cout, batch, h, w):
+    from skin_image_analysis_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(cin + h)
+    x = _bf(torch.randn(batch, cin, h, w, device="cuda", generator=g))
+    wt = _bf(torch.randn(cout, cin, 3, 3, device="cuda", generator=g) * 0.05)
+    b = torch.randn(cout, device="cuda", generator=g) * 0.1
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+    out = ops.conv3x3_relu_pool2(x_nhwc, ops.pack_conv3x3(wt), b, cout)
+    assert out.shape == (batch, h // 2, w // 2, cout)
+    _close_bf16(out.permute(0, 3, 1, 2), _ref_block(x, wt, b), extra_atol=2e-3)
+
+
+@pytest.mark.parametrize("m,n,k,splits", [(128, 128, 64, 1), (256, 512, 6400, 5), (32, 512, 100352, 37),
+                                          (200, 256, 1280, 20)])
+def test_linear_splitk(m, n, k, splits):
+    from skin_image_analysis_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(m + k)
+    a = (torch.randn(m, k, device="cuda", generator=g)).to(torch.bfloat16)
+    w = (torch.randn(n, k, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+    part = ops.linear_splitk(a, w, splits)
+    got = part.sum(0)
+    want = a.double() @ w.double().t()
+    assert torch.allclose(got.double(), want, rtol=1e-4, atol=1e-2 * (k ** 0.5) * 0.05)
+
+
+def test_pack_linear_permutes_chw_to_hwc():
+    from skin_image_analysis_b200 import ops
+    w = torch.arange(4 * 3 * 5, dtype=torch.float32, device="cuda").view(4, 15)
+    p = ops.pack_linear_chw_to_hwc(w, 3, 5).float()
+    assert torch.equal(p.view(4, 5, 3), w.view(4, 3, 5).permute(0, 2, 1))
+
+
+def test_head_tail_matches_torch():
+    from skin_image_analysis_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(5)
+    m, s = 37, 6
+    part = torch.randn(s, m, 512, device="cuda", generator=g)
+    b1 = torch.randn(512, device="cuda", generator=g)
+    w2 = torch.randn(256, 512, device="cuda", generator=g) * 0.05
+    b2 = torch.randn(256, device="cuda", generator=g)
+    w3 = torch.randn(2, 256, device="cuda", generator=g) * 0.1
+    b3 = torch.randn(2, device="cuda", generator=g)
+    label = torch.randint(0, 2, (m,), device="cuda", dtype=torch.uint8)
+    groups = torch.randint(0, 7, (3, m), device="cuda", dtype=torch.uint8)
+    counts = torch.zeros((3, 6, 2, 2), dtype=torch.int64, device="cuda")
+    logp, pred = ops.head_tail(part, b1, w2.t().contiguous(), b2, w3, b3, label=label, groups=groups, n_groups=6,
+                               counts=counts)
+    h1 = F.relu(part.double().sum(0) + b1.double())
+    h2 = F.relu(h1 @ w2.double().t() + b2.double())
+    z = h2 @ w3.double().t() + b3.double()
+    want = F.log_softmax(z, 1)
+    assert torch.allclose(logp.double(), want, atol=1e-4, rtol=1e-4)
+    safe = (z[:, 1] - z[:, 0]).abs() > 1e-3
+    assert torch.equal(pred[safe].long(), torch.max(want, 1)[1][safe])
+    assert torch.equal(counts, ops.confusion_counts(pred, label, groups, 6))
+
+
+@pytest.mark.parametrize("kind", [om.LIST_MODEL])
+def test_module_forward_matches_reference_fixture(golden_dir, kind):
+    """Same weights + input as tests/golden/model_<kind>.npz (produced by the reference's own class)."""
+    from skin_image_analysis_b200 import tone_bias_model as tm
+    g = np.load(os.path.join(golden_dir, f"model_{kind}.npz"))
+    model = getattr(tm, kind)(helpers.CLASS_NAMES)
+    model.load_state_dict(om.synthetic_state_dict(kind, seed=7))
+    model = model.cuda().eval()
+    x = helpers.synthetic_batch_f32(4, 224, seed=21).cuda()
+    logp = model(x).cpu().numpy()
+    assert logp.shape == (4, 2)
+    assert np.abs(logp - g["logp"]).max() <= LOGP_TOL
+    margin = g["logp"][:, 1] - g["logp"][:, 0]
+    safe = np.abs(margin) > 2 * LOGP_TOL
+    assert np.array_equal(logp.argmax(1)[safe], g["pred"][safe])
+
+
+def test_module_surface_and_loud_failures():
+    from skin_image_analysis_b200 import tone_bias_model as tm
+    from skin_image_analysis_b200._lib import SiaError
+    m = tm.SkinCancerListModel(helpers.CLASS_NAMES)
+    assert list(m.state_dict().keys()) == list(om.param_shapes(om.LIST_MODEL).keys())
+    assert m.get_class_names() == helpers.CLASS_NAMES
+    m = m.cuda()
+    with pytest.raises(SiaError):
+        m(torch.rand(1, 3, 224, 224, device="cuda"))            # still in training mode
+    m.eval()
+    with pytest.raises(SiaError):
+        m(torch.rand(1, 3, 224, 224))                            # CPU tensor: no fallback
+    out = m(torch.rand(3, 3, 224, 224, device="cuda"))
+    assert out.shape == (3, 2) and torch.allclose(out.exp().sum(1), torch.ones(3, device="cuda"), atol=1e-5)
+
+
+def test_batch_32_vs_oracle_with_margin_rule():
+    """BASELINE configs[0] shape: batch 32; labels must agree wherever the fp32 margin exceeds 2*tol."""
+    from skin_image_analysis_b200 import tone_bias_model as tm
+    state = om.synthetic_state_dict(om.LIST_MODEL, seed=3)
+    x = helpers.synthetic_batch_f32(32, 224, seed=5)
+    ref = om.forward(om.LIST_MODEL, {k: v.cuda() for k, v in state.items()}, x.cuda()).cpu()
+    # centre the head so both classes occur, same shift on both sides
+    shift = float((ref[:, 1] - ref[:, 0]).median())
+    state["layers.16.bias"][1] -= shift
+    ref = om.forward(om.LIST_MODEL, {k: v.cuda() for k, v in state.items()}, x.cuda()).cpu()
+    model = tm.SkinCancerListModel(helpers.CLASS_NAMES)
+    model.load_state_dict(state)
+    got = model.cuda().eval()(x.cuda()).cpu()
+    assert (got - ref).abs().max().item() <= LOGP_TOL
+    margin = ref[:, 1] - ref[:, 0]
+    safe = margin.abs() > 2 * LOGP_TOL
+    assert torch.equal(got.argmax(1)[safe], ref.argmax(1)[safe])
+    assert 0 < int(ref.argmax(1).sum()) < 32
+
+
+def test_engine_end_to_end_counts_bit_exact_given_predictions():
+    """u8 images -> engine counts == oracle analysis of the engine's own predictions (the reduction is
+    bit-exact), and predictions == fp32 oracle wherever its margin exceeds the tolerance."""
+    from skin_image_analysis_b200.engine import EvalEngine
+    from skin_image_analysis_b200 import tone_bias_test as tt
+    from oracle import analysis as oa
+    from oracle import resize as R
+    batch = 8
+    state = om.synthetic_state_dict(om.LIST_MODEL, seed=11)
+    imgs = np.stack([helpers.synthetic_u8_image(450, 600, 300 + i, "smooth") for i in range(batch)])
+    x_ref = torch.from_numpy(np.stack([R.transform_u8(im, (224, 224)) for im in imgs]))
+    ref = om.forward(om.LIST_MODEL, {k: v.cuda() for k, v in state.items()}, x_ref.cuda()).cpu()
+    state["layers.16.bias"][1] -= float((ref[:, 1] - ref[:, 0]).median())
+    ref = om.forward(om.LIST_MODEL, {k: v.cuda() for k, v in state.items()}, x_ref.cuda()).cpu()
+    label, ftype, sex, control = helpers.counter_metadata(np.arange(batch), seed=1)
+    eng = EvalEngine(state, batch)
+    for use_graph_replays in range(2):
+        eng.reset_counts()
+        eng.step(torch.from_numpy(imgs).cuda(), torch.from_numpy(label).cuda(),
+                 torch.from_numpy(np.stack([ftype, sex, control])).cuda(), slot=use_graph_replays)
+        counts = eng.read_counts()
+        logp, pred = eng.logp.cpu(), eng.pred.cpu().numpy()
+        assert (logp - ref).abs().max().item() <= LOGP_TOL
+        safe = (ref[:, 1] - ref[:, 0]).abs() > 2 * LOGP_TOL
+        assert np.array_equal(pred[safe.numpy()], ref.argmax(1).numpy()[safe.numpy()])
+        inst = {}
+        for i in range(batch):
+            t = helpers.FITZPATRICK[ftype[i]]
+            inst[i] = {"benign_malignant": helpers.CLASS_NAMES[label[i]], "prediction": helpers.CLASS_NAMES[pred[i]],
+                       "skin_type": t, "skin_tone": "light" if t in ("I", "II") else "dark",
+                       "sex": ["male", "female"][sex[i]], "control": ["rich", "poor"][control[i]], "age": 50.0}
+        tab = oa.counts_table(inst, {"skin_type": helpers.FITZPATRICK, "sex": ["male", "female"],
+                                     "control": ["rich", "poor"]})
+        assert counts[0].tolist() == tab["skin_type"]
+        assert counts[1, :2].tolist() == tab["sex"] and counts[2, :2].tolist() == tab["control"]
+        assert int(counts[0].sum()) == batch

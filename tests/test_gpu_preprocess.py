@@ -1,0 +1,96 @@
+"""K1-K3 parity: sia_preprocess_u8hwc vs the oracle transform (and the reference-generated fixtures)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import resize as R
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+F32_TOL = 1e-6          # fp32 output vs the oracle's fp64-accumulate result
+
+
+def _gpu(u8_list, size, layout, **kw):
+    from skin_image_analysis_b200 import ops
+    x = torch.from_numpy(np.stack(u8_list)).cuda()
+    return ops.preprocess_u8hwc(x, size, layout, **kw)
+
+
+@pytest.mark.parametrize("kind", ["noise", "smooth", "extremes"])
+def test_f32_nchw_matches_oracle_224(kind):
+    from skin_image_analysis_b200 import ops
+    imgs = [helpers.synthetic_u8_image(450, 600, 100 + i, kind) for i in range(3)]
+    got = _gpu(imgs, (224, 224), ops.LAYOUT_NCHW_F32).cpu().numpy()
+    for i, im in enumerate(imgs):
+        want = R.transform_u8(im, (224, 224))
+        assert got[i].shape == want.shape
+        assert np.abs(got[i] - want).max() <= F32_TOL
+
+
+def test_reference_fixture_cases(golden_dir):
+    """The same cases the reference's Rescale+ToTensor produced in tests/golden/transform.npz."""
+    from skin_image_analysis_b200 import ops
+    from skin_image_analysis_b200.resize_weights import rescale_size
+    g = np.load(os.path.join(golden_dir, "transform.npz"))
+    cases = [("noise_450x600_224", 450, 600, 31, "noise", (224, 224)),
+             ("noise_450x600_512", 450, 600, 34, "noise", (512, 512)),
+             ("noise_97x131_int64", 97, 131, 35, "noise", 64),
+             ("noise_131x97_int48", 131, 97, 36, "noise", 48)]
+    for name, h, w, seed, kind, size in cases:
+        u8 = helpers.synthetic_u8_image(h, w, seed, kind)
+        oh, ow = rescale_size(h, w, size)
+        got = _gpu([u8], (oh, ow), ops.LAYOUT_NCHW_F32)[0].cpu().numpy()
+        assert tuple(g[name + "_shape"]) == got.shape
+        ref = g[name + "_full"] if name + "_full" in g else g[name + "_sub"]
+        sub = got if name + "_full" in g else got[:, ::7, ::5]
+        assert np.abs(sub - ref).max() <= F32_TOL, name
+
+
+def test_bf16_layouts_within_one_ulp():
+    from skin_image_analysis_b200 import ops
+    imgs = [helpers.synthetic_u8_image(450, 600, 200 + i, "smooth") for i in range(2)]
+    want = np.stack([R.transform_u8(im, (224, 224)) for im in imgs])
+    want_bf = torch.from_numpy(want).to(torch.bfloat16).float().numpy()
+    nchw = _gpu(imgs, (224, 224), ops.LAYOUT_NCHW_BF16).float().cpu().numpy()
+    nhwc4 = _gpu(imgs, (224, 224), ops.LAYOUT_NHWC4_BF16).float().cpu().numpy()
+    assert nhwc4.shape == (2, 224, 224, 4) and np.all(nhwc4[..., 3] == 0)
+    assert np.array_equal(nhwc4[..., :3].transpose(0, 3, 1, 2), nchw)
+    ulp = np.maximum(np.abs(want_bf), 2.0 ** -126) * 2.0 ** -7
+    assert np.all(np.abs(nchw - want_bf) <= ulp)
+    assert (nchw != want_bf).mean() < 0.01          # the fp32 math differs from fp64 only near ties
+
+
+def test_mean_std_and_rows_per_cta_invariance():
+    from skin_image_analysis_b200 import ops
+    im = helpers.synthetic_u8_image(450, 600, 7, "noise")
+    base = _gpu([im], (224, 224), ops.LAYOUT_NCHW_F32)[0]
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    norm = _gpu([im], (224, 224), ops.LAYOUT_NCHW_F32, mean=mean, std=std)[0]
+    m = torch.tensor(mean, device="cuda").view(3, 1, 1)
+    s = torch.tensor(std, device="cuda").view(3, 1, 1)
+    assert torch.allclose(norm, (base - m) / s, atol=2e-6, rtol=0)
+    for rows in (1, 7, 16, 224):
+        assert torch.equal(_gpu([im], (224, 224), ops.LAYOUT_NCHW_F32, rows_per_cta=rows)[0], base)
+
+
+def test_constant_image_and_batch_independence():
+    from skin_image_analysis_b200 import ops
+    const = np.full((450, 600, 3), 200, np.uint8)
+    noise = helpers.synthetic_u8_image(450, 600, 9, "noise")
+    out = _gpu([const, noise, const], (224, 224), ops.LAYOUT_NCHW_F32)
+    assert np.abs(out[0].cpu().numpy() - np.float32(200 / 255.0)).max() <= 2e-7
+    assert torch.equal(out[0], out[2])
+    assert torch.equal(out[1], _gpu([noise], (224, 224), ops.LAYOUT_NCHW_F32)[0])
+
+
+def test_rescale_dropin_tuple_semantics():
+    from skin_image_analysis_b200.tone_bias_dataset import Rescale, ToTensor
+    u8 = helpers.synthetic_u8_image(97, 131, 35, "noise")
+    sample = (np.float32(u8) / 255.0, 1, 42)
+    img, label, idx = Rescale(64)(sample)
+    assert (label, idx) == (1, 42) and img.shape == (64, 86, 3) and img.dtype == np.float32
+    t, _, _ = ToTensor()((img, label, idx))
+    assert np.abs(t.numpy() - R.transform_u8(u8, 64)).max() <= F32_TOL

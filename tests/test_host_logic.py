@@ -1,0 +1,152 @@
+"""CPU-side checks of the product's host logic: the C-ABI library loads and exports every symbol of
+include/sia_b200.h, the banded resize tables equal the oracle's operator, the count -> metrics
+arithmetic equals the oracle / reference fixtures, and the product path refuses to run without CUDA."""
+import contextlib
+import io
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import analysis as oa
+from oracle import resize as R
+from tests import helpers
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from skin_image_analysis_b200 import _lib, build
+    build.build()
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "sia_b200.h")).read()
+    declared = set(re.findall(r"\b(sia_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in sia_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.sia_version() == 100
+    assert lib.sia_error_string(-2).decode().startswith("sia:")
+    assert lib.sia_pack_conv7x7_c3_bytes() == 64 * 224 * 2
+    assert lib.sia_pack_conv3x3_bytes(64, 128) == 9 * 64 * 128 * 2
+
+
+@pytest.mark.parametrize("shape", [(450, 600, 224, 224), (450, 600, 512, 512), (97, 131, 64, 86), (600, 450, 298, 224)])
+def test_resize_tables_equal_oracle_operator(shape):
+    from skin_image_analysis_b200 import resize_weights as rw
+    h, w, oh, ow = shape
+    t = rw.build_tables(h, w, oh, ow, keep_dense=True)
+    aa = oh < h or ow < w
+    assert np.abs(t.wy_dense - R.axis_weight_matrix(h, oh, aa)).max() < 1e-15
+    assert np.abs(t.wx_dense - R.axis_weight_matrix(w, ow, aa)).max() < 1e-7     # x_w is stored as float32
+    assert t.x_taps in (8, 16) and np.all(t.x_off >= 0) and np.all(t.x_off + t.x_taps <= w)
+    # every output row is emitted exactly once, after its last contributing source row
+    emitted = t.row_emit[t.row_emit >= 0]
+    assert sorted(emitted.tolist()) == list(range(oh))
+    for r in range(h):
+        for s in range(4):
+            e = t.row_emit[r, s]
+            if e >= 0:
+                assert t.y_first_last[e, 1] == r and e % 4 == s
+    # emulate the kernel's slot schedule on a random column
+    col = np.random.default_rng(0).random(h)
+    acc, out = np.zeros(4), np.zeros(oh)
+    for r in range(h):
+        for s in range(4):
+            acc[s] += float(t.row_w[r, s]) * col[r]
+            if t.row_emit[r, s] >= 0:
+                out[t.row_emit[r, s]] = acc[s]
+                acc[s] = 0.0
+    assert np.abs(out * 255.0 - R.axis_weight_matrix(h, oh, aa) @ col).max() < 1e-6
+
+
+def test_resize_tables_reject_unsupported_geometry():
+    from skin_image_analysis_b200 import resize_weights as rw
+    with pytest.raises(ValueError):
+        rw.build_tables(2000, 2000, 100, 100)          # 20x shrink: window far beyond 16 taps
+    with pytest.raises(ValueError):
+        rw.build_tables(4, 4, 8, 8)                    # narrower than the 8-tap window
+    assert rw.rescale_size(450, 600, 224) == (224, 298)
+
+
+@pytest.mark.parametrize("case", ["n500", "n64", "n1087"])
+def test_results_from_counts_equals_reference_fixture(golden_dir, case):
+    """Counts built on the CPU by the oracle -> product host arithmetic -> the reference's exact dict+stdout."""
+    from skin_image_analysis_b200 import tone_bias_test as tt
+    with open(os.path.join(golden_dir, "analysis_synth.json")) as f:
+        g = json.load(f)[case]
+    inst = helpers.synthetic_instances(g["n"], g["seed"], g["with_oddities"])
+    keys, pred, label, groups = tt.encode_instances(inst)
+    counts = np.zeros((len(tt.ATTRIBUTES), tt.N_GROUPS, 2, 2), np.int64)
+    for a in range(groups.shape[0]):
+        ok = groups[a] < tt.N_GROUPS
+        np.add.at(counts, (a, groups[a][ok], label[ok], pred[ok]), 1)
+    tab = oa.counts_table(inst, {"skin_tone": ["light", "dark"], "sex": ["male", "female"]})
+    assert counts[0, :2].tolist() == tab["skin_tone"] and counts[1, :2].tolist() == tab["sex"]
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        res = tt.results_from_counts(counts)
+    assert json.loads(json.dumps(res)) == g["result"]
+    assert buf.getvalue() == g["stdout"]
+    # the compact [3][6][2][2] tensor of the sharded engine maps to the same result
+    compact = np.stack([counts[3], counts[1], counts[2]])
+    res2 = tt.results_from_type_counts(compact, out=lambda *a: None)
+    assert json.loads(json.dumps(res2)) == g["result"]
+
+
+def test_notebook_known_answer_through_product_arithmetic(golden_dir):
+    from skin_image_analysis_b200 import tone_bias_test as tt
+    with open(os.path.join(golden_dir, "notebook_di.json")) as f:
+        nb = json.load(f)
+    for attr in ("tone", "sex"):
+        c = nb[attr]["cells"]
+        mn = [[c["tn_min"], c["fp_min"]], [c["fn_min"], c["tp_min"]]]
+        mj = [[c["tn_maj"], c["fp_maj"]], [c["fn_maj"], c["tp_maj"]]]
+        r = tt.di_from_tables(mn, mj)
+        assert r == oa.di_from_cells(c["tp_min"], c["tn_min"], c["fp_min"], c["fn_min"],
+                                     c["tp_maj"], c["tn_maj"], c["fp_maj"], c["fn_maj"])
+        assert f"{r['di']:.3f}" == f"{nb[attr]['printed']['di']:.3f}"
+        assert list(r.keys()) == list(tt.DI_KEYS) and len(r) == 27
+
+
+def test_model_drop_in_surface_on_cpu():
+    """Construction, state_dict compatibility and save/load work anywhere; forward needs the GPU."""
+    from oracle import model as om
+    from skin_image_analysis_b200 import jgi_hiba_2022_model as hm
+    from skin_image_analysis_b200 import tone_bias_model as tm
+    from skin_image_analysis_b200._lib import SiaError
+    for kind, cls in ((om.LIST_MODEL, tm.SkinCancerListModel), (om.FOUR_CONV_MODEL, hm.SkinCancerModel)):
+        m = cls(helpers.CLASS_NAMES)
+        shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        assert shapes == om.param_shapes(kind)
+        assert m.get_class_names() == helpers.CLASS_NAMES
+    assert isinstance(tm.create_model(helpers.CLASS_NAMES), tm.SkinCancerModel)
+    assert isinstance(tm.create_loss_function(), torch.nn.NLLLoss)
+    m = tm.SkinCancerListModel(helpers.CLASS_NAMES).eval()
+    if not torch.cuda.is_available():
+        with pytest.raises(SiaError):
+            m(torch.rand(1, 3, 224, 224))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "skin_image_analysis_b200")
+    for dirpath, _d, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert "import oracle" not in src and "from oracle" not in src, fn
+
+
+def test_no_cuda_no_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from skin_image_analysis_b200 import tone_bias_test as tt
+    from skin_image_analysis_b200._lib import SiaError
+    from skin_image_analysis_b200.tone_bias_dataset import Rescale
+    with pytest.raises(SiaError):
+        tt.analyse_predictions(helpers.synthetic_instances(10, 1, False))
+    with pytest.raises(SiaError):
+        Rescale((8, 8))((np.zeros((16, 16, 3), np.float32), 0, 0))

@@ -66,7 +66,7 @@ def test_constant_image_is_a_fixed_point():
 def test_weight_matrix_composition_matches():
     img = R.u8_to_unit_float(helpers.synthetic_u8_image(450, 600, 8, "noise")).astype(np.float64)
     wy, wx = R.axis_weight_matrix(450, 224, True), R.axis_weight_matrix(600, 224, True)
-    comp = np.einsum("ih,hwc,jw->ijc", wy, img, wx)
+    comp = np.einsum("jw,iwc->ijc", wx, np.tensordot(wy, img, axes=(1, 0)), optimize=True)
     np.testing.assert_allclose(comp, R.resize(img.astype(np.float32), (224, 224)), rtol=0, atol=2e-7)
     np.testing.assert_allclose(wy.sum(1), 1.0, atol=1e-12)
     assert (np.abs(wy) > 0).sum(1).max() == 6 and (np.abs(wx) > 0).sum(1).max() == 8

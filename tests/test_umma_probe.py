@@ -1,0 +1,235 @@
+"""Hardware bring-up of the tcgen05 descriptor conventions the conv / linear kernels rely on.
+
+Each experiment writes a shared-memory image exactly as TMA (or the weight packer) would, issues
+tcgen05.mma through ``sia_debug_umma_probe`` and compares the 128 x N accumulator with numpy.
+Inputs are small integers, so the fp32 result is exact and the comparison is ``==``.
+
+REQUIRED experiments are the layouts the shipped kernels use; the others are exploratory (future
+single-halo-copy conv design) and only recorded in gpurun_out/probe_report.json.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+SW_NONE, SW_128, SW_64 = 0, 2, 4
+
+
+def desc(addr, lbo, sbo, layout, base_offset=0):
+    return ((addr >> 4) & 0x3FFF) | (((lbo >> 4) & 0x3FFF) << 16) | (((sbo >> 4) & 0x3FFF) << 32) | (1 << 46) \
+        | ((base_offset & 7) << 49) | ((layout & 7) << 61)
+
+
+def bf16_bits(a):
+    return torch.from_numpy(np.asarray(a, np.float32)).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+
+
+def rand_int(rng, shape, lo=-3, hi=4):
+    return rng.integers(lo, hi, shape).astype(np.float32)
+
+
+class Image:
+    def __init__(self, nbytes):
+        self.buf = np.zeros(nbytes // 2, np.uint16)
+
+    def put_rows_swizzled(self, base, mat, row_bytes, first_row=0):
+        """mat [R, row_bytes/2]: row r goes to smem row (first_row + r); 16-byte units XOR-swizzled by the
+        ABSOLUTE smem row index, as TMA SWIZZLE_128B / 64B writes them (base aligned to 1024)."""
+        bits = bf16_bits(mat)
+        units = row_bytes // 16
+        for r in range(mat.shape[0]):
+            row = first_row + r
+            x = (row % 8) if row_bytes == 128 else ((row >> 1) & 3)
+            for u in range(units):
+                dst = (base + row * row_bytes + ((u ^ x) * 16)) // 2
+                self.buf[dst:dst + 8] = bits[r, u * 8:(u + 1) * 8]
+
+    def put_core_matrices(self, base, mat, lbo, sbo):
+        """no-swizzle K-major: (r,k) at (r//8)*sbo + (k//8)*lbo + (r%8)*16 + (k%8)*2."""
+        bits = bf16_bits(mat)
+        for r in range(mat.shape[0]):
+            for kc in range(mat.shape[1] // 8):
+                dst = (base + (r // 8) * sbo + kc * lbo + (r % 8) * 16) // 2
+                self.buf[dst:dst + 8] = bits[r, kc * 8:(kc + 1) * 8]
+
+    def put_raw(self, base, mat):
+        bits = bf16_bits(mat).reshape(-1)
+        self.buf[base // 2: base // 2 + bits.size] = bits
+
+    def tensor(self):
+        return torch.from_numpy(self.buf.view(np.uint8).copy()).cuda()
+
+
+def run(img, a_descs, b_descs, n):
+    from skin_image_analysis_b200 import ops
+    return ops.umma_probe(img.tensor(), a_descs, b_descs, n).cpu().numpy()
+
+
+REPORT = {}
+
+
+def record(name, ok, required, extra=None):
+    REPORT[name] = {"ok": bool(ok), "required": required, **(extra or {})}
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/probe_report.json", "w") as f:
+        json.dump(REPORT, f, indent=1, sort_keys=True)
+
+
+@pytest.mark.parametrize("n", [64, 128, 256, 32])
+def test_sw128_canonical(n):
+    rng = np.random.default_rng(n)
+    a, b = rand_int(rng, (128, 64)), rand_int(rng, (n, 64))
+    img = Image(16384 + n * 128)
+    img.put_rows_swizzled(0, a, 128)
+    img.put_rows_swizzled(16384, b, 128)
+    ad = [desc(kk * 32, 0, 1024, SW_128) for kk in range(4)]
+    bd = [desc(16384 + kk * 32, 0, 1024, SW_128) for kk in range(4)]
+    got = run(img, ad, bd, n)
+    ok = np.array_equal(got, a @ b.T)
+    record(f"sw128_canonical_n{n}", ok, True, {"maxerr": float(np.abs(got - a @ b.T).max())})
+    assert ok
+
+
+def test_sw64_canonical():
+    rng = np.random.default_rng(1)
+    a, b = rand_int(rng, (128, 32)), rand_int(rng, (64, 32))
+    img = Image(8192 + 4096)
+    img.put_rows_swizzled(0, a, 64)
+    img.put_rows_swizzled(8192, b, 64)
+    ad = [desc(kk * 32, 0, 512, SW_64) for kk in range(2)]
+    bd = [desc(8192 + kk * 32, 0, 512, SW_64) for kk in range(2)]
+    got = run(img, ad, bd, 64)
+    ok = np.array_equal(got, a @ b.T)
+    record("sw64_canonical", ok, True, {"maxerr": float(np.abs(got - a @ b.T).max())})
+    assert ok
+
+
+@pytest.mark.parametrize("r", [1, 2])
+def test_swizzled_vertical_tap_shift(r):
+    """conv3x3: the halo buffer is 144 smem rows; tap r starts r*8 rows (whole atoms) further."""
+    rng = np.random.default_rng(10 + r)
+    halo, b = rand_int(rng, (144, 64)), rand_int(rng, (128, 64))
+    img = Image(18432 + 16384)
+    img.put_rows_swizzled(0, halo, 128)
+    img.put_rows_swizzled(18432, b, 128)
+    ad = [desc(r * 1024 + kk * 32, 0, 1024, SW_128) for kk in range(4)]
+    bd = [desc(18432 + kk * 32, 0, 1024, SW_128) for kk in range(4)]
+    got = run(img, ad, bd, 128)
+    want = halo[r * 8: r * 8 + 128] @ b.T
+    ok = np.array_equal(got, want)
+    record(f"sw128_tap_shift_r{r}", ok, True)
+    # the same for 64-byte rows (conv 32 -> 64)
+    halo, b = rand_int(rng, (144, 32)), rand_int(rng, (64, 32))
+    img = Image(9216 + 4096)
+    img.put_rows_swizzled(0, halo, 64)
+    img.put_rows_swizzled(9216, b, 64)
+    ad = [desc(r * 512 + kk * 32, 0, 512, SW_64) for kk in range(2)]
+    bd = [desc(9216 + kk * 32, 0, 512, SW_64) for kk in range(2)]
+    got2 = run(img, ad, bd, 64)
+    ok2 = np.array_equal(got2, halo[r * 8: r * 8 + 128] @ b.T)
+    record(f"sw64_tap_shift_r{r}", ok2, True)
+    assert ok and ok2
+
+
+def test_noswizzle_canonical_and_field_meaning():
+    """K = 32 (4 chunks of 8): which of LBO / SBO is the K-direction stride?  conv1's B operand assumes
+    LBO = K-adjacent core matrices, SBO = next 8 rows."""
+    rng = np.random.default_rng(3)
+    a, b = rand_int(rng, (128, 32)), rand_int(rng, (64, 32))
+    res = {}
+    for name, (k_stride_field) in (("lbo_is_k", "lbo"), ("sbo_is_k", "sbo")):
+        img = Image(8192 + 4096)
+        # physical layout: chunks along K contiguous (128 B apart), 8-row groups 512 B apart
+        img.put_core_matrices(0, a, 128, 512)
+        img.put_core_matrices(8192, b, 128, 512)
+        if k_stride_field == "lbo":
+            mk = lambda addr: desc(addr, 128, 512, SW_NONE)          # noqa: E731
+        else:
+            mk = lambda addr: desc(addr, 512, 128, SW_NONE)          # noqa: E731
+        ad = [mk(kk * 256) for kk in range(2)]
+        bd = [mk(8192 + kk * 256) for kk in range(2)]
+        got = run(img, ad, bd, 64)
+        res[name] = bool(np.array_equal(got, a @ b.T))
+    record("nosw_lbo_is_k", res["lbo_is_k"], True, res)
+    assert res["lbo_is_k"], res
+
+
+def test_noswizzle_overlapping_windows_conv1():
+    """conv1: A rows are pixel PAIRS 16 B apart in a raw [22][192 B] image patch, K-adjacent core matrix
+    = next two pixels (LBO 16 B), next 8 rows = next image row (SBO 192 B).  All 14 UMMAs of a tile."""
+    rng = np.random.default_rng(4)
+    patch = rand_int(rng, (22, 96))                # 24 px * 4 ch per row
+    bmat = rand_int(rng, (64, 224))
+    a_bytes = 4352
+    img = Image(a_bytes + 28672)
+    img.put_raw(0, patch)
+    img.put_core_matrices(a_bytes, bmat, 128, 3584)
+    ad, bd = [], []
+    for r in range(7):
+        for kk in range(2):
+            ad.append(desc(r * 192 + kk * 32, 16, 192, SW_NONE))
+            bd.append(desc(a_bytes + (r * 4 + kk * 2) * 128, 128, 3584, SW_NONE))
+    got = run(img, ad, bd, 64)
+    # expected: A[m = y*8 + xp][r*32 + j] = patch[y + r][xp*8 + j]
+    a = np.zeros((128, 224), np.float32)
+    for y in range(16):
+        for xp in range(8):
+            for r in range(7):
+                a[y * 8 + xp, r * 32:(r + 1) * 32] = patch[y + r, xp * 8: xp * 8 + 32]
+    ok = np.array_equal(got, a @ bmat.T)
+    record("nosw_overlap_conv1", ok, True, {"maxerr": float(np.abs(got - a @ bmat.T).max())})
+    assert ok
+
+
+def test_exploratory_row_shifts_inside_swizzle_atoms():
+    """Not used by shipped kernels: start addresses shifted by single 128 B rows (an x tap shift on one
+    halo copy) and 8-row groups that are not 1024-byte multiples apart.  Recorded, not asserted."""
+    rng = np.random.default_rng(5)
+    halo, b = rand_int(rng, (200, 64)), rand_int(rng, (128, 64))
+    img = Image(25600 + 16384)
+    img.put_rows_swizzled(0, halo, 128)
+    img.put_rows_swizzled(25600, b, 128)
+    bd = [desc(25600 + kk * 32, 0, 1024, SW_128) for kk in range(4)]
+    for s in (1, 2, 3):
+        for bo in sorted({0, s}):
+            ad = [desc(s * 128 + kk * 32, 0, 1024, SW_128, bo) for kk in range(4)]
+            got = run(img, ad, bd, 128)
+            ok = np.array_equal(got, halo[s: s + 128] @ b.T)
+            record(f"explore_sw128_rowshift{s}_baseoff{bo}", ok, False)
+    # groups 10 rows apart (a [18][10]-pixel halo tile): row m -> smem row (m//8)*10 + m%8 + shift
+    for shift in (0, 1, 11):
+        idx = np.array([(m // 8) * 10 + m % 8 + shift for m in range(128)])
+        for bo in sorted({0, shift % 8}):
+            ad = [desc(shift * 128 + kk * 32, 0, 1280, SW_128, bo) for kk in range(4)]
+            got = run(img, ad, bd, 128)
+            ok = np.array_equal(got, halo[idx] @ b.T)
+            record(f"explore_sw128_sbo1280_shift{shift}_baseoff{bo}", ok, False)
+
+
+def test_exploratory_issue_rate():
+    """SM-clock cycles per UMMA (M=128, K=16) for the operand layouts in use -- recorded only."""
+    from skin_image_analysis_b200 import ops
+    rng = np.random.default_rng(6)
+    out = {}
+    for n in (32, 64, 128, 256):
+        a, b = rand_int(rng, (128, 64)), rand_int(rng, (n, 64))
+        img = Image(16384 + n * 128)
+        img.put_rows_swizzled(0, a, 128)
+        img.put_rows_swizzled(16384, b, 128)
+        ad = [desc(kk * 32, 0, 1024, SW_128) for kk in range(4)] * 8
+        bd = [desc(16384 + kk * 32, 0, 1024, SW_128) for kk in range(4)] * 8
+        _, cyc = ops.umma_probe(img.tensor(), ad, bd, n, repeat=64, want_cycles=True)
+        out[f"sw128_n{n}_cycles_per_mma"] = cyc / (64 * 32)
+    patch, bmat = rand_int(rng, (22, 96)), rand_int(rng, (64, 224))
+    img = Image(4352 + 28672)
+    img.put_raw(0, patch)
+    img.put_core_matrices(4352, bmat, 128, 3584)
+    ad = [desc(r * 192 + kk * 32, 16, 192, SW_NONE) for r in range(7) for kk in range(2)]
+    bd = [desc(4352 + (r * 4 + kk * 2) * 128, 128, 3584, SW_NONE) for r in range(7) for kk in range(2)]
+    _, cyc = ops.umma_probe(img.tensor(), ad, bd, 64, repeat=128, want_cycles=True)
+    out["conv1_nosw_n64_cycles_per_mma"] = cyc / (128 * 14)
+    record("issue_rate", True, False, out)
