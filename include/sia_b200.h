@@ -44,7 +44,10 @@ extern "C" {
 /* Output layouts of sia_preprocess_u8hwc */
 #define SIA_LAYOUT_NCHW_F32 0   /* [B,3,S,S] float32  -- what ToTensor + default collate produce        */
 #define SIA_LAYOUT_NCHW_BF16 1  /* [B,3,S,S] bfloat16                                                    */
-#define SIA_LAYOUT_NHWC4_BF16 2 /* [B,S,S,4] bfloat16, channel 3 = 0 -- the layout conv7x7_c3 consumes   */
+#define SIA_LAYOUT_NHWC4_BF16 2 /* [B,S,S+8,4] bfloat16 -- the layout conv7x7_c3 consumes: channel 3 = 0,  */
+                                /* image pixel x in column x+1, columns 0 and S+1..S+7 zero (the 8-byte  */
+                                /* shift makes every TMA window start 16-byte aligned)                   */
+#define SIA_NHWC4_PAD 8         /* extra pixels per row of the NHWC4 layout                              */
 
 int sia_version(void);
 const char* sia_error_string(int code);
@@ -74,7 +77,7 @@ int sia_preprocess_u8hwc(const uint8_t* src, int batch, int src_h, int src_w, co
                          const float* out_bias_host, int layout, int rows_per_cta, void* dst, void* stream);
 
 /* Model boundary: NCHW fp32 [B,3,h,w] (the tensor the reference DataLoader feeds to model(images),
- * src/tone_bias_test.py:190-196) -> NHWC4 bf16 [B,h,w,4] (channel 3 = 0), the conv7x7_c3 input. */
+ * src/tone_bias_test.py:190-196) -> padded NHWC4 bf16 [B,h,w+8,4] (SIA_LAYOUT_NHWC4_BF16). */
 int sia_nchw_f32_to_nhwc4_bf16(const float* src, int batch, int h, int w, void* dst, void* stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -92,7 +95,7 @@ int sia_pack_linear_chw_to_hwc(const float* w, int n, int c, int hw, void* packe
 
 /* ------------------------------------------------------------------------------------------
  * K4  convolution blocks: conv + bias + ReLU + 2x2/2 max-pool, bf16 in / fp32 accumulate / bf16 out.
- *   in  : NHWC4 bf16 [B,h,w,4] (conv7x7_c3)  or NHWC bf16 [B,h,w,cin] (conv3x3)
+ *   in  : padded NHWC4 bf16 [B,h,w+8,4] (conv7x7_c3)  or NHWC bf16 [B,h,w,cin] (conv3x3)
  *   out : NHWC bf16 [B,h/2,w/2,cout]
  * h and w must be even; conv7x7_c3 needs h%16==0 and w%16==0; conv3x3 needs w%8==0.
  * Supported (cin,cout): (32,64), (64,128), (128,256).
@@ -141,6 +144,13 @@ int sia_confusion_counts(const uint8_t* pred, const uint8_t* label, const uint8_
 int sia_debug_umma_probe(const void* smem_image, int image_bytes, const uint64_t* a_desc_host,
                          const uint64_t* b_desc_host, int n_mma, int n, float* out_128xn, int repeat,
                          long long* cycles_host, void* stream);
+
+/* Debug / bring-up: one TMA tiled load of a bf16 tensor (rank 2..4; dims / box in elements, innermost
+ * first; strides in bytes for dims 1..rank-1; swizzle_bytes in {0,32,64,128}) at the given coordinates;
+ * `out` receives the box bytes exactly as they landed in shared memory. */
+int sia_debug_tma_probe(const void* base, int rank, const uint64_t* dims_host, const uint64_t* strides_bytes_host,
+                        const uint32_t* box_host, int swizzle_bytes, const int* coords_host, void* out,
+                        void* stream);
 
 #ifdef __cplusplus
 }

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(HERE, "libsia_b200.so")
 LAYOUT_NCHW_F32 = 0
 LAYOUT_NCHW_BF16 = 1
 LAYOUT_NHWC4_BF16 = 2
+NHWC4_PAD = 8            # SIA_NHWC4_PAD: extra pixels per row of the NHWC4 layout
 
 _P = c_void_p
 
@@ -40,6 +41,8 @@ SIGNATURES = {
     "sia_confusion_counts": (c_int, [_P, _P, _P, c_longlong, c_longlong, c_int, c_int, _P, _P]),
     "sia_debug_umma_probe": (c_int, [_P, c_int, ctypes.POINTER(c_uint64), ctypes.POINTER(c_uint64), c_int, c_int,
                                      _P, c_int, ctypes.POINTER(c_longlong), _P]),
+    "sia_debug_tma_probe": (c_int, [_P, c_int, ctypes.POINTER(c_uint64), ctypes.POINTER(c_uint64),
+                                    ctypes.POINTER(ctypes.c_uint32), c_int, ctypes.POINTER(c_int), _P, _P]),
 }
 
 _lib = None

@@ -87,8 +87,9 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
         const int n = tile / (tiles_x * tiles_y);
         mbar_wait(&empty_bar[stage], phase ^ 1, 30);
         mbar_arrive_expect_tx(&full_bar[stage], C1_STAGE_BYTES);
-        // innermost coordinate is in bf16 elements: 4 per pixel
-        tma_load_3d(smem_a + stage * C1_STAGE_STRIDE, &tmap_in, &full_bar[stage], (tx * C1_TILE - 3) * 4,
+        // innermost coordinate is in bf16 elements (4 per pixel) and must be 16-byte aligned for TMA:
+        // image pixel x sits in column x+1 of the padded row, so the window start x0-3 is column x0-2
+        tma_load_3d(smem_a + stage * C1_STAGE_STRIDE, &tmap_in, &full_bar[stage], (tx * C1_TILE - 2) * 4,
                     ty * C1_TILE - 3, n);
         if (++stage == C1_NSTAGE) { stage = 0; phase ^= 1; }
       }
@@ -214,9 +215,12 @@ extern "C" int sia_conv7x7_c3_relu_pool2(const void* in_nhwc4, int batch, int h,
   SIA_REQUIRE(in_nhwc4 && w_packed && bias && out_nhwc && batch >= 1 && h >= 16 && w >= 16);
   SIA_REQUIRE(aligned(in_nhwc4, 16) && aligned(w_packed, 16) && aligned(out_nhwc, 16));
   if (h % C1_TILE != 0 || w % C1_TILE != 0) return SIA_E_UNSUPPORTED;
+  if (int wrc = ensure_watchdog()) return wrc;
   CUtensorMap tmap;
-  const uint64_t dims[3] = {(uint64_t)w * 4, (uint64_t)h, (uint64_t)batch};
-  const uint64_t strides[2] = {(uint64_t)w * 8, (uint64_t)h * w * 8};
+  // padded NHWC4 rows: (w + 8) pixels of 8 bytes, image pixel x in column x + 1
+  const uint64_t wp = (uint64_t)w + SIA_NHWC4_PAD;
+  const uint64_t dims[3] = {wp * 4, (uint64_t)h, (uint64_t)batch};
+  const uint64_t strides[2] = {wp * 8, (uint64_t)h * wp * 8};
   const uint32_t box[3] = {C1_WIN_PX * 4, C1_ROWS, 1};
   int rc = encode_tmap_bf16(&tmap, in_nhwc4, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
   if (rc != 0) return rc;

@@ -245,6 +245,7 @@ template <int CIN, int COUT, int NSTAGE>
 static int launch_conv3x3(const void* in, int batch, int h, int w, const void* w_packed, const float* bias, void* out,
                           cudaStream_t st) {
   using C = ConvCfg<CIN, COUT>;
+  if (int wrc = ensure_watchdog()) return wrc;
   CUtensorMap tmap;
   const uint64_t dims[4] = {(uint64_t)CIN, (uint64_t)w, (uint64_t)h, (uint64_t)batch};
   const uint64_t strides[3] = {(uint64_t)CIN * 2, (uint64_t)w * CIN * 2, (uint64_t)h * w * CIN * 2};

@@ -2,6 +2,29 @@
 #include "sia_host.cuh"
 #include "sia_ptx.cuh"
 
+namespace sia {
+
+static volatile unsigned int* g_wd_host = nullptr;
+
+volatile unsigned int* watchdog_host_word() { return g_wd_host; }
+
+int ensure_watchdog() {
+  if (g_wd_host != nullptr) return 0;
+  unsigned int* h = nullptr;
+  cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&h), sizeof(unsigned int), cudaHostAllocMapped);
+  if (e != cudaSuccess) return (int)e;
+  *h = 0;
+  unsigned int* d = nullptr;
+  e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&d), h, 0);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemcpyToSymbol(g_watchdog_word, &d, sizeof(d));
+  if (e != cudaSuccess) return (int)e;
+  g_wd_host = h;
+  return 0;
+}
+
+}  // namespace sia
+
 extern "C" {
 
 int sia_version(void) { return SIA_VERSION; }
@@ -28,12 +51,10 @@ int sia_device_info(int* sm_count_host, int* cc_major_host, int* cc_minor_host) 
 }
 
 unsigned int sia_debug_watchdog(int reset) {
-  unsigned int v = 0;
-  if (cudaMemcpyFromSymbol(&v, sia::g_watchdog_code, sizeof(v)) != cudaSuccess) return 0xffffffffu;
-  if (reset) {
-    unsigned int z = 0;
-    cudaMemcpyToSymbol(sia::g_watchdog_code, &z, sizeof(z));
-  }
+  volatile unsigned int* w = sia::watchdog_host_word();
+  if (w == nullptr) return 0;
+  const unsigned int v = *w;
+  if (reset) *w = 0;
   return v;
 }
 

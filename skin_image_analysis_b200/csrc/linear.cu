@@ -220,6 +220,7 @@ extern "C" int sia_linear_splitk(const void* a_bf16, const void* w_bf16, int m, 
   SIA_REQUIRE(a_bf16 && w_bf16 && partial && m >= 1 && n >= 1 && k >= 1 && splits >= 1);
   SIA_REQUIRE(aligned(a_bf16, 16) && aligned(w_bf16, 16) && aligned(partial, 16));
   if (n % LN_BN != 0 || k % LN_BK != 0 || splits > k / LN_BK || splits > 65535) return SIA_E_UNSUPPORTED;
+  if (int wrc = ensure_watchdog()) return wrc;
   CUtensorMap ta, tw;
   {
     const uint64_t dims[2] = {(uint64_t)k, (uint64_t)m};

@@ -158,10 +158,17 @@ preprocess_kernel(const __grid_constant__ PreParams p) {
             const float v1 = fmaf(acc[s][1], p.scale[1], p.bias[1]);
             const float v2 = fmaf(acc[s][2], p.scale[2], p.bias[2]);
             if (p.layout == SIA_LAYOUT_NHWC4_BF16) {
+              // padded rows: pixel x lives in column x+1 of a (out_w + 8)-pixel row; pad columns are zero
               uint2 o;
               o.x = pack_bf16x2(v0, v1);
               o.y = pack_bf16x2(v2, 0.f);
-              reinterpret_cast<uint2*>(p.dst)[((size_t)n * p.out_h + e) * p.out_w + x] = o;
+              uint2* row = reinterpret_cast<uint2*>(p.dst) + ((size_t)n * p.out_h + e) * (p.out_w + SIA_NHWC4_PAD);
+              row[x + 1] = o;
+              if (x == 0) row[0] = make_uint2(0u, 0u);
+              if (x == p.out_w - 1) {
+#pragma unroll
+                for (int k = 2; k <= SIA_NHWC4_PAD; ++k) row[x + k] = make_uint2(0u, 0u);
+              }
             } else {
               const size_t plane = (size_t)p.out_h * p.out_w;
               const size_t o = (size_t)n * 3 * plane + (size_t)e * p.out_w + x;
@@ -201,6 +208,7 @@ extern "C" int sia_preprocess_u8hwc(const uint8_t* src, int batch, int src_h, in
   if (x_taps != 8 && x_taps != 16) return SIA_E_UNSUPPORTED;
   if (batch > 65535) return SIA_E_UNSUPPORTED;
 
+  if (int wrc = ensure_watchdog()) return wrc;
   PreParams p;
   p.src = src; p.x_off = x_off; p.x_w = x_w;
   p.row_w = reinterpret_cast<const float4*>(row_w);
@@ -243,7 +251,7 @@ extern "C" int sia_preprocess_u8hwc(const uint8_t* src, int batch, int src_h, in
 // ----------------------------------------------------------------------------------------------
 namespace sia {
 __global__ void nchw_f32_to_nhwc4_kernel(const float* __restrict__ src, uint2* __restrict__ dst, size_t pixels_per_image,
-                                         size_t total_pixels) {
+                                         size_t total_pixels, int w) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_pixels;
        i += (size_t)gridDim.x * blockDim.x) {
     const size_t n = i / pixels_per_image, p = i % pixels_per_image;
@@ -251,7 +259,13 @@ __global__ void nchw_f32_to_nhwc4_kernel(const float* __restrict__ src, uint2* _
     uint2 o;
     o.x = pack_bf16x2(s[0], s[pixels_per_image]);
     o.y = pack_bf16x2(s[2 * pixels_per_image], 0.f);
-    dst[i] = o;
+    const size_t y = p / w, x = p % w;
+    uint2* row = dst + (n * (pixels_per_image / w) + y) * (w + SIA_NHWC4_PAD);
+    row[x + 1] = o;
+    if (x == 0) row[0] = make_uint2(0u, 0u);
+    if (x == (size_t)w - 1) {
+      for (int k = 2; k <= SIA_NHWC4_PAD; ++k) row[x + k] = make_uint2(0u, 0u);
+    }
   }
 }
 }  // namespace sia
@@ -264,6 +278,6 @@ extern "C" int sia_nchw_f32_to_nhwc4_bf16(const float* src, int batch, int h, in
   const size_t cap = (size_t)sm_count() * 16;
   if (blocks > cap) blocks = cap;
   nchw_f32_to_nhwc4_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      src, static_cast<uint2*>(dst), ppi, total);
+      src, static_cast<uint2*>(dst), ppi, total, w);
   return launch_status();
 }

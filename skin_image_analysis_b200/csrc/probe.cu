@@ -95,6 +95,7 @@ extern "C" int sia_debug_umma_probe(const void* smem_image, int image_bytes, con
   SIA_REQUIRE(n_mma >= 1 && n_mma <= PROBE_MAX_MMA && n >= 16 && n <= 256 && n % 16 == 0);
   SIA_REQUIRE(image_bytes > 0 && image_bytes % 16 == 0 && image_bytes <= 200 * 1024);
   SIA_REQUIRE(aligned(smem_image, 16) && repeat >= 1);
+  if (int wrc = ensure_watchdog()) return wrc;
   ProbeParams p;
   for (int i = 0; i < n_mma; ++i) {
     p.a_desc[i] = a_desc_host[i];
@@ -119,4 +120,75 @@ extern "C" int sia_debug_umma_probe(const void* smem_image, int image_bytes, con
   }
   if (d_cycles) cudaFree(d_cycles);
   return rc;
+}
+
+// ----------------------------------------------------------------------------------------------
+// TMA bring-up: load one box of a bf16 tensor with the given swizzle / coordinates (negative and
+// out-of-range coordinates included) and return the shared-memory bytes exactly as TMA wrote them.
+// ----------------------------------------------------------------------------------------------
+namespace sia {
+
+struct TmaProbeParams {
+  int rank;
+  int coords[5];
+  uint32_t box_bytes;
+};
+
+__global__ void __launch_bounds__(128, 1)
+tma_probe_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TmaProbeParams p,
+                 uint8_t* __restrict__ out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t bar;
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  for (uint32_t i = threadIdx.x * 16; i < p.box_bytes; i += blockDim.x * 16) {
+    *reinterpret_cast<uint4*>(base + i) = make_uint4(0xdeadbeefu, 0xdeadbeefu, 0xdeadbeefu, 0xdeadbeefu);
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  fence_proxy_async_smem();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(&bar, p.box_bytes);
+    if (p.rank == 2) tma_load_2d(base, &tmap, &bar, p.coords[0], p.coords[1]);
+    if (p.rank == 3) tma_load_3d(base, &tmap, &bar, p.coords[0], p.coords[1], p.coords[2]);
+    if (p.rank == 4) tma_load_4d(base, &tmap, &bar, p.coords[0], p.coords[1], p.coords[2], p.coords[3]);
+  }
+  mbar_wait(&bar, 0, 5);
+  for (uint32_t i = threadIdx.x * 16; i < p.box_bytes; i += blockDim.x * 16) {
+    *reinterpret_cast<uint4*>(out + i) = *reinterpret_cast<const uint4*>(base + i);
+  }
+}
+
+}  // namespace sia
+
+extern "C" int sia_debug_tma_probe(const void* base, int rank, const uint64_t* dims_host,
+                                   const uint64_t* strides_bytes_host, const uint32_t* box_host, int swizzle_bytes,
+                                   const int* coords_host, void* out, void* stream) {
+  using namespace sia;
+  SIA_REQUIRE(base && dims_host && strides_bytes_host && box_host && coords_host && out);
+  SIA_REQUIRE(rank >= 2 && rank <= 4 && aligned(base, 16) && aligned(out, 16));
+  if (int wrc = ensure_watchdog()) return wrc;
+  CUtensorMapSwizzle sw = swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                          : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUtensorMap tmap;
+  int rc = encode_tmap_bf16(&tmap, base, rank, dims_host, strides_bytes_host, box_host, sw);
+  if (rc != 0) return rc;
+  TmaProbeParams p;
+  p.rank = rank;
+  uint64_t bytes = 2;
+  for (int i = 0; i < rank; ++i) {
+    p.coords[i] = coords_host[i];
+    bytes *= box_host[i];
+  }
+  SIA_REQUIRE(bytes % 16 == 0 && bytes <= 200 * 1024);
+  p.box_bytes = (uint32_t)bytes;
+  const int smem = (int)bytes + 1024;
+  static int configured = 0;
+  if (int rc2 = ensure_dynamic_smem(tma_probe_kernel, smem, &configured)) return rc2;
+  tma_probe_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(tmap, p, static_cast<uint8_t*>(out));
+  return launch_status();
 }

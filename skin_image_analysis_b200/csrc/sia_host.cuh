@@ -22,6 +22,10 @@ namespace sia {
     if (!(cond)) return SIA_E_INVALID; \
   } while (0)
 
+// Sets up the pinned watchdog word on first use (per process); every launcher calls it.
+int ensure_watchdog();
+volatile unsigned int* watchdog_host_word();
+
 inline int launch_status() {
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;

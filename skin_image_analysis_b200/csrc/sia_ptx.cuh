@@ -15,7 +15,9 @@ namespace sia {
 // bug surfaces as a launch error instead of a hung GPU.
 // ------------------------------------------------------------------------------------------
 // The library is built as ONE translation unit (libsia_unity.cu), so this is the single copy.
-static __device__ unsigned int g_watchdog_code = 0;
+// It points at a word of pinned, device-mapped HOST memory: a trap kills the CUDA context, the
+// host word survives and sia_debug_watchdog() can still say which wait timed out.
+static __device__ volatile unsigned int* g_watchdog_word = nullptr;
 
 #ifndef SIA_WATCHDOG_SPINS
 #define SIA_WATCHDOG_SPINS (1u << 24)
@@ -71,7 +73,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > SIA_WATCHDOG_SPINS) {
-      atomicCAS(&g_watchdog_code, 0u, 0x80000000u | (site << 16) | (blockIdx.x & 0xffffu));
+      if (g_watchdog_word != nullptr) {
+        *g_watchdog_word = 0x80000000u | (site << 16) | (blockIdx.x & 0xffffu);
+        __threadfence_system();
+      }
       __trap();
     }
   }

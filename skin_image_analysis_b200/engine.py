@@ -55,7 +55,7 @@ class EvalEngine:
                        for _ in range(n_slots)]
             self.label = [torch.zeros((batch,), dtype=torch.uint8, device=d) for _ in range(n_slots)]
             self.groups = [torch.full((N_ATTR, batch), 255, dtype=torch.uint8, device=d) for _ in range(n_slots)]
-            self.x4 = torch.empty((batch, out_size, out_size, 4), dtype=torch.bfloat16, device=d)
+            self.x4 = torch.zeros((batch, out_size, out_size + ops.NHWC4_PAD, 4), dtype=torch.bfloat16, device=d)
             self.counts = torch.zeros((N_ATTR, N_GROUPS, 2, 2), dtype=torch.int64, device=d)
             ws = self.plan.workspace(batch)
             self.logp, self.pred = ws["logp"], ws["pred"]

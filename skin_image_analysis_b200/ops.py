@@ -13,12 +13,13 @@ import torch
 
 from . import _lib
 from . import resize_weights as _rw
-from ._lib import LAYOUT_NCHW_BF16, LAYOUT_NCHW_F32, LAYOUT_NHWC4_BF16, SiaError, check, ptr, stream_ptr
+from ._lib import (LAYOUT_NCHW_BF16, LAYOUT_NCHW_F32, LAYOUT_NHWC4_BF16, NHWC4_PAD, SiaError, check, ptr,
+                   stream_ptr)
 
 __all__ = [
     "preprocess_u8hwc", "nchw_f32_to_nhwc4", "pack_conv7x7_c3", "pack_conv3x3", "pack_linear_chw_to_hwc",
     "conv7x7_c3_relu_pool2", "conv3x3_relu_pool2", "linear_splitk", "head_tail", "confusion_counts",
-    "umma_probe", "LAYOUT_NCHW_F32", "LAYOUT_NCHW_BF16", "LAYOUT_NHWC4_BF16",
+    "umma_probe", "tma_probe", "LAYOUT_NCHW_F32", "LAYOUT_NCHW_BF16", "LAYOUT_NHWC4_BF16", "NHWC4_PAD",
 ]
 
 
@@ -68,7 +69,7 @@ def preprocess_u8hwc(src: torch.Tensor, size, layout: int = LAYOUT_NCHW_F32, mea
     b, sh, sw, _ = src.shape
     oh, ow = int(size[0]), int(size[1])
     tab = _tables(src.device.index, sh, sw, oh, ow, float(scale), antialias)
-    shape = (b, oh, ow, 4) if layout == LAYOUT_NHWC4_BF16 else (b, 3, oh, ow)
+    shape = (b, oh, ow + NHWC4_PAD, 4) if layout == LAYOUT_NHWC4_BF16 else (b, 3, oh, ow)
     if out is None:
         out = torch.empty(shape, dtype=_LAYOUT_DTYPE[layout], device=src.device)
     else:
@@ -90,7 +91,7 @@ def nchw_f32_to_nhwc4(x: torch.Tensor, out: torch.Tensor | None = None) -> torch
     if c != 3:
         raise ValueError("expected [B,3,H,W]")
     if out is None:
-        out = torch.empty((b, h, w, 4), dtype=torch.bfloat16, device=x.device)
+        out = torch.empty((b, h, w + NHWC4_PAD, 4), dtype=torch.bfloat16, device=x.device)
     check(_lib.load().sia_nchw_f32_to_nhwc4_bf16(ptr(x), b, h, w, ptr(out), stream_ptr()), "sia_nchw_f32_to_nhwc4_bf16")
     return out
 
@@ -137,9 +138,10 @@ def conv7x7_c3_relu_pool2(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.T
     _need(x, torch.bfloat16, "x")
     _need(w_packed, torch.uint8, "w_packed")
     _need(bias, torch.float32, "bias")
-    b, h, w, c = x.shape
-    if c != 4:
-        raise ValueError("expected NHWC4 input")
+    b, h, wp, c = x.shape
+    w = wp - NHWC4_PAD
+    if c != 4 or w < 16:
+        raise ValueError("expected padded NHWC4 input [B,H,W+8,4]")
     if out is None:
         out = torch.empty((b, h // 2, w // 2, 32), dtype=torch.bfloat16, device=x.device)
     check(_lib.load().sia_conv7x7_c3_relu_pool2(ptr(x), b, h, w, ptr(w_packed), ptr(bias), ptr(out), stream_ptr()),
@@ -244,3 +246,20 @@ def umma_probe(image: torch.Tensor, a_descs, b_descs, n: int, repeat: int = 1, w
           "sia_debug_umma_probe")
     torch.cuda.synchronize()
     return (out, cyc.value) if want_cycles else out
+
+
+def tma_probe(t: torch.Tensor, dims, strides_bytes, box, swizzle_bytes: int, coords) -> torch.Tensor:
+    """One TMA box load of a bf16 tensor -> the shared-memory bytes as uint8 (bring-up tests)."""
+    _need(t, torch.bfloat16, "t")
+    rank = len(dims)
+    nbytes = 2
+    for b in box:
+        nbytes *= int(b)
+    out = torch.zeros(nbytes, dtype=torch.uint8, device=t.device)
+    check(_lib.load().sia_debug_tma_probe(
+        ptr(t), rank, (ctypes.c_uint64 * rank)(*[int(d) for d in dims]),
+        (ctypes.c_uint64 * max(1, rank - 1))(*[int(s) for s in strides_bytes]),
+        (ctypes.c_uint32 * rank)(*[int(b) for b in box]), int(swizzle_bytes),
+        (ctypes.c_int * rank)(*[int(c) for c in coords]), ptr(out), stream_ptr()), "sia_debug_tma_probe")
+    torch.cuda.synchronize()
+    return out

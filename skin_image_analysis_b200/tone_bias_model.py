@@ -88,7 +88,7 @@ class CnnPlan:
         return ws
 
     def forward_nhwc4(self, x4: torch.Tensor, label=None, groups=None, n_groups: int = 0, counts=None):
-        """x4: [B,S,S,4] bf16 -> (logp [B,2] f32, pred [B] u8).  Buffers are reused per batch size."""
+        """x4: padded NHWC4 [B,S,S+8,4] bf16 -> (logp [B,2] f32, pred [B] u8).  Buffers are reused per batch size."""
         batch = x4.shape[0]
         ws = self.workspace(batch)
         h = x4

@@ -30,3 +30,18 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.hookimpl(hookwrapper=True)
+def pytest_runtest_makereport(item, call):
+    """On a failing GPU test, say whether a kernel watchdog fired (the word lives in pinned host memory,
+    so it is readable even after the trap killed the CUDA context)."""
+    outcome = yield
+    rep = outcome.get_result()
+    if rep.when == "call" and rep.failed and "gpu" in item.keywords:
+        try:
+            from skin_image_analysis_b200 import _lib
+            wd = _lib.load().sia_debug_watchdog(0)
+            rep.sections.append(("sia watchdog", f"0x{wd:08x} (site {(wd >> 16) & 0x7fff}, block {wd & 0xffff})"))
+        except Exception as exc:      # pragma: no cover
+            rep.sections.append(("sia watchdog", f"unavailable: {exc}"))

@@ -63,7 +63,7 @@ def synthetic_u8_image(h: int, w: int, seed: int, kind: str = "noise") -> np.nda
         f = (coarse[y0][:, x0] * (1 - ty) * (1 - tx) + coarse[y0 + 1][:, x0] * ty * (1 - tx)
              + coarse[y0][:, x0 + 1] * (1 - ty) * tx + coarse[y0 + 1][:, x0 + 1] * ty * tx)
         img = f * 255 + rng.integers(-8, 9, (h, w, 3))
-        return img.clip(0, 255).astype(np.uint8)
+        return np.ascontiguousarray(img.clip(0, 255).astype(np.uint8))
     if kind == "extremes":
         img = np.zeros((h, w, 3), np.uint8)
         img[::2, ::3] = 255

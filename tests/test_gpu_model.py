@@ -38,7 +38,9 @@ def test_conv7x7_block(batch, h, w):
     wt = _bf(torch.randn(32, 3, 7, 7, device="cuda", generator=g) * 0.1)
     b = torch.randn(32, device="cuda", generator=g) * 0.1
     x4 = ops.nchw_f32_to_nhwc4(x)
-    assert torch.equal(x4[..., :3].float(), x.permute(0, 2, 3, 1)) and bool((x4[..., 3] == 0).all())
+    assert x4.shape == (batch, h, w + ops.NHWC4_PAD, 4)
+    assert torch.equal(x4[:, :, 1:w + 1, :3].float(), x.permute(0, 2, 3, 1)) and bool((x4[..., 3] == 0).all())
+    assert bool((x4[:, :, 0] == 0).all()) and bool((x4[:, :, w + 1:] == 0).all())
     out = ops.conv7x7_c3_relu_pool2(x4, ops.pack_conv7x7_c3(wt), b)
     assert out.shape == (batch, h // 2, w // 2, 32)
     _close_bf16(out.permute(0, 3, 1, 2), _ref_block(x, wt, b))

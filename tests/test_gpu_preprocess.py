@@ -56,8 +56,9 @@ def test_bf16_layouts_within_one_ulp():
     want_bf = torch.from_numpy(want).to(torch.bfloat16).float().numpy()
     nchw = _gpu(imgs, (224, 224), ops.LAYOUT_NCHW_BF16).float().cpu().numpy()
     nhwc4 = _gpu(imgs, (224, 224), ops.LAYOUT_NHWC4_BF16).float().cpu().numpy()
-    assert nhwc4.shape == (2, 224, 224, 4) and np.all(nhwc4[..., 3] == 0)
-    assert np.array_equal(nhwc4[..., :3].transpose(0, 3, 1, 2), nchw)
+    assert nhwc4.shape == (2, 224, 224 + ops.NHWC4_PAD, 4) and np.all(nhwc4[..., 3] == 0)
+    assert np.all(nhwc4[:, :, 0] == 0) and np.all(nhwc4[:, :, 225:] == 0)        # zero pad columns
+    assert np.array_equal(nhwc4[:, :, 1:225, :3].transpose(0, 3, 1, 2), nchw)
     ulp = np.maximum(np.abs(want_bf), 2.0 ** -126) * 2.0 ** -7
     assert np.all(np.abs(nchw - want_bf) <= ulp)
     assert (nchw != want_bf).mean() < 0.01          # the fp32 math differs from fp64 only near ties

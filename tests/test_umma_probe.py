@@ -73,9 +73,16 @@ REPORT = {}
 
 
 def record(name, ok, required, extra=None):
-    REPORT[name] = {"ok": bool(ok), "required": required, **(extra or {})}
+    """Merged into gpurun_out/probe_report.json (each experiment may run in its own process)."""
     os.makedirs("gpurun_out", exist_ok=True)
-    with open("gpurun_out/probe_report.json", "w") as f:
+    path = "gpurun_out/probe_report.json"
+    try:
+        with open(path) as f:
+            REPORT.update(json.load(f))
+    except Exception:
+        pass
+    REPORT[name] = {"ok": bool(ok), "required": required, **(extra or {})}
+    with open(path, "w") as f:
         json.dump(REPORT, f, indent=1, sort_keys=True)
 
 
@@ -233,3 +240,82 @@ def test_exploratory_issue_rate():
     _, cyc = ops.umma_probe(img.tensor(), ad, bd, 64, repeat=128, want_cycles=True)
     out["conv1_nosw_n64_cycles_per_mma"] = cyc / (128 * 14)
     record("issue_rate", True, False, out)
+
+
+# ----------------------------------------------------------------------------------------------------
+# TMA bring-up: the exact shared-memory image of the boxes the conv / linear kernels request
+# ----------------------------------------------------------------------------------------------------
+def _coded(shape, seed):
+    rng = np.random.default_rng(seed)
+    return torch.from_numpy(rng.integers(-120, 121, shape).astype(np.float32)).to(torch.bfloat16).cuda()
+
+
+def _swizzle_rows(rows_u16, row_bytes, swizzle):
+    """rows_u16 [R, row_bytes/2] -> bytes as TMA lays them out (16-byte units XORed by the row index)."""
+    out = np.zeros_like(rows_u16)
+    units = row_bytes // 16
+    for r in range(rows_u16.shape[0]):
+        x = 0 if swizzle == 0 else (r % 8) if swizzle == 128 else ((r >> 1) & 3) if swizzle == 64 else ((r >> 2) & 1)
+        for u in range(units):
+            out[r, (u ^ x) * 8:(u ^ x) * 8 + 8] = rows_u16[r, u * 8:u * 8 + 8]
+    return out.reshape(-1)
+
+
+def _bits(t):
+    return t.cpu().view(torch.int16).numpy().view(np.uint16)
+
+
+@pytest.mark.parametrize("cin,swz", [(64, 128), (32, 64)])
+@pytest.mark.parametrize("coords", [(0, -1, -1, 0), (0, 8, 15, 1), (0, 3, 2, 1)])
+def test_tma_conv3x3_halo_box(cin, swz, coords):
+    """box [C<=64, 8 x, 18 y, 1 n] of an NHWC tensor: 144 smem rows of one pixel, zero outside the image."""
+    from skin_image_analysis_b200 import ops
+    b, h, w = 2, 20, 16
+    t = _coded((b, h, w, cin), 7)
+    got = ops.tma_probe(t, (cin, w, h, b), (cin * 2, w * cin * 2, h * w * cin * 2), (cin, 8, 18, 1), swz, coords)
+    src = _bits(t)
+    rows = np.zeros((144, cin), np.uint16)
+    for yy in range(18):
+        for xx in range(8):
+            y, x = coords[2] + yy, coords[1] + xx
+            if 0 <= y < h and 0 <= x < w:
+                rows[yy * 8 + xx] = src[coords[3], y, x]
+    want = _swizzle_rows(rows, cin * 2, swz)
+    ok = np.array_equal(got.cpu().numpy().view(np.uint16), want)
+    record(f"tma_conv3x3_c{cin}_{coords}", ok, True)
+    assert ok
+
+
+@pytest.mark.parametrize("coords", [(-8, -3, 0), (56, 13, 1), (120, 29, 1)])
+def test_tma_conv1_patch_box(coords):
+    """box [24 px * 4 ch, 22 rows, 1] of the padded NHWC4 image seen as [B, H, (W+8)*4].  The innermost
+    start must be a multiple of 8 elements (16 bytes) -- (x0-2)*4 with x0 % 16 == 0 -- an unaligned start
+    raises an illegal-instruction fault (found on the first bring-up run)."""
+    from skin_image_analysis_b200 import ops
+    b, h, w = 2, 32, 56
+    t = _coded((b, h, w * 4), 8)
+    got = ops.tma_probe(t, (w * 4, h, b), (w * 8, h * w * 8), (96, 22, 1), 0, coords)
+    src = _bits(t)
+    rows = np.zeros((22, 96), np.uint16)
+    for yy in range(22):
+        y = coords[1] + yy
+        for e in range(96):
+            x = coords[0] + e
+            if 0 <= y < h and 0 <= x < w * 4:
+                rows[yy, e] = src[coords[2], y, x]
+    ok = np.array_equal(got.cpu().numpy().view(np.uint16), rows.reshape(-1))
+    record(f"tma_conv1_{coords}", ok, True)
+    assert ok
+
+
+def test_tma_linear_tile_box():
+    from skin_image_analysis_b200 import ops
+    m, k = 200, 256
+    t = _coded((m, k), 9)
+    got = ops.tma_probe(t, (k, m), (k * 2,), (64, 128), 128, (64, 128))
+    src = _bits(t)
+    rows = np.zeros((128, 64), np.uint16)
+    rows[:72] = src[128:200, 64:128]
+    ok = np.array_equal(got.cpu().numpy().view(np.uint16), _swizzle_rows(rows, 128, 128))
+    record("tma_linear_tile", ok, True)
+    assert ok

@@ -11,14 +11,25 @@ nvidia-smi --query-gpu=name,driver_version,clocks.max.sm,memory.total --format=c
 
 if [[ " $WHAT " == *" tests "* ]]; then
   : > $OUT/tests_summary.txt
-  # probe experiments one per process (a bad descriptor poisons the CUDA context)
-  for id in $(python -m pytest tests/test_umma_probe.py --collect-only -q -m gpu 2>/dev/null | grep "::"); do
+  # probe experiments one per process (a bad descriptor poisons the CUDA context); PROBE_FILTER narrows them
+  for id in $(python -m pytest tests/test_umma_probe.py --collect-only -q -m gpu -k "${PROBE_FILTER:-test_}" 2>/dev/null | grep "::"); do
     timeout 300 python -m pytest "$id" -q -m gpu -x -p no:cacheprovider > $OUT/t.log 2>&1
     rc=$?
     echo "$rc $id" >> $OUT/tests_summary.txt
     if [ $rc -ne 0 ]; then { echo "=== $id"; tail -40 $OUT/t.log; } >> $OUT/tests_failures.txt; fi
   done
-  for f in tests/test_gpu_counts.py tests/test_gpu_preprocess.py tests/test_gpu_model.py; do
+  if [ "${ISOLATE_MODEL:-0}" = "1" ]; then
+    for id in $(python -m pytest tests/test_gpu_model.py --collect-only -q -m gpu 2>/dev/null | grep "::"); do
+      timeout 300 python -m pytest "$id" -q -m gpu -x -p no:cacheprovider > $OUT/t.log 2>&1
+      rc=$?
+      echo "$rc $id" >> $OUT/tests_summary.txt
+      if [ $rc -ne 0 ]; then { echo "=== $id"; grep -v "^$" $OUT/t.log | tail -45; } >> $OUT/tests_failures.txt; fi
+    done
+    MODEL_FILES=""
+  else
+    MODEL_FILES="tests/test_gpu_model.py"
+  fi
+  for f in tests/test_gpu_counts.py tests/test_gpu_preprocess.py $MODEL_FILES; do
     timeout 900 python -m pytest "$f" -q -m gpu -p no:cacheprovider > $OUT/$(basename $f .py).log 2>&1
     echo "$? $f" >> $OUT/tests_summary.txt
     tail -60 $OUT/$(basename $f .py).log >> $OUT/tests_failures.txt
