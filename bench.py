@@ -182,13 +182,15 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
-def build_state(device):
+def build_state(device, centre: bool = True):
     """Random-init weights of the reference architecture (xavier-normal weights, default biases) with the
     head centred so both classes occur (un-centred random init predicts one class)."""
     from skin_image_analysis_b200.tone_bias_model import SkinCancerListModel
     torch.manual_seed(0)
     model = SkinCancerListModel(["benign", "malignant"])
     state = {k: v.clone() for k, v in model.state_dict().items()}
+    if not centre:
+        return state
     model = model.to(device).eval()
     g = torch.Generator(device=device).manual_seed(1)
     logp = model(torch.rand(64, 3, OUT, OUT, device=device, generator=g))

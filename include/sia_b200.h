@@ -152,6 +152,10 @@ int sia_debug_tma_probe(const void* base, int rank, const uint64_t* dims_host, c
                         const uint32_t* box_host, int swizzle_bytes, const int* coords_host, void* out,
                         void* stream);
 
+/* Debug / bring-up: lane-operations per SM clock (one resident CTA of 1024 threads) for
+ * FFMA, PRMT, I2F.U8(+IADD), DP4A, DP2A, IMAD, SHF, FFMA2 -- out_host needs room for 8 doubles. */
+int sia_debug_alu_rates(double* out_host, int n);
+
 #ifdef __cplusplus
 }
 #endif

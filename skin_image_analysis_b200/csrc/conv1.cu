@@ -72,7 +72,7 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = bcast0(*tmem_slot);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -95,38 +95,40 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, C1_N);
-      const uint32_t a_base = smem_u32(smem_a);
-      const uint32_t b_base = smem_u32(smem_b);
-      mbar_wait(wload_bar, 0, 31);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 32);
-        mbar_wait(&full_bar[stage], phase, 33);
-        tc_fence_after_sync();
+    // whole warp runs the uniform control flow; one elected lane issues UMMAs + commits
+    constexpr uint32_t idesc = make_idesc_bf16(128, C1_N);
+    // A: rows = pixel pairs 16 B apart, K-adjacent core matrix = next 2 pixels (LBO 16 B), next 8 rows =
+    //    next image row (SBO = row pitch).  B: canonical no-swizzle, core matrices contiguous along K.
+    constexpr uint32_t a_hi = desc_hi(C1_ROWB, SW_NONE);
+    constexpr uint32_t b_hi = desc_hi(C1_B_SBO, SW_NONE);
+    const uint32_t a_lo0 = desc_lo(smem_u32(smem_a), 16);
+    const uint32_t b_lo0 = desc_lo(smem_u32(smem_b), 128);
+    mbar_wait(wload_bar, 0, 31);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 32);
+      mbar_wait(&full_bar[stage], phase, 33);
+      tc_fence_after_sync();
+      if (elect_one()) {
         const uint32_t d_tmem = tmem_base + acc * C1_N;
-        const uint32_t a_stage = a_base + stage * C1_STAGE_STRIDE;
+        const uint32_t a_lo = a_lo0 + stage * (C1_STAGE_STRIDE >> 4);
 #pragma unroll
         for (int r = 0; r < 7; ++r) {
 #pragma unroll
           for (int kk = 0; kk < 2; ++kk) {
-            // A: rows = pixel pairs 16 B apart, K-adjacent core matrix = next 2 pixels (LBO 16 B),
-            //    next 8 rows = next image row (SBO = row pitch)
-            const uint64_t a_desc = make_smem_desc(a_stage + r * C1_ROWB + kk * 32, 16, C1_ROWB, SW_NONE);
-            // B: canonical no-swizzle, core matrices contiguous along K (LBO 128 B)
-            const uint64_t b_desc = make_smem_desc(b_base + (r * 4 + kk * 2) * 128, 128, C1_B_SBO, SW_NONE);
-            umma_bf16_ss(d_tmem, a_desc, b_desc, idesc, (r | kk) ? 1u : 0u);
+            umma_bf16_ss_w(d_tmem, a_lo + r * (C1_ROWB >> 4) + kk * 2, a_hi, b_lo0 + (r * 4 + kk * 2) * 8, b_hi, idesc,
+                           (r | kk) ? 1u : 0u);
           }
         }
         umma_commit(&empty_bar[stage]);
         umma_commit(&tfull_bar[acc]);
-        if (++stage == C1_NSTAGE) { stage = 0; phase ^= 1; }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
+      __syncwarp();
+      if (++stage == C1_NSTAGE) { stage = 0; phase ^= 1; }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
     const int e = warp - 4;

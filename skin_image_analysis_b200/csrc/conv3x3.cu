@@ -84,7 +84,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = bcast0(*tmem_slot);
 
   if (warp == 0) {
     // ================================ TMA producer ==========================================
@@ -115,43 +115,46 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ============================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, COUT);
-      const uint32_t a_base = smem_u32(smem_a);
-      const uint32_t b_base = smem_u32(smem_b);
-      mbar_wait(wload_bar, 0, 21);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 22);
-        tc_fence_after_sync();
-        const uint32_t d_tmem = tmem_base + acc * COUT;
-        uint32_t first = 1;
-        for (int s = 0; s < 3; ++s) {
-          for (int kc = 0; kc < C::NCHUNK; ++kc) {
-            mbar_wait(&full_bar[stage], phase, 23);
-            tc_fence_after_sync();
-            const uint32_t a_stage = a_base + stage * C::STAGE_BYTES;
+    // The whole warp runs the (warp-uniform) control flow so descriptors stay in uniform registers;
+    // one elected lane issues the UMMAs and their commits.
+    constexpr uint32_t idesc = make_idesc_bf16(128, COUT);
+    constexpr uint32_t hi = desc_hi(C::ATOM, C::SWZ);
+    const uint32_t a_lo0 = desc_lo(smem_u32(smem_a), 0);
+    const uint32_t b_lo0 = desc_lo(smem_u32(smem_b), 0);
+    mbar_wait(wload_bar, 0, 21);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 22);
+      tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_base + acc * COUT;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+#pragma unroll
+        for (int kc = 0; kc < C::NCHUNK; ++kc) {
+          mbar_wait(&full_bar[stage], phase, 23);
+          tc_fence_after_sync();
+          if (elect_one()) {
+            const uint32_t a_lo = a_lo0 + stage * (C::STAGE_BYTES >> 4);
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
-              const uint32_t b_tap = b_base + ((r * 3 + s) * C::NCHUNK + kc) * C::B_TAP_BYTES;
+              const uint32_t b_lo = b_lo0 + ((r * 3 + s) * C::NCHUNK + kc) * (C::B_TAP_BYTES >> 4);
 #pragma unroll
               for (int kk = 0; kk < C::CK / 16; ++kk) {
-                const uint64_t a_desc = make_smem_desc(a_stage + r * C::ATOM + kk * 32, 0, C::ATOM, C::SWZ);
-                const uint64_t b_desc = make_smem_desc(b_tap + kk * 32, 0, C::ATOM, C::SWZ);
-                umma_bf16_ss(d_tmem, a_desc, b_desc, idesc, first ? 0u : 1u);
-                first = 0;
+                umma_bf16_ss_w(d_tmem, a_lo + r * (C::ATOM >> 4) + kk * 2, hi, b_lo + kk * 2, hi, idesc,
+                               (s | kc | r | kk) ? 1u : 0u);
               }
             }
-            umma_commit(&empty_bar[stage]);  // buffer reusable once these MMAs have read it
-            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+            umma_commit(&empty_bar[stage]);          // buffer reusable once these MMAs have read it
+            if (s == 2 && kc == C::NCHUNK - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete
           }
+          __syncwarp();
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);        // accumulator complete -> epilogue
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
     // ================================ epilogue ==============================================
@@ -174,11 +177,9 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
       mbar_wait(&tfull_bar[acc], acc_phase, 24);
       tc_fence_after_sync();
       const uint32_t t_addr = tmem_base + ((uint32_t)(32 * e) << 16) + acc * COUT;
-#pragma unroll 1
-      for (int cb = 0; cb < COUT; cb += 32) {
-        uint32_t v[32];
-        tmem_ld32(t_addr + cb, v);
-        tmem_ld_wait();
+
+      // bias + ReLU + bf16 + 2x2 max-pool (shuffle reduce-scatter) + 16-byte store of one 32-channel chunk
+      auto finish_chunk = [&](const uint32_t (&v)[32], int cb) {
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -186,17 +187,16 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
           const float b = fmaxf(__uint_as_float(v[2 * j + 1]) + smem_bias[cb + 2 * j + 1], 0.f);
           pk[j] = pack_bf16x2(a, b);
         }
-        // reduce-scatter over the 2x2 window: x partner keeps/sends 8 of 16 regs, y partner 4 of 8
         uint32_t h8[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 8; ++j) {     // x partner (lane^1): keep 8 of 16 registers, send the other 8
           const uint32_t keep = odd_x ? pk[8 + j] : pk[j];
           const uint32_t send = odd_x ? pk[j] : pk[8 + j];
           h8[j] = max_bf16x2(keep, __shfl_xor_sync(0xffffffffu, send, 1));
         }
         uint32_t q4[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 4; ++j) {     // y partner (lane^8): keep 4 of 8
           const uint32_t keep = odd_y ? h8[4 + j] : h8[j];
           const uint32_t send = odd_y ? h8[j] : h8[4 + j];
           q4[j] = max_bf16x2(keep, __shfl_xor_sync(0xffffffffu, send, 8));
@@ -205,10 +205,27 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
           const int ch = cb + (odd_x ? 16 : 0) + (odd_y ? 8 : 0);
           *reinterpret_cast<uint4*>(orow + ch) = make_uint4(q4[0], q4[1], q4[2], q4[3]);
         }
+      };
+
+      // two register buffers: the TMEM load of chunk c+1 is in flight while chunk c is finished
+      uint32_t va[32], vb[32];
+      tmem_ld32(t_addr, va);
+#pragma unroll
+      for (int cb = 0; cb < COUT; cb += 64) {
+        tmem_ld_wait();
+        tmem_ld32(t_addr + cb + 32, vb);
+        finish_chunk(va, cb);
+        tmem_ld_wait();
+        if (cb + 64 < COUT) {
+          tmem_ld32(t_addr + cb + 64, va);
+        } else {
+          // every column of this accumulator is in registers: hand it back to the MMA warp
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+        finish_chunk(vb, cb + 32);
       }
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }

@@ -54,7 +54,7 @@ linear_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = bcast0(*tmem_slot);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -71,25 +71,26 @@ linear_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(LN_BM, LN_BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = kb_lo; kb < kb_hi; ++kb) {
-        mbar_wait(&full_bar[stage], phase, 41);
-        tc_fence_after_sync();
-        const uint32_t sa = smem_u32(smem + stage * LN_STAGE_BYTES);
-        const uint32_t sw = sa + LN_BM * LN_BK * 2;
+    constexpr uint32_t idesc = make_idesc_bf16(LN_BM, LN_BN);
+    constexpr uint32_t hi = desc_hi(1024, SW_128B);
+    const uint32_t lo0 = desc_lo(smem_u32(smem), 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = kb_lo; kb < kb_hi; ++kb) {
+      mbar_wait(&full_bar[stage], phase, 41);
+      tc_fence_after_sync();
+      if (elect_one()) {
+        const uint32_t a_lo = lo0 + stage * (LN_STAGE_BYTES >> 4);
+        const uint32_t b_lo = a_lo + ((LN_BM * LN_BK * 2) >> 4);
 #pragma unroll
         for (int kk = 0; kk < LN_BK / 16; ++kk) {
-          const uint64_t a_desc = make_smem_desc(sa + kk * 32, 0, 1024, SW_128B);
-          const uint64_t b_desc = make_smem_desc(sw + kk * 32, 0, 1024, SW_128B);
-          umma_bf16_ss(tmem_base, a_desc, b_desc, idesc, (kb > kb_lo || kk > 0) ? 1u : 0u);
+          umma_bf16_ss_w(tmem_base, a_lo + kk * 2, hi, b_lo + kk * 2, hi, idesc, (kb > kb_lo || kk > 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[stage]);
-        if (++stage == LN_NSTAGE) { stage = 0; phase ^= 1; }
+        if (kb == kb_hi - 1) umma_commit(done_bar);
       }
-      umma_commit(done_bar);
+      __syncwarp();
+      if (++stage == LN_NSTAGE) { stage = 0; phase ^= 1; }
     }
   } else {
     // epilogue: warp w may only touch TMEM lanes 32*(w%4) ..
@@ -118,7 +119,7 @@ linear_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 }
 
 // ------------------------------------- tail --------------------------------------------------
-constexpr int TAIL_THREADS = 256;
+constexpr int TAIL_THREADS = 512;
 constexpr int TAIL_IMGS = 4;     // images per CTA (amortises the W2 read)
 constexpr int TAIL_MAX_N1 = 512;
 constexpr int TAIL_MAX_N2 = 256;
@@ -130,34 +131,64 @@ head_tail_kernel(const float* __restrict__ partial, int splits, int M, int n1, i
                  const uint8_t* __restrict__ label, const uint8_t* __restrict__ groups, int groups_stride, int n_attr,
                  int n_groups, unsigned long long* __restrict__ counts) {
   __shared__ float h1[TAIL_IMGS][TAIL_MAX_N1];
-  __shared__ float h2[TAIL_IMGS][TAIL_MAX_N2];
+  __shared__ float h2p[2][TAIL_IMGS][TAIL_MAX_N2];   // the two K-halves of fc2
   __shared__ float z[TAIL_IMGS][2];
   const int m0 = blockIdx.x * TAIL_IMGS;
 
-  // h1 = relu(b1 + sum over splits, in split order)
+  // h1 = relu(b1 + sum over splits, in split order): the loads of one element are independent
   for (int i = threadIdx.x; i < TAIL_IMGS * n1; i += blockDim.x) {
     const int img = i / n1, k = i % n1;
     float s = 0.f;
     if (m0 + img < M) {
-      for (int sp = 0; sp < splits; ++sp) s += partial[((size_t)sp * M + m0 + img) * n1 + k];
+      const float* src = partial + (size_t)(m0 + img) * n1 + k;
+      const size_t step = (size_t)M * n1;
+      int sp = 0;
+      for (; sp + 4 <= splits; sp += 4) {
+        const float a = src[(size_t)sp * step], b = src[(size_t)(sp + 1) * step];
+        const float c = src[(size_t)(sp + 2) * step], d = src[(size_t)(sp + 3) * step];
+        s = (((s + a) + b) + c) + d;
+      }
+      for (; sp < splits; ++sp) s += src[(size_t)sp * step];
       s = fmaxf(s + b1[k], 0.f);
     }
     h1[img][k] = s;
   }
   __syncthreads();
 
-  // h2 = relu(W2 h1 + b2): thread j owns output j for all images; w2t is [n1][n2] so reads coalesce
-  for (int j = threadIdx.x; j < n2; j += blockDim.x) {
-    float a[TAIL_IMGS];
+  // h2 = relu(W2 h1 + b2): thread (j, half) owns output j over half of K for all images; w2t is [n1][n2]
+  // so a warp reads 128 contiguous bytes per k
+  {
+    const int half = threadIdx.x / (TAIL_THREADS / 2);
+    const int j0 = threadIdx.x % (TAIL_THREADS / 2);
+    const int k_lo = half * (n1 / 2), k_hi = half == 0 ? n1 / 2 : n1;
+    for (int j = j0; j < n2; j += TAIL_THREADS / 2) {
+      float a[TAIL_IMGS];
 #pragma unroll
-    for (int img = 0; img < TAIL_IMGS; ++img) a[img] = 0.f;
-    for (int k = 0; k < n1; ++k) {
-      const float w = w2t[(size_t)k * n2 + j];
+      for (int img = 0; img < TAIL_IMGS; ++img) a[img] = 0.f;
+      int k = k_lo;
+      for (; k + 8 <= k_hi; k += 8) {
+        float w[8];
 #pragma unroll
-      for (int img = 0; img < TAIL_IMGS; ++img) a[img] = fmaf(w, h1[img][k], a[img]);
+        for (int u = 0; u < 8; ++u) w[u] = w2t[(size_t)(k + u) * n2 + j];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+#pragma unroll
+          for (int img = 0; img < TAIL_IMGS; ++img) a[img] = fmaf(w[u], h1[img][k + u], a[img]);
+        }
+      }
+      for (; k < k_hi; ++k) {
+        const float w = w2t[(size_t)k * n2 + j];
+#pragma unroll
+        for (int img = 0; img < TAIL_IMGS; ++img) a[img] = fmaf(w, h1[img][k], a[img]);
+      }
+#pragma unroll
+      for (int img = 0; img < TAIL_IMGS; ++img) h2p[half][img][j] = a[img];
     }
-#pragma unroll
-    for (int img = 0; img < TAIL_IMGS; ++img) h2[img][j] = fmaxf(a[img] + b2[j], 0.f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < TAIL_IMGS * n2; i += blockDim.x) {
+    const int img = i / n2, j = i % n2;
+    h2p[0][img][j] = fmaxf(h2p[0][img][j] + h2p[1][img][j] + b2[j], 0.f);
   }
   __syncthreads();
 
@@ -166,7 +197,7 @@ head_tail_kernel(const float* __restrict__ partial, int splits, int M, int n1, i
   if (warp < TAIL_IMGS * 2) {
     const int img = warp >> 1, cls = warp & 1;
     float s = 0.f;
-    for (int j = lane; j < n2; j += 32) s = fmaf(w3[cls * n2 + j], h2[img][j], s);
+    for (int j = lane; j < n2; j += 32) s = fmaf(w3[cls * n2 + j], h2p[0][img][j], s);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) z[img][cls] = s + b3[cls];
@@ -251,7 +282,7 @@ extern "C" int sia_head_tail(const float* partial, int splits, int m, int n1, in
                              int n_groups, long long* counts, void* stream) {
   using namespace sia;
   SIA_REQUIRE(partial && b1 && w2t && b2 && w3 && b3 && logp && pred && splits >= 1 && m >= 1);
-  if (n1 < 1 || n1 > TAIL_MAX_N1 || n2 < 1 || n2 > TAIL_MAX_N2) return SIA_E_UNSUPPORTED;
+  if (n1 < 2 || n1 > TAIL_MAX_N1 || n1 % 2 != 0 || n2 < 1 || n2 > TAIL_MAX_N2) return SIA_E_UNSUPPORTED;
   if (counts != nullptr) {
     SIA_REQUIRE(label && groups && n_attr >= 1 && n_groups >= 1 && groups_stride >= m);
   }

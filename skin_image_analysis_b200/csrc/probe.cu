@@ -45,25 +45,26 @@ umma_probe_kernel(const uint8_t* __restrict__ image, const __grid_constant__ Pro
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem = tmem_slot;
+  const uint32_t tmem = bcast0(tmem_slot);
 
   const uint32_t idesc = make_idesc_bf16(128, p.n);
-  if (threadIdx.x == 0) {
-    long long t0 = clock64();
-    for (int rep = 0; rep < p.repeat; ++rep) {
-      for (int i = 0; i < p.n_mma; ++i) {
-        // start-address field is relative: add the image base (16-byte units, 14 bits)
-        uint64_t a = p.a_desc[i];
-        uint64_t b = p.b_desc[i];
-        a = (a & ~uint64_t(0x3fff)) | (((a & 0x3fff) + (base_addr >> 4)) & 0x3fff);
-        b = (b & ~uint64_t(0x3fff)) | (((b & 0x3fff) + (base_addr >> 4)) & 0x3fff);
-        umma_bf16_ss(tmem, a, b, idesc, i > 0 ? 1u : 0u);
+  if (threadIdx.x < 32) {
+    // warp-uniform control flow (descriptors come from the constant bank); one elected lane issues
+    const uint32_t base16 = base_addr >> 4;
+    long long t0 = 0;
+    if (elect_one()) {
+      t0 = clock64();
+      for (int rep = 0; rep < p.repeat; ++rep) {
+        for (int i = 0; i < p.n_mma; ++i) {
+          // start-address field is relative to the image base (no carry: the image is < 256 KB)
+          umma_bf16_ss(tmem, p.a_desc[i] + base16, p.b_desc[i] + base16, idesc, i > 0 ? 1u : 0u);
+        }
       }
+      umma_commit(&done_bar);
     }
-    umma_commit(&done_bar);
+    __syncwarp();
     mbar_wait(&done_bar, 0, 1);
-    long long t1 = clock64();
-    if (cycles) *cycles = t1 - t0;
+    if (threadIdx.x == 0 && cycles) *cycles = clock64() - t0;
   }
   __syncthreads();
   mbar_wait(&done_bar, 0, 2);
@@ -191,4 +192,109 @@ extern "C" int sia_debug_tma_probe(const void* base, int rank, const uint64_t* d
   if (int rc2 = ensure_dynamic_smem(tma_probe_kernel, smem, &configured)) return rc2;
   tma_probe_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(tmap, p, static_cast<uint8_t*>(out));
   return launch_status();
+}
+
+// ----------------------------------------------------------------------------------------------
+// ALU issue-rate probe: lane-operations per SM clock for the instruction kinds the preprocess kernel
+// can be built from (measured, because the B200 rates of I2F / IDP / packed-fp32 are not documented).
+// ----------------------------------------------------------------------------------------------
+namespace sia {
+
+constexpr int RATE_KINDS = 8;
+constexpr int RATE_ITERS = 512;
+constexpr int RATE_CHAINS = 8;
+
+template <int KIND>
+__device__ __forceinline__ void rate_body(uint32_t (&r)[RATE_CHAINS], uint32_t s0, uint32_t s1) {
+#pragma unroll
+  for (int c = 0; c < RATE_CHAINS; ++c) {
+    if constexpr (KIND == 0) {  // FFMA
+      r[c] = __float_as_uint(fmaf(__uint_as_float(r[c]), __uint_as_float(s0), __uint_as_float(s1)));
+    } else if constexpr (KIND == 1) {  // PRMT
+      r[c] = __byte_perm(r[c], s0, 0x7650 + (c & 3));
+    } else if constexpr (KIND == 2) {  // I2F from a byte
+      r[c] = __float_as_uint((float)((r[c] >> 8) & 0xffu)) + s0;
+    } else if constexpr (KIND == 3) {  // dp4a
+      r[c] = __dp4a(r[c], s0, r[c]);
+    } else if constexpr (KIND == 4) {  // dp2a
+      r[c] = __dp2a_lo(s0, r[c], r[c]);
+    } else if constexpr (KIND == 5) {  // IMAD
+      r[c] = r[c] * s0 + s1;
+    } else if constexpr (KIND == 6) {  // funnel shift
+      r[c] = __funnelshift_r(r[c], s0, s1);
+    }
+  }
+}
+
+template <int KIND>
+__device__ __forceinline__ long long rate_run(uint32_t seed, uint32_t* sink) {
+  uint32_t r[RATE_CHAINS];
+#pragma unroll
+  for (int c = 0; c < RATE_CHAINS; ++c) r[c] = seed + c * 0x01010101u;
+  const uint32_t s0 = seed | 0x3f000001u, s1 = (seed & 7u) + 1u;
+  __syncthreads();
+  const long long t0 = clock64();
+#pragma unroll 4
+  for (int i = 0; i < RATE_ITERS; ++i) rate_body<KIND>(r, s0, s1);
+  const long long t1 = clock64();
+  uint32_t x = 0;
+#pragma unroll
+  for (int c = 0; c < RATE_CHAINS; ++c) x ^= r[c];
+  if (x == 0x12345678u) *sink = x;
+  __syncthreads();
+  return t1 - t0;
+}
+
+__global__ void __launch_bounds__(1024, 1) alu_rate_kernel(long long* cycles, uint32_t seed, uint32_t* sink) {
+  long long c[RATE_KINDS];
+  c[0] = rate_run<0>(seed, sink);
+  c[1] = rate_run<1>(seed, sink);
+  c[2] = rate_run<2>(seed, sink);
+  c[3] = rate_run<3>(seed, sink);
+  c[4] = rate_run<4>(seed, sink);
+  c[5] = rate_run<5>(seed, sink);
+  c[6] = rate_run<6>(seed, sink);
+  // packed fp32: 2 FMAs per lane-instruction
+  {
+    float2 r[RATE_CHAINS];
+#pragma unroll
+    for (int k = 0; k < RATE_CHAINS; ++k) r[k] = make_float2(1.0f + k, 2.0f + k);
+    const float2 a = make_float2(1.0000001f, 0.9999999f), b = make_float2(1e-7f, -1e-7f);
+    __syncthreads();
+    const long long t0 = clock64();
+#pragma unroll 4
+    for (int i = 0; i < RATE_ITERS; ++i) {
+#pragma unroll
+      for (int k = 0; k < RATE_CHAINS; ++k) r[k] = __ffma2_rn(r[k], a, b);
+    }
+    c[7] = clock64() - t0;
+    float x = 0.f;
+#pragma unroll
+    for (int k = 0; k < RATE_CHAINS; ++k) x += r[k].x + r[k].y;
+    if (x == 1234.5f) *sink = 1;
+  }
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < RATE_KINDS; ++k) cycles[k] = c[k];
+  }
+}
+
+}  // namespace sia
+
+// out_host[k] = lane-operations per SM clock for k = FFMA, PRMT, I2F.U8(+IADD), DP4A, DP2A, IMAD, SHF, FFMA2
+extern "C" int sia_debug_alu_rates(double* out_host, int n) {
+  using namespace sia;
+  SIA_REQUIRE(out_host && n >= RATE_KINDS);
+  long long* d = nullptr;
+  uint32_t* sink = nullptr;
+  SIA_CUDA_OK(cudaMalloc(&d, RATE_KINDS * sizeof(long long)));
+  SIA_CUDA_OK(cudaMalloc(&sink, sizeof(uint32_t)));
+  alu_rate_kernel<<<1, 1024>>>(d, 12345u, sink);
+  long long h[RATE_KINDS];
+  cudaError_t e = cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  cudaFree(sink);
+  if (e != cudaSuccess) return (int)e;
+  const double ops = 1024.0 * RATE_ITERS * RATE_CHAINS;
+  for (int k = 0; k < RATE_KINDS; ++k) out_host[k] = ops / (double)h[k];
+  return 0;
 }

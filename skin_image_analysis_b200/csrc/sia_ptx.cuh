@@ -33,6 +33,10 @@ __device__ __forceinline__ uint32_t lane_id() {
   return l;
 }
 
+// Broadcast from lane 0: tells the compiler the value is warp-uniform (it can then live in a uniform
+// register, which is what UTCHMMA / UTMALDG operands need -- otherwise ptxas emits a serialising loop).
+__device__ __forceinline__ uint32_t bcast0(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
@@ -149,6 +153,19 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, u
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same, with the descriptors as (lo, hi) words: lo = (addr>>4) | (LBO>>4)<<16 advances by plain
+// 32-bit adds (byte offset >> 4), hi = (SBO>>4) | version | layout is a compile-time constant.
+__device__ __forceinline__ void umma_bf16_ss_w(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                               uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // All previously issued UMMAs of this thread arrive on `bar` when they complete.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -182,6 +199,13 @@ __host__ __device__ constexpr uint64_t make_smem_desc(uint32_t addr, uint32_t lb
   return (uint64_t)((addr >> 4) & 0x3fffu) | ((uint64_t)((lbo >> 4) & 0x3fffu) << 16) |
          ((uint64_t)((sbo >> 4) & 0x3fffu) << 32) | ((uint64_t)1 << 46) | ((uint64_t)(base_offset & 7u) << 49) |
          ((uint64_t)(layout & 7u) << 61);
+}
+
+__host__ __device__ constexpr uint32_t desc_lo(uint32_t addr, uint32_t lbo) {
+  return ((addr >> 4) & 0x3fffu) | (((lbo >> 4) & 0x3fffu) << 16);
+}
+__host__ __device__ constexpr uint32_t desc_hi(uint32_t sbo, uint32_t layout) {
+  return ((sbo >> 4) & 0x3fffu) | (1u << 14) | ((layout & 7u) << 29);
 }
 
 // Instruction descriptor, kind::f16: bf16 x bf16 -> fp32, both operands K-major.

@@ -319,3 +319,13 @@ def test_tma_linear_tile_box():
     ok = np.array_equal(got.cpu().numpy().view(np.uint16), _swizzle_rows(rows, 128, 128))
     record("tma_linear_tile", ok, True)
     assert ok
+
+
+def test_exploratory_alu_rates():
+    """Lane-ops per SM clock of the instruction kinds the preprocess kernel can be built from."""
+    import ctypes
+    from skin_image_analysis_b200 import _lib
+    out = (ctypes.c_double * 8)()
+    _lib.check(_lib.load().sia_debug_alu_rates(out, 8))
+    names = ["FFMA", "PRMT", "I2F_U8_plus_IADD", "DP4A", "DP2A", "IMAD", "SHF", "FFMA2"]
+    record("alu_rates_lane_ops_per_clk_per_sm", True, False, dict(zip(names, [round(v, 1) for v in out])))
