@@ -84,7 +84,7 @@ int sia_nchw_f32_to_nhwc4_bf16(const float* src, int batch, int h, int w, void* 
  * Weight packing (one-off, at model load).  Inputs are the reference's state_dict tensors
  * (fp32, OIHW conv weights / [out,in] linear weights).
  * ------------------------------------------------------------------------------------------ */
-/* conv1 [32,3,7,7] -> the 64 x 224 bf16 "two output pixels per GEMM row" operand (28672 bytes). */
+/* conv1 [32,3,7,7] -> the 128 x 256 bf16 "2x2 output pixels per GEMM row" operand (65536 bytes). */
 int sia_pack_conv7x7_c3(const float* w_oihw, void* packed, void* stream);
 size_t sia_pack_conv7x7_c3_bytes(void);
 /* conv [cout,cin,3,3] -> 9 taps x (cin/64 or 1) chunks of [cout][<=64] bf16, pre-swizzled. */
@@ -97,7 +97,7 @@ int sia_pack_linear_chw_to_hwc(const float* w, int n, int c, int hw, void* packe
  * K4  convolution blocks: conv + bias + ReLU + 2x2/2 max-pool, bf16 in / fp32 accumulate / bf16 out.
  *   in  : padded NHWC4 bf16 [B,h,w+8,4] (conv7x7_c3)  or NHWC bf16 [B,h,w,cin] (conv3x3)
  *   out : NHWC bf16 [B,h/2,w/2,cout]
- * h and w must be even; conv7x7_c3 needs h%16==0 and w%16==0; conv3x3 needs w%8==0.
+ * h must be even; conv7x7_c3 needs w%16==0; conv3x3 needs w%8==0.
  * Supported (cin,cout): (32,64), (64,128), (128,256).
  * ------------------------------------------------------------------------------------------ */
 int sia_conv7x7_c3_relu_pool2(const void* in_nhwc4, int batch, int h, int w, const void* w_packed,

@@ -5,12 +5,13 @@
 //   D[128 pixels, cout] = sum over 9 taps (r,s), cin:  X[pixel + (r-1, s-1), cin] * W[cout, cin, r, s]
 //
 // * M-tile  = 16 rows x 8 columns of output pixels (row m = y*8 + x); N = cout; K = 9*cin.
-// * A operand: for each horizontal tap s the producer TMA-loads ONE x-shifted halo copy of the
-//   input patch, box [<=64 ch, 8 x, 18 y] (zero fill outside the image = 'same' padding).  In the
-//   swizzled K-major layout that box is 144 consecutive smem "rows" of one pixel each, so the three
-//   vertical taps r are simply the same buffer advanced by r*8 rows (= whole swizzle atoms): each
-//   loaded byte feeds 3 taps, every descriptor is canonical.  A ring of such buffers decouples TMA
-//   from the MMA issue.
+// * A operand: ONE halo copy of the input patch per tile -- TMA box [<=64 ch, 10 x, 18 y] (zero fill
+//   outside the image = 'same' padding) lands as 180 shared-memory rows of one pixel each in the
+//   swizzled K-major layout.  Tap (r,s) is the same buffer read from row r*10+s with an 8-row-group
+//   stride of one halo row (SBO = 10 rows): the swizzle XOR is a function of the absolute smem address
+//   (pinned on hardware by tests/test_umma_probe.py), so shifted starts and non-1024-byte group
+//   strides address exactly what TMA wrote.  Every input byte is fetched once per tile and feeds all
+//   9 taps; a ring of such buffers decouples TMA from the MMA issue.
 // * B operand: all 9 taps of the packed weights stay resident in shared memory (loaded once per
 //   persistent CTA with bulk copies).
 // * Accumulators: two 128 x cout fp32 tiles in TMEM, so the epilogue of tile i overlaps the MMAs
@@ -27,7 +28,9 @@ namespace sia {
 
 constexpr int CV_TILE_Y = 16;
 constexpr int CV_TILE_X = 8;
-constexpr int CV_HALO_ROWS = CV_TILE_Y + 2;
+constexpr int CV_HALO_Y = CV_TILE_Y + 2;
+constexpr int CV_HALO_X = CV_TILE_X + 2;
+constexpr int CV_HALO_ROWS = CV_HALO_Y * CV_HALO_X;   // 180 pixels
 constexpr int CV_THREADS = 256;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-7 epilogue
 
 template <int CIN, int COUT>
@@ -36,12 +39,34 @@ struct ConvCfg {
   static constexpr int NCHUNK = CIN / CK;
   static constexpr int ROWB = CK * 2;                   // bytes per smem row (one pixel)
   static constexpr uint32_t SWZ = ROWB == 128 ? SW_128B : SW_64B;
-  static constexpr int ATOM = 8 * ROWB;                 // 8-row swizzle atom = SBO
-  static constexpr int STAGE_BYTES = CV_HALO_ROWS * CV_TILE_X * ROWB;
+  static constexpr int GROUP_STRIDE = CV_HALO_X * ROWB;                               // SBO: next tile row
+  static constexpr int CHUNK_BYTES = CV_HALO_ROWS * ROWB;                              // one TMA box
+  static constexpr int CHUNK_STRIDE = (CHUNK_BYTES + 1023) / 1024 * 1024;
+  static constexpr int STAGE_STRIDE = NCHUNK * CHUNK_STRIDE;
+  static constexpr int STAGE_TX_BYTES = NCHUNK * CHUNK_BYTES;
   static constexpr int B_TAP_BYTES = COUT * ROWB;       // one (tap, chunk) weight block
   static constexpr int B_BYTES = 9 * NCHUNK * B_TAP_BYTES;
-  static constexpr int STEPS = 3 * NCHUNK;              // (s, chunk) buffers per tile
   static constexpr int TMEM_COLS = 2 * COUT;
+};
+
+// Decomposes the persistent-CTA tile stride once, so that walking tiles needs no integer division.
+struct TileWalker {
+  int tx, ty, n, dtx, dty, dn, tiles_x, tiles_y;
+  __device__ TileWalker(int first, int step, int tiles_x_, int tiles_y_) : tiles_x(tiles_x_), tiles_y(tiles_y_) {
+    tx = first % tiles_x;
+    ty = (first / tiles_x) % tiles_y;
+    n = first / (tiles_x * tiles_y);
+    dtx = step % tiles_x;
+    dty = (step / tiles_x) % tiles_y;
+    dn = step / (tiles_x * tiles_y);
+  }
+  __device__ __forceinline__ void next() {
+    tx += dtx;
+    ty += dty;
+    n += dn;
+    if (tx >= tiles_x) { tx -= tiles_x; ++ty; }
+    if (ty >= tiles_y) { ty -= tiles_y; ++n; }
+  }
 };
 
 template <int CIN, int COUT, int NSTAGE>
@@ -51,10 +76,11 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
                int tiles_x, int total_tiles) {
   using C = ConvCfg<CIN, COUT>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // keep the shared address space visible to the compiler (offset arithmetic, no integer round trip)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_b = smem;                               // B_BYTES (multiple of 1024)
-  uint8_t* smem_a = smem + C::B_BYTES;                  // NSTAGE * STAGE_BYTES
-  float* smem_bias = reinterpret_cast<float*>(smem_a + NSTAGE * C::STAGE_BYTES);
+  uint8_t* smem_a = smem + C::B_BYTES;                  // NSTAGE * STAGE_STRIDE
+  float* smem_bias = reinterpret_cast<float*>(smem_a + NSTAGE * C::STAGE_STRIDE);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_bias + COUT);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + NSTAGE;
@@ -98,19 +124,16 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
       }
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int tx = tile % tiles_x;
-        const int ty = (tile / tiles_x) % tiles_y;
-        const int n = tile / (tiles_x * tiles_y);
-        for (int s = 0; s < 3; ++s) {
-          for (int kc = 0; kc < C::NCHUNK; ++kc) {
-            mbar_wait(&empty_bar[stage], phase ^ 1, 20);
-            mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-            tma_load_4d(smem_a + stage * C::STAGE_BYTES, &tmap_in, &full_bar[stage], kc * C::CK,
-                        tx * CV_TILE_X + s - 1, ty * CV_TILE_Y - 1, n);
-            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-          }
+      TileWalker t(blockIdx.x, gridDim.x, tiles_x, tiles_y);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, t.next()) {
+        mbar_wait(&empty_bar[stage], phase ^ 1, 20);
+        mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_TX_BYTES);
+#pragma unroll
+        for (int kc = 0; kc < C::NCHUNK; ++kc) {
+          tma_load_4d(smem_a + stage * C::STAGE_STRIDE + kc * C::CHUNK_STRIDE, &tmap_in, &full_bar[stage],
+                      kc * C::CK, t.tx * CV_TILE_X - 1, t.ty * CV_TILE_Y - 1, t.n);
         }
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -118,7 +141,8 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
     // The whole warp runs the (warp-uniform) control flow so descriptors stay in uniform registers;
     // one elected lane issues the UMMAs and their commits.
     constexpr uint32_t idesc = make_idesc_bf16(128, COUT);
-    constexpr uint32_t hi = desc_hi(C::ATOM, C::SWZ);
+    constexpr uint32_t a_hi = desc_hi(C::GROUP_STRIDE, C::SWZ);   // 8-row groups one halo row apart
+    constexpr uint32_t b_hi = desc_hi(8 * C::ROWB, C::SWZ);       // dense rows
     const uint32_t a_lo0 = desc_lo(smem_u32(smem_a), 0);
     const uint32_t b_lo0 = desc_lo(smem_u32(smem_b), 0);
     mbar_wait(wload_bar, 0, 21);
@@ -128,32 +152,31 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 22);
+      mbar_wait(&full_bar[stage], phase, 23);
       tc_fence_after_sync();
-      const uint32_t d_tmem = tmem_base + acc * COUT;
-#pragma unroll
-      for (int s = 0; s < 3; ++s) {
+      if (elect_one()) {
+        const uint32_t d_tmem = tmem_base + acc * COUT;
+        const uint32_t a_stage = a_lo0 + stage * (C::STAGE_STRIDE >> 4);
 #pragma unroll
         for (int kc = 0; kc < C::NCHUNK; ++kc) {
-          mbar_wait(&full_bar[stage], phase, 23);
-          tc_fence_after_sync();
-          if (elect_one()) {
-            const uint32_t a_lo = a_lo0 + stage * (C::STAGE_BYTES >> 4);
 #pragma unroll
-            for (int r = 0; r < 3; ++r) {
-              const uint32_t b_lo = b_lo0 + ((r * 3 + s) * C::NCHUNK + kc) * (C::B_TAP_BYTES >> 4);
+          for (int r = 0; r < 3; ++r) {
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+              const uint32_t a_lo = a_stage + ((kc * C::CHUNK_STRIDE + (r * CV_HALO_X + s) * C::ROWB) >> 4);
+              const uint32_t b_lo = b_lo0 + (((r * 3 + s) * C::NCHUNK + kc) * C::B_TAP_BYTES >> 4);
 #pragma unroll
               for (int kk = 0; kk < C::CK / 16; ++kk) {
-                umma_bf16_ss_w(d_tmem, a_lo + r * (C::ATOM >> 4) + kk * 2, hi, b_lo + kk * 2, hi, idesc,
-                               (s | kc | r | kk) ? 1u : 0u);
+                umma_bf16_ss_w(d_tmem, a_lo + kk * 2, a_hi, b_lo + kk * 2, b_hi, idesc, (kc | r | s | kk) ? 1u : 0u);
               }
             }
-            umma_commit(&empty_bar[stage]);          // buffer reusable once these MMAs have read it
-            if (s == 2 && kc == C::NCHUNK - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete
           }
-          __syncwarp();
-          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
+        umma_commit(&empty_bar[stage]);   // halo buffer reusable once these MMAs have read it
+        umma_commit(&tfull_bar[acc]);     // accumulator complete -> epilogue
       }
+      __syncwarp();
+      if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
@@ -166,14 +189,12 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
     const bool odd_y = (lane >> 3) & 1;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int tx = tile % tiles_x;
-      const int ty = (tile / tiles_x) % tiles_y;
-      const int n = tile / (tiles_x * tiles_y);
-      const int py = ((ty * CV_TILE_Y + 4 * e + ly) >> 1);
-      const int px = ((tx * CV_TILE_X + lx) >> 1);
+    TileWalker t(blockIdx.x, gridDim.x, tiles_x, tiles_y);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, t.next()) {
+      const int py = ((t.ty * CV_TILE_Y + 4 * e + ly) >> 1);
+      const int px = ((t.tx * CV_TILE_X + lx) >> 1);
       const bool in_range = py < Ho && px < Wo;
-      __nv_bfloat16* orow = out + (((size_t)n * Ho + py) * Wo + px) * COUT;
+      __nv_bfloat16* orow = out + (((size_t)t.n * Ho + py) * Wo + px) * COUT;
       mbar_wait(&tfull_bar[acc], acc_phase, 24);
       tc_fence_after_sync();
       const uint32_t t_addr = tmem_base + ((uint32_t)(32 * e) << 16) + acc * COUT;
@@ -266,14 +287,14 @@ static int launch_conv3x3(const void* in, int batch, int h, int w, const void* w
   CUtensorMap tmap;
   const uint64_t dims[4] = {(uint64_t)CIN, (uint64_t)w, (uint64_t)h, (uint64_t)batch};
   const uint64_t strides[3] = {(uint64_t)CIN * 2, (uint64_t)w * CIN * 2, (uint64_t)h * w * CIN * 2};
-  const uint32_t box[4] = {(uint32_t)C::CK, CV_TILE_X, CV_HALO_ROWS, 1};
+  const uint32_t box[4] = {(uint32_t)C::CK, CV_HALO_X, CV_HALO_Y, 1};
   int rc = encode_tmap_bf16(&tmap, in, 4, dims, strides, box,
                             C::ROWB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc != 0) return rc;
   const int tiles_y = (h + CV_TILE_Y - 1) / CV_TILE_Y;
   const int tiles_x = w / CV_TILE_X;
   const int total = tiles_y * tiles_x * batch;
-  const int smem = 1024 + C::B_BYTES + NSTAGE * C::STAGE_BYTES + COUT * 4 + (2 * NSTAGE + 6) * 8;
+  const int smem = 1024 + C::B_BYTES + NSTAGE * C::STAGE_STRIDE + COUT * 4 + (2 * NSTAGE + 6) * 8;
   auto kern = conv3x3_kernel<CIN, COUT, NSTAGE>;
   static int configured = 0;
   if (int rc2 = ensure_dynamic_smem(kern, smem, &configured)) return rc2;
@@ -304,7 +325,7 @@ extern "C" int sia_conv3x3_relu_pool2(const void* in_nhwc, int batch, int h, int
   SIA_REQUIRE(aligned(in_nhwc, 16) && aligned(w_packed, 16) && aligned(out_nhwc, 16));
   if (h % 2 != 0 || w % CV_TILE_X != 0) return SIA_E_UNSUPPORTED;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (cin == 32 && cout == 64) return launch_conv3x3<32, 64, 8>(in_nhwc, batch, h, w, w_packed, bias, out_nhwc, st);
-  if (cin == 64 && cout == 128) return launch_conv3x3<64, 128, 4>(in_nhwc, batch, h, w, w_packed, bias, out_nhwc, st);
+  if (cin == 32 && cout == 64) return launch_conv3x3<32, 64, 6>(in_nhwc, batch, h, w, w_packed, bias, out_nhwc, st);
+  if (cin == 64 && cout == 128) return launch_conv3x3<64, 128, 3>(in_nhwc, batch, h, w, w_packed, bias, out_nhwc, st);
   return SIA_E_UNSUPPORTED;
 }

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     assert lib.sia_version() == 100
     assert lib.sia_error_string(-2).decode().startswith("sia:")
-    assert lib.sia_pack_conv7x7_c3_bytes() == 64 * 224 * 2
+    assert lib.sia_pack_conv7x7_c3_bytes() == 128 * 256 * 2
     assert lib.sia_pack_conv3x3_bytes(64, 128) == 9 * 64 * 128 * 2
 
 

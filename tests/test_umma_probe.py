@@ -166,27 +166,28 @@ def test_noswizzle_canonical_and_field_meaning():
 
 
 def test_noswizzle_overlapping_windows_conv1():
-    """conv1: A rows are pixel PAIRS 16 B apart in a raw [22][192 B] image patch, K-adjacent core matrix
-    = next two pixels (LBO 16 B), next 8 rows = next image row (SBO 192 B).  All 14 UMMAs of a tile."""
+    """conv1: A rows are pixel PAIRS 16 B apart in a raw [38][192 B] image patch, K-adjacent core matrix
+    = next two pixels (LBO 16 B), next 8 rows = next output-row pair = two image rows down (SBO 384 B).
+    All 16 UMMAs of a tile, N = 128 (2x2 output pixels per GEMM row)."""
     rng = np.random.default_rng(4)
-    patch = rand_int(rng, (22, 96))                # 24 px * 4 ch per row
-    bmat = rand_int(rng, (64, 224))
-    a_bytes = 4352
-    img = Image(a_bytes + 28672)
+    patch = rand_int(rng, (38, 96))                # 24 px * 4 ch per row
+    bmat = rand_int(rng, (128, 256), -2, 3)
+    a_bytes = 7424
+    img = Image(a_bytes + 65536)
     img.put_raw(0, patch)
-    img.put_core_matrices(a_bytes, bmat, 128, 3584)
+    img.put_core_matrices(a_bytes, bmat, 128, 4096)
     ad, bd = [], []
-    for r in range(7):
+    for r in range(8):
         for kk in range(2):
-            ad.append(desc(r * 192 + kk * 32, 16, 192, SW_NONE))
-            bd.append(desc(a_bytes + (r * 4 + kk * 2) * 128, 128, 3584, SW_NONE))
-    got = run(img, ad, bd, 64)
-    # expected: A[m = y*8 + xp][r*32 + j] = patch[y + r][xp*8 + j]
-    a = np.zeros((128, 224), np.float32)
-    for y in range(16):
+            ad.append(desc(r * 192 + kk * 32, 16, 384, SW_NONE))
+            bd.append(desc(a_bytes + (r * 4 + kk * 2) * 128, 128, 4096, SW_NONE))
+    got = run(img, ad, bd, 128)
+    # expected: A[m = yp*8 + xp][r*32 + j] = patch[2*yp + r][xp*8 + j]
+    a = np.zeros((128, 256), np.float32)
+    for yp in range(16):
         for xp in range(8):
-            for r in range(7):
-                a[y * 8 + xp, r * 32:(r + 1) * 32] = patch[y + r, xp * 8: xp * 8 + 32]
+            for r in range(8):
+                a[yp * 8 + xp, r * 32:(r + 1) * 32] = patch[2 * yp + r, xp * 8: xp * 8 + 32]
     ok = np.array_equal(got, a @ bmat.T)
     record("nosw_overlap_conv1", ok, True, {"maxerr": float(np.abs(got - a @ bmat.T).max())})
     assert ok
@@ -231,14 +232,14 @@ def test_exploratory_issue_rate():
         bd = [desc(16384 + kk * 32, 0, 1024, SW_128) for kk in range(4)] * 8
         _, cyc = ops.umma_probe(img.tensor(), ad, bd, n, repeat=64, want_cycles=True)
         out[f"sw128_n{n}_cycles_per_mma"] = cyc / (64 * 32)
-    patch, bmat = rand_int(rng, (22, 96)), rand_int(rng, (64, 224))
-    img = Image(4352 + 28672)
+    patch, bmat = rand_int(rng, (38, 96)), rand_int(rng, (128, 256))
+    img = Image(7424 + 65536)
     img.put_raw(0, patch)
-    img.put_core_matrices(4352, bmat, 128, 3584)
-    ad = [desc(r * 192 + kk * 32, 16, 192, SW_NONE) for r in range(7) for kk in range(2)]
-    bd = [desc(4352 + (r * 4 + kk * 2) * 128, 128, 3584, SW_NONE) for r in range(7) for kk in range(2)]
-    _, cyc = ops.umma_probe(img.tensor(), ad, bd, 64, repeat=128, want_cycles=True)
-    out["conv1_nosw_n64_cycles_per_mma"] = cyc / (128 * 14)
+    img.put_core_matrices(7424, bmat, 128, 4096)
+    ad = [desc(r * 192 + kk * 32, 16, 384, SW_NONE) for r in range(8) for kk in range(2)]
+    bd = [desc(7424 + (r * 4 + kk * 2) * 128, 128, 4096, SW_NONE) for r in range(8) for kk in range(2)]
+    _, cyc = ops.umma_probe(img.tensor(), ad, bd, 128, repeat=128, want_cycles=True)
+    out["conv1_nosw_n128_cycles_per_mma"] = cyc / (128 * 16)
     record("issue_rate", True, False, out)
 
 
@@ -287,17 +288,18 @@ def test_tma_conv3x3_halo_box(cin, swz, coords):
 
 
 @pytest.mark.parametrize("coords", [(-8, -3, 0), (56, 13, 1), (120, 29, 1)])
-def test_tma_conv1_patch_box(coords):
-    """box [24 px * 4 ch, 22 rows, 1] of the padded NHWC4 image seen as [B, H, (W+8)*4].  The innermost
+def test_tma_conv1_patch_box(coords, rows=38):
+    """box [24 px * 4 ch, 38 rows, 1] of the padded NHWC4 image seen as [B, H, (W+8)*4].  The innermost
     start must be a multiple of 8 elements (16 bytes) -- (x0-2)*4 with x0 % 16 == 0 -- an unaligned start
     raises an illegal-instruction fault (found on the first bring-up run)."""
     from skin_image_analysis_b200 import ops
     b, h, w = 2, 32, 56
     t = _coded((b, h, w * 4), 8)
-    got = ops.tma_probe(t, (w * 4, h, b), (w * 8, h * w * 8), (96, 22, 1), 0, coords)
+    n_rows = rows
+    got = ops.tma_probe(t, (w * 4, h, b), (w * 8, h * w * 8), (96, n_rows, 1), 0, coords)
     src = _bits(t)
-    rows = np.zeros((22, 96), np.uint16)
-    for yy in range(22):
+    rows = np.zeros((n_rows, 96), np.uint16)
+    for yy in range(n_rows):
         y = coords[1] + yy
         for e in range(96):
             x = coords[0] + e
@@ -329,3 +331,29 @@ def test_exploratory_alu_rates():
     _lib.check(_lib.load().sia_debug_alu_rates(out, 8))
     names = ["FFMA", "PRMT", "I2F_U8_plus_IADD", "DP4A", "DP2A", "IMAD", "SHF", "FFMA2"]
     record("alu_rates_lane_ops_per_clk_per_sm", True, False, dict(zip(names, [round(v, 1) for v in out])))
+
+
+@pytest.mark.parametrize("row_bytes,layout", [(128, SW_128), (64, SW_64)])
+def test_single_halo_copy_taps(row_bytes, layout):
+    """conv3x3 A operand: ONE [18][10]-pixel halo copy in the swizzled layout; tap (r,s) reads rows
+    (y+r)*10 + (x+s): start shifted by (r*10+s) rows, 8-row groups one halo row (10 rows) apart.  Works
+    because the swizzle XOR is taken from the absolute shared-memory address (base_offset stays 0)."""
+    rng = np.random.default_rng(row_bytes)
+    k = row_bytes // 2
+    n = 128 if row_bytes == 128 else 64
+    halo, b = rand_int(rng, (180, k)), rand_int(rng, (n, k))
+    a_bytes = (180 * row_bytes + 1023) // 1024 * 1024
+    img = Image(a_bytes + n * row_bytes)
+    img.put_rows_swizzled(0, halo, row_bytes)
+    img.put_rows_swizzled(a_bytes, b, row_bytes)
+    all_ok = True
+    for r in range(3):
+        for s in range(3):
+            shift = r * 10 + s
+            ad = [desc(shift * row_bytes + kk * 32, 0, 10 * row_bytes, layout) for kk in range(k // 16)]
+            bd = [desc(a_bytes + kk * 32, 0, 8 * row_bytes, layout) for kk in range(k // 16)]
+            got = run(img, ad, bd, n)
+            idx = np.array([(m // 8) * 10 + m % 8 + shift for m in range(128)])
+            all_ok &= bool(np.array_equal(got, halo[idx] @ b.T))
+    record(f"single_halo_taps_rowbytes{row_bytes}", all_ok, True)
+    assert all_ok
