@@ -64,6 +64,9 @@ unsigned int sia_debug_watchdog(int reset);
  * i.e. skimage.transform.resize with the reference's defaults.  The caller passes the bands:
  *   x_off[out_w]            first source column of output column j's window
  *   x_w  [out_w * x_taps]   its x_taps weights (zero padded); x_taps is 8 or 16
+ *   x_wq [out_w * 4]        optional (may be NULL): the same 8 weights as packed pairs of 15-bit fixed
+ *                           point (w*2^15, renormalised to sum to 2^15); enables the integer-dot-product
+ *                           horizontal pass for the bf16 layouts (error <= 0.03 bf16 ulp)
  *   row_w   [src_h * 4]     per SOURCE row r: weight of row r in each of the 4 accumulator slots
  *   row_emit[src_h * 4]     per SOURCE row r: output row completed in that slot after r, or -1
  *   y_first_last[out_h * 2] first and last source row that contribute to each output row
@@ -72,7 +75,8 @@ unsigned int sia_debug_watchdog(int reset);
  * rows_per_cta output rows are produced per thread block.
  * ------------------------------------------------------------------------------------------ */
 int sia_preprocess_u8hwc(const uint8_t* src, int batch, int src_h, int src_w, const int32_t* x_off,
-                         const float* x_w, int x_taps, const float* row_w, const int32_t* row_emit,
+                         const float* x_w, const uint32_t* x_wq, int x_taps, const float* row_w,
+                         const int32_t* row_emit,
                          const int32_t* y_first_last, int out_h, int out_w, const float* out_scale_host,
                          const float* out_bias_host, int layout, int rows_per_cta, void* dst, void* stream);
 

@@ -11,6 +11,14 @@
 //   horizontal pass  h[c]      = sum_t x_w[t] * u8[row][x_off + t][c]          (weights in registers)
 //   vertical pass    acc[s][c] += row_w[row][s] * h[c]   for the <=4 output rows in flight
 //   emit             when a source row completes an output row, scale/bias it and store it.
+// Two arithmetic variants of the horizontal pass (the kernel is issue-bound, not HBM-bound, so the
+// instruction mix is what matters -- rates measured on B200 by tests/test_umma_probe.py):
+//   exact : byte -> fp32 by PRMT into the mantissa of 2^23 and one FADD (I2F.U8 runs at 16 lanes/clk),
+//           fp32 FMAs.  Used for the fp32 output (parity 1e-6 with the fp64 reference filter).
+//   fast  : 15-bit fixed-point weights and IDP.2A (two u8*u16 MACs per instruction, exact integer
+//           accumulation, weights renormalised to sum to 2^15 so flat regions stay exact), one
+//           int->fp32 per channel.  Error <= 8 * 2^-16 of full scale = 0.03 bf16 ulp; used for the
+//           bf16 outputs only.
 // Nothing intermediate touches shared or global memory; source rows are staged once per CTA in a
 // 3-deep ring of shared-memory chunks by a producer warp using 1-D bulk async copies
 // (cp.async.bulk + mbarrier complete_tx), so every HBM byte is read once per row band.
@@ -30,6 +38,7 @@ struct PreParams {
   const uint8_t* src;
   const int32_t* x_off;
   const float* x_w;
+  const uint32_t* x_wq;     // fast variant: [out_w][4] packed pairs of 15-bit weights
   const float4* row_w;
   const int4* row_emit;
   const int32_t* y_first_last;
@@ -40,9 +49,10 @@ struct PreParams {
   float scale[3], bias[3];
 };
 
-template <int TX>
+template <int TX, bool FAST>
 __global__ void __launch_bounds__(PRE_THREADS)
 preprocess_kernel(const __grid_constant__ PreParams p) {
+  static_assert(!FAST || TX == 8, "the fixed-point variant is built for 8-tap windows");
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t full_bar[PRE_RING];
   __shared__ uint64_t empty_bar[PRE_RING];
@@ -101,9 +111,15 @@ preprocess_kernel(const __grid_constant__ PreParams p) {
   const int x = blockIdx.y * PRE_CONSUMERS + threadIdx.x;
   const bool active = x < p.out_w;
   const int xc = active ? x : p.out_w - 1;
-  float xw[TX];
+  float xw[FAST ? 1 : TX];
+  uint32_t xq[4] = {0u, 0u, 0u, 0u};
+  if constexpr (FAST) {
 #pragma unroll
-  for (int t = 0; t < TX; ++t) xw[t] = p.x_w[(size_t)xc * TX + t];
+    for (int t = 0; t < 4; ++t) xq[t] = p.x_wq[(size_t)xc * 4 + t];
+  } else {
+#pragma unroll
+    for (int t = 0; t < TX; ++t) xw[t] = p.x_w[(size_t)xc * TX + t];
+  }
   const int b0 = p.x_off[xc] * 3;
 
   float acc[PRE_SLOTS][3];
@@ -127,19 +143,42 @@ preprocess_kernel(const __grid_constant__ PreParams p) {
       uint32_t w[NW + 1];
 #pragma unroll
       for (int k = 0; k <= NW; ++k) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[k]) : "r"(a4 + 4u * k));
-      float h0 = 0.f, h1 = 0.f, h2 = 0.f;
+      uint32_t q[NW];       // the window, byte-aligned: q[k] = bytes 4k .. 4k+3
 #pragma unroll
-      for (int t = 0; t < TX; ++t) {
-        float v[3];
+      for (int k = 0; k < NW; ++k) q[k] = __funnelshift_r(w[k], w[k + 1], sh);
+      float h0, h1, h2;
+      if constexpr (FAST) {
+        // channel ch, taps (t, t+1): bytes 3t+ch and 3t+ch+3 -> low two bytes of one register (PRMT),
+        // then IDP.2A with the packed 15-bit weight pair; exact integer sums < 2^23
+        uint32_t acc[3] = {0u, 0u, 0u};
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
-          const int j = t * 3 + ch;
-          const uint32_t q = __funnelshift_r(w[j / 4], w[j / 4 + 1], sh);
-          v[ch] = (float)((q >> (8 * (j % 4))) & 0xffu);
+#pragma unroll
+          for (int tp = 0; tp < 4; ++tp) {
+            const int o = 6 * tp + ch;                                    // byte offset of tap 2*tp
+            const uint32_t pair = __byte_perm(q[o / 4], q[(o / 4 + 1) < NW ? o / 4 + 1 : o / 4],
+                                              (o % 4) | ((o % 4 + 3) << 4));
+            acc[ch] = __dp2a_lo(xq[tp], pair, acc[ch]);
+          }
         }
-        h0 = fmaf(xw[t], v[0], h0);
-        h1 = fmaf(xw[t], v[1], h1);
-        h2 = fmaf(xw[t], v[2], h2);
+        h0 = __uint_as_float(acc[0] | 0x4B000000u) - 8388608.0f;
+        h1 = __uint_as_float(acc[1] | 0x4B000000u) - 8388608.0f;
+        h2 = __uint_as_float(acc[2] | 0x4B000000u) - 8388608.0f;
+      } else {
+        h0 = h1 = h2 = 0.f;
+#pragma unroll
+        for (int t = 0; t < TX; ++t) {
+          float v[3];
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) {
+            const int j = t * 3 + ch;
+            // byte -> low mantissa byte of 2^23, then subtract 2^23: exact, two full-rate instructions
+            v[ch] = __uint_as_float(__byte_perm(q[j / 4], 0x4B000000u, 0x7650 | (j % 4))) - 8388608.0f;
+          }
+          h0 = fmaf(xw[t], v[0], h0);
+          h1 = fmaf(xw[t], v[1], h1);
+          h2 = fmaf(xw[t], v[2], h2);
+        }
       }
       // ---- vertical pass: scatter into the output rows in flight ----------------------------
       const float4 rw = p.row_w[r];
@@ -196,8 +235,8 @@ preprocess_kernel(const __grid_constant__ PreParams p) {
 }  // namespace sia
 
 extern "C" int sia_preprocess_u8hwc(const uint8_t* src, int batch, int src_h, int src_w, const int32_t* x_off,
-                                    const float* x_w, int x_taps, const float* row_w, const int32_t* row_emit,
-                                    const int32_t* y_first_last, int out_h, int out_w,
+                                    const float* x_w, const uint32_t* x_wq, int x_taps, const float* row_w,
+                                    const int32_t* row_emit, const int32_t* y_first_last, int out_h, int out_w,
                                     const float* out_scale_host, const float* out_bias_host, int layout,
                                     int rows_per_cta, void* dst, void* stream) {
   using namespace sia;
@@ -207,10 +246,10 @@ extern "C" int sia_preprocess_u8hwc(const uint8_t* src, int batch, int src_h, in
   SIA_REQUIRE(aligned(row_w, 16) && aligned(row_emit, 16) && aligned(dst, 16));
   if (x_taps != 8 && x_taps != 16) return SIA_E_UNSUPPORTED;
   if (batch > 65535) return SIA_E_UNSUPPORTED;
-
   if (int wrc = ensure_watchdog()) return wrc;
+
   PreParams p;
-  p.src = src; p.x_off = x_off; p.x_w = x_w;
+  p.src = src; p.x_off = x_off; p.x_w = x_w; p.x_wq = x_wq;
   p.row_w = reinterpret_cast<const float4*>(row_w);
   p.row_emit = reinterpret_cast<const int4*>(row_emit);
   p.y_first_last = y_first_last;
@@ -233,14 +272,21 @@ extern "C" int sia_preprocess_u8hwc(const uint8_t* src, int batch, int src_h, in
   const int smem = PRE_RING * p.chunk_stride;
   dim3 grid((out_h + rows_per_cta - 1) / rows_per_cta, (out_w + PRE_CONSUMERS - 1) / PRE_CONSUMERS, batch);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (x_taps == 8) {
+  // fixed-point horizontal pass only where its 0.03-ulp error is invisible: the bf16 outputs
+  const bool fast = x_wq != nullptr && x_taps == 8 && layout != SIA_LAYOUT_NCHW_F32;
+  if (fast) {
+    for (int c = 0; c < 3; ++c) p.scale[c] *= (1.0f / 32768.0f);   // the integer pass carries a 2^15 factor
     static int configured = 0;
-    if (int rc2 = ensure_dynamic_smem(preprocess_kernel<8>, smem, &configured)) return rc2;
-    preprocess_kernel<8><<<grid, PRE_THREADS, smem, st>>>(p);
+    if (int rc2 = ensure_dynamic_smem(preprocess_kernel<8, true>, smem, &configured)) return rc2;
+    preprocess_kernel<8, true><<<grid, PRE_THREADS, smem, st>>>(p);
+  } else if (x_taps == 8) {
+    static int configured = 0;
+    if (int rc2 = ensure_dynamic_smem(preprocess_kernel<8, false>, smem, &configured)) return rc2;
+    preprocess_kernel<8, false><<<grid, PRE_THREADS, smem, st>>>(p);
   } else {
     static int configured = 0;
-    if (int rc2 = ensure_dynamic_smem(preprocess_kernel<16>, smem, &configured)) return rc2;
-    preprocess_kernel<16><<<grid, PRE_THREADS, smem, st>>>(p);
+    if (int rc2 = ensure_dynamic_smem(preprocess_kernel<16, false>, smem, &configured)) return rc2;
+    preprocess_kernel<16, false><<<grid, PRE_THREADS, smem, st>>>(p);
   }
   return launch_status();
 }

@@ -41,6 +41,7 @@ class _DeviceTables:
         self.host = t
         self.x_off = torch.from_numpy(t.x_off).to(device)
         self.x_w = torch.from_numpy(np.ascontiguousarray(t.x_w)).to(device)
+        self.x_wq = None if t.x_wq is None else torch.from_numpy(t.x_wq.view(np.int32).copy()).to(device)
         self.row_w = torch.from_numpy(np.ascontiguousarray(t.row_w)).to(device)
         self.row_emit = torch.from_numpy(np.ascontiguousarray(t.row_emit)).to(device)
         self.y_first_last = torch.from_numpy(np.ascontiguousarray(t.y_first_last)).to(device)
@@ -57,11 +58,14 @@ _LAYOUT_DTYPE = {LAYOUT_NCHW_F32: torch.float32, LAYOUT_NCHW_BF16: torch.bfloat1
 
 def preprocess_u8hwc(src: torch.Tensor, size, layout: int = LAYOUT_NCHW_F32, mean=(0.0, 0.0, 0.0),
                      std=(1.0, 1.0, 1.0), scale: float = 1.0 / 255.0, antialias="skimage",
-                     rows_per_cta: int = 32, out: torch.Tensor | None = None) -> torch.Tensor:
+                     rows_per_cta: int = 32, out: torch.Tensor | None = None,
+                     fixed_point: bool = True) -> torch.Tensor:
     """[B,H,W,3] uint8 -> resized / scaled / normalised batch in ``layout``.
 
     Defaults reproduce the reference transform exactly: ``float32(u8)/255`` (tone_bias_dataset.py:335),
-    ``skimage.transform.resize`` (:425), no mean/std, CHW (:470).
+    ``skimage.transform.resize`` (:425), no mean/std, CHW (:470).  ``fixed_point`` lets the bf16 layouts
+    use the 15-bit integer-dot-product horizontal pass (<= 0.03 bf16 ulp from the fp32 pass); the fp32
+    layout always uses fp32 arithmetic.
     """
     _need(src, torch.uint8, "src")
     if src.dim() != 4 or src.shape[3] != 3:
@@ -79,7 +83,8 @@ def preprocess_u8hwc(src: torch.Tensor, size, layout: int = LAYOUT_NCHW_F32, mea
     osc = (ctypes.c_float * 3)(*[1.0 / float(s) for s in std])
     obi = (ctypes.c_float * 3)(*[-float(m) / float(s) for m, s in zip(mean, std)])
     check(_lib.load().sia_preprocess_u8hwc(
-        ptr(src), b, sh, sw, ptr(tab.x_off), ptr(tab.x_w), tab.host.x_taps, ptr(tab.row_w), ptr(tab.row_emit),
+        ptr(src), b, sh, sw, ptr(tab.x_off), ptr(tab.x_w), ptr(tab.x_wq) if fixed_point else 0, tab.host.x_taps,
+        ptr(tab.row_w), ptr(tab.row_emit),
         ptr(tab.y_first_last), oh, ow, osc, obi, layout, int(rows_per_cta), ptr(out), stream_ptr()),
         "sia_preprocess_u8hwc")
     return out

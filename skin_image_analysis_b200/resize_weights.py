@@ -81,6 +81,25 @@ def axis_bands(n_in: int, n_out: int, antialias: bool, min_taps: int = 1):
     return off, w
 
 
+X_FIXED_ONE = 1 << 15
+
+
+def quantise_x_weights(x_w: np.ndarray) -> np.ndarray | None:
+    """[out_w, 8] float64 -> [out_w, 4] uint32 of packed 15-bit fixed-point pairs (w[2i] | w[2i+1] << 16)
+    for the IDP.2A horizontal pass.  Each row is renormalised to sum to exactly 2^15 (the largest weight
+    absorbs the rounding residue), so a flat image stays exactly flat.  None if a weight is negative."""
+    if x_w.shape[1] != 8 or np.any(x_w < 0):
+        return None
+    q = np.rint(x_w * X_FIXED_ONE).astype(np.int64)
+    target = np.rint(x_w.sum(1) * X_FIXED_ONE).astype(np.int64)
+    rows = np.arange(q.shape[0])
+    q[rows, q.argmax(1)] += target - q.sum(1)
+    if np.any(q < 0) or np.any(q > 0xFFFF):
+        return None
+    q = q.astype(np.uint32)
+    return (q[:, 0::2] | (q[:, 1::2] << np.uint32(16))).astype(np.uint32)
+
+
 @dataclass
 class ResizeTables:
     src_h: int
@@ -90,6 +109,7 @@ class ResizeTables:
     x_taps: int
     x_off: np.ndarray          # int32 [out_w]
     x_w: np.ndarray            # float32 [out_w, x_taps]
+    x_wq: np.ndarray | None    # uint32 [out_w, 4]: packed pairs of 15-bit weights (8-tap windows only)
     row_w: np.ndarray          # float32 [src_h, 4]
     row_emit: np.ndarray       # int32 [src_h, 4]
     y_first_last: np.ndarray   # int32 [out_h, 2]
@@ -134,6 +154,7 @@ def build_tables(src_h: int, src_w: int, out_h: int, out_w: int, scale: float = 
     if np.any(np.diff(y_first_last[:, 0]) < 0) or np.any(np.diff(y_first_last[:, 1]) < 0):
         raise ValueError("vertical windows are not monotonic: unsupported geometry")
     t = ResizeTables(src_h, src_w, out_h, out_w, x_taps, x_off.astype(np.int32), x_w.astype(np.float32),
+                     quantise_x_weights(x_w) if x_taps == 8 else None,
                      row_w.astype(np.float32), row_emit, y_first_last)
     if keep_dense:
         wy = np.zeros((out_h, src_h))

@@ -49,19 +49,33 @@ def test_reference_fixture_cases(golden_dir):
         assert np.abs(sub - ref).max() <= F32_TOL, name
 
 
-def test_bf16_layouts_within_one_ulp():
+@pytest.mark.parametrize("fixed_point", [False, True])
+def test_bf16_layouts_within_one_ulp(fixed_point):
+    """bf16 outputs: fp32 arithmetic (fixed_point=False) and the 15-bit integer-dot-product horizontal
+    pass (the default for bf16) both stay within one bf16 ulp of the bf16-rounded oracle."""
     from skin_image_analysis_b200 import ops
-    imgs = [helpers.synthetic_u8_image(450, 600, 200 + i, "smooth") for i in range(2)]
+    imgs = [helpers.synthetic_u8_image(450, 600, 200 + i, k) for i, k in enumerate(["smooth", "noise"])]
     want = np.stack([R.transform_u8(im, (224, 224)) for im in imgs])
     want_bf = torch.from_numpy(want).to(torch.bfloat16).float().numpy()
-    nchw = _gpu(imgs, (224, 224), ops.LAYOUT_NCHW_BF16).float().cpu().numpy()
-    nhwc4 = _gpu(imgs, (224, 224), ops.LAYOUT_NHWC4_BF16).float().cpu().numpy()
+    nchw = _gpu(imgs, (224, 224), ops.LAYOUT_NCHW_BF16, fixed_point=fixed_point).float().cpu().numpy()
+    nhwc4 = _gpu(imgs, (224, 224), ops.LAYOUT_NHWC4_BF16, fixed_point=fixed_point).float().cpu().numpy()
     assert nhwc4.shape == (2, 224, 224 + ops.NHWC4_PAD, 4) and np.all(nhwc4[..., 3] == 0)
     assert np.all(nhwc4[:, :, 0] == 0) and np.all(nhwc4[:, :, 225:] == 0)        # zero pad columns
     assert np.array_equal(nhwc4[:, :, 1:225, :3].transpose(0, 3, 1, 2), nchw)
     ulp = np.maximum(np.abs(want_bf), 2.0 ** -126) * 2.0 ** -7
     assert np.all(np.abs(nchw - want_bf) <= ulp)
-    assert (nchw != want_bf).mean() < 0.01          # the fp32 math differs from fp64 only near ties
+    # before rounding the two arithmetic variants differ from the oracle by <= 1e-6 / <= 2.5e-4 of full scale
+    assert np.abs(nchw - want).max() <= 2.0 ** -8 + (2.5e-4 if fixed_point else 1e-6)
+    assert (nchw != want_bf).mean() < (0.25 if fixed_point else 0.01)
+
+
+def test_fixed_point_pass_keeps_flat_images_exact():
+    from skin_image_analysis_b200 import ops
+    for v in (0, 1, 127, 200, 255):
+        const = np.full((450, 600, 3), v, np.uint8)
+        out = _gpu([const], (224, 224), ops.LAYOUT_NCHW_BF16)[0].float().cpu().numpy()
+        want = torch.tensor(np.float32(v) / 255.0).to(torch.bfloat16).float().item()
+        assert np.all(out == want), v
 
 
 def test_mean_std_and_rows_per_cta_invariance():
