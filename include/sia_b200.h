@@ -156,6 +156,11 @@ int sia_debug_tma_probe(const void* base, int rank, const uint64_t* dims_host, c
                         const uint32_t* box_host, int swizzle_bytes, const int* coords_host, void* out,
                         void* stream);
 
+/* Debug: per-CTA role timing of the conv kernels.  device_buffer holds 8 uint64 per CTA (SM-clock cycles:
+ * producer wait-for-stage, MMA wait-for-accumulator, MMA wait-for-operands, MMA loop, epilogue
+ * wait-for-accumulator, epilogue loop, tiles); NULL switches the instrumentation off (default). */
+int sia_debug_set_stats(unsigned long long* device_buffer_or_null);
+
 /* Debug / bring-up: lane-operations per SM clock (one resident CTA of 1024 threads) for
  * FFMA, PRMT, I2F.U8(+IADD), DP4A, DP2A, IMAD, SHF, FFMA2 -- out_host needs room for 8 doubles. */
 int sia_debug_alu_rates(double* out_host, int n);

@@ -115,8 +115,11 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
       int stage = 0;
       uint32_t phase = 0;
       TileWalker1 t(blockIdx.x, gridDim.x, tiles_x, tiles_y);
+      RoleTimer wait_stage;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, t.next()) {
+        wait_stage.begin();
         mbar_wait(&empty_bar[stage], phase ^ 1, 30);
+        wait_stage.end();
         mbar_arrive_expect_tx(&full_bar[stage], C1_STAGE_BYTES);
         // innermost coordinate is in bf16 elements (4 per pixel) and must be 16-byte aligned for TMA:
         // image pixel x sits in column x+1 of the padded row, so the window start x0-3 is column x0-2
@@ -124,6 +127,7 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
                     t.ty * C1_TILE_Y - 3, t.n);
         if (++stage == C1_NSTAGE) { stage = 0; phase ^= 1; }
       }
+      wait_stage.store(0);
     }
   } else if (warp == 1) {
     // whole warp runs the uniform control flow; one elected lane issues UMMAs + commits
@@ -139,9 +143,15 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    RoleTimer wait_acc, wait_ops, loop;
+    loop.begin();
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      wait_acc.begin();
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 32);
+      wait_acc.end();
+      wait_ops.begin();
       mbar_wait(&full_bar[stage], phase, 33);
+      wait_ops.end();
       tc_fence_after_sync();
       if (elect_one()) {
         const uint32_t d_tmem = tmem_base + acc * C1_N;
@@ -161,6 +171,8 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
       if (++stage == C1_NSTAGE) { stage = 0; phase ^= 1; }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    loop.end();
+    if (lane == 0) { wait_acc.store(1); wait_ops.store(2); loop.store(3); }
   } else if (warp >= 4) {
     // epilogue: thread = one GEMM row = one pooled output pixel, 32 channels
     const int e = warp - 4;
@@ -170,12 +182,18 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
     int acc = 0;
     uint32_t acc_phase = 0;
     TileWalker1 t(blockIdx.x, gridDim.x, tiles_x, tiles_y);
+    RoleTimer wait_full, eloop;
+    unsigned long long ntiles = 0;
+    eloop.begin();
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, t.next()) {
+      ++ntiles;
       const int py = t.ty * (C1_TILE_Y / 2) + yp;
       const int px = t.tx * (C1_TILE_X / 2) + xp;
       const bool in_range = py < Ho && px < Wo;
       uint4* opix = reinterpret_cast<uint4*>(out + (((size_t)t.n * Ho + py) * Wo + px) * 32);
+      wait_full.begin();
       mbar_wait(&tfull_bar[acc], acc_phase, 34);
+      wait_full.end();
       tc_fence_after_sync();
       const uint32_t t_addr = tmem_base + ((uint32_t)(32 * e) << 16) + acc * C1_N;
 
@@ -215,6 +233,12 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);   // the whole accumulator is in registers now
       finish_half(b0, b1, b2, b3, 1);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    eloop.end();
+    if (warp == 4 && lane == 0) {
+      wait_full.store(4);
+      eloop.store(5);
+      if (g_stats) g_stats[blockIdx.x * 8 + 6] = ntiles;
     }
   }
 

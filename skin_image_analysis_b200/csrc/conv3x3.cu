@@ -125,8 +125,11 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
       int stage = 0;
       uint32_t phase = 0;
       TileWalker t(blockIdx.x, gridDim.x, tiles_x, tiles_y);
+      RoleTimer wait_stage;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, t.next()) {
+        wait_stage.begin();
         mbar_wait(&empty_bar[stage], phase ^ 1, 20);
+        wait_stage.end();
         mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_TX_BYTES);
 #pragma unroll
         for (int kc = 0; kc < C::NCHUNK; ++kc) {
@@ -135,6 +138,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
         }
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
       }
+      wait_stage.store(0);
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ============================================
@@ -150,9 +154,15 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    RoleTimer wait_acc, wait_ops, loop;
+    loop.begin();
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      wait_acc.begin();
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 22);
+      wait_acc.end();
+      wait_ops.begin();
       mbar_wait(&full_bar[stage], phase, 23);
+      wait_ops.end();
       tc_fence_after_sync();
       if (elect_one()) {
         const uint32_t d_tmem = tmem_base + acc * COUT;
@@ -179,6 +189,8 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
       if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    loop.end();
+    if (lane == 0) { wait_acc.store(1); wait_ops.store(2); loop.store(3); }
   } else if (warp >= 4) {
     // ================================ epilogue ==============================================
     const int e = warp - 4;                   // TMEM lanes 32e .. 32e+31
@@ -190,12 +202,18 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
     int acc = 0;
     uint32_t acc_phase = 0;
     TileWalker t(blockIdx.x, gridDim.x, tiles_x, tiles_y);
+    RoleTimer wait_full, eloop;
+    unsigned long long ntiles = 0;
+    eloop.begin();
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, t.next()) {
+      ++ntiles;
       const int py = ((t.ty * CV_TILE_Y + 4 * e + ly) >> 1);
       const int px = ((t.tx * CV_TILE_X + lx) >> 1);
       const bool in_range = py < Ho && px < Wo;
       __nv_bfloat16* orow = out + (((size_t)t.n * Ho + py) * Wo + px) * COUT;
+      wait_full.begin();
       mbar_wait(&tfull_bar[acc], acc_phase, 24);
+      wait_full.end();
       tc_fence_after_sync();
       const uint32_t t_addr = tmem_base + ((uint32_t)(32 * e) << 16) + acc * COUT;
 
@@ -248,6 +266,12 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
         finish_chunk(vb, cb + 32);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    eloop.end();
+    if (warp == 4 && lane == 0) {
+      wait_full.store(4);
+      eloop.store(5);
+      if (g_stats) g_stats[blockIdx.x * 8 + 6] = ntiles;
     }
   }
 

@@ -19,6 +19,20 @@ namespace sia {
 // host word survives and sia_debug_watchdog() can still say which wait timed out.
 static __device__ volatile unsigned int* g_watchdog_word = nullptr;
 
+// Optional per-CTA role timing (sia_debug_set_stats): 8 counters per CTA, SM clock cycles.
+//   0 producer: waiting for a free stage      1 MMA: waiting for a free accumulator
+//   2 MMA: waiting for operands (TMA)         3 MMA: whole loop
+//   4 epilogue warp 4: waiting for tfull      5 epilogue warp 4: whole loop      6 tiles done by this CTA
+static __device__ unsigned long long* g_stats = nullptr;
+
+struct RoleTimer {
+  unsigned long long acc = 0;
+  long long t0 = 0;
+  __device__ __forceinline__ void begin() { if (g_stats) t0 = clock64(); }
+  __device__ __forceinline__ void end() { if (g_stats) acc += (unsigned long long)(clock64() - t0); }
+  __device__ __forceinline__ void store(int slot) { if (g_stats) g_stats[blockIdx.x * 8 + slot] = acc; }
+};
+
 #ifndef SIA_WATCHDOG_SPINS
 #define SIA_WATCHDOG_SPINS (1u << 24)
 #endif

@@ -232,6 +232,22 @@ def test_exploratory_issue_rate():
         bd = [desc(16384 + kk * 32, 0, 1024, SW_128) for kk in range(4)] * 8
         _, cyc = ops.umma_probe(img.tensor(), ad, bd, n, repeat=64, want_cycles=True)
         out[f"sw128_n{n}_cycles_per_mma"] = cyc / (64 * 32)
+    # 64-byte rows (conv 32->64) and the single-halo addressing (8-row groups one halo row apart)
+    for name, rb, lay, n, shift, sbo in (("sw64_n64_aligned", 64, SW_64, 64, 0, 8 * 64),
+                                         ("sw64_n64_halo_shift11", 64, SW_64, 64, 11, 10 * 64),
+                                         ("sw64_n64_halo_shift0", 64, SW_64, 64, 0, 10 * 64),
+                                         ("sw128_n128_halo_shift11", 128, SW_128, 128, 11, 10 * 128),
+                                         ("sw128_n64_halo_shift11", 128, SW_128, 64, 11, 10 * 128)):
+        k = rb // 2
+        halo, b = rand_int(rng, (200, k)), rand_int(rng, (n, k))
+        a_bytes = (200 * rb + 1023) // 1024 * 1024
+        img = Image(a_bytes + n * rb)
+        img.put_rows_swizzled(0, halo, rb)
+        img.put_rows_swizzled(a_bytes, b, rb)
+        ad = [desc(shift * rb + kk * 32, 0, sbo, lay) for kk in range(k // 16)] * (32 // (k // 16))
+        bd = [desc(a_bytes + kk * 32, 0, 8 * rb, lay) for kk in range(k // 16)] * (32 // (k // 16))
+        _, cyc = ops.umma_probe(img.tensor(), ad, bd, n, repeat=64, want_cycles=True)
+        out[name + "_cycles_per_mma"] = cyc / (64 * 32)
     patch, bmat = rand_int(rng, (38, 96)), rand_int(rng, (128, 256))
     img = Image(7424 + 65536)
     img.put_raw(0, patch)
