@@ -36,7 +36,9 @@ constexpr int C1_N = 128;
 constexpr int C1_K = 256;                    // 8 window rows * 32
 constexpr int C1_B_BYTES = C1_N * C1_K * 2;  // 65536
 constexpr int C1_B_SBO = (C1_K / 8) * 128;   // 4096: next group of 8 B rows
-constexpr int C1_THREADS = 256;
+constexpr int C1_NACC = 4;                   // TMEM accumulator ring (4 x 128 columns)
+constexpr int C1_THREADS = 384;              // warps 0-3 TMA / MMA / TMEM alloc / idle, 4-7 and 8-11 epilogue groups
+constexpr int C1_BIAS_BYTES = C1_N * 32;
 
 struct TileWalker1 {
   int tx, ty, n, dtx, dty, dn, tiles_x, tiles_y;
@@ -76,14 +78,15 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_b = smem;                                   // 65536
   uint8_t* smem_a = smem + C1_B_BYTES;                      // NSTAGE * STRIDE
-  float* smem_bias = reinterpret_cast<float*>(smem_a + C1_NSTAGE * C1_STAGE_STRIDE);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_bias + 32);
+  uint8_t* smem_ones = smem_a + C1_NSTAGE * C1_STAGE_STRIDE;
+  uint8_t* smem_biasop = smem_ones + ONES_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_biasop + C1_BIAS_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + C1_NSTAGE;
   uint64_t* tfull_bar = bars + 2 * C1_NSTAGE;
-  uint64_t* tempty_bar = bars + 2 * C1_NSTAGE + 2;
-  uint64_t* wload_bar = bars + 2 * C1_NSTAGE + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C1_NSTAGE + 5);
+  uint64_t* tempty_bar = bars + 2 * C1_NSTAGE + C1_NACC;
+  uint64_t* wload_bar = bars + 2 * C1_NSTAGE + 2 * C1_NACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C1_NSTAGE + 2 * C1_NACC + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -93,7 +96,7 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < C1_NACC; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 4);
     }
@@ -101,8 +104,11 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
     fence_mbar_init();
     tma_prefetch_desc(&tmap_in);
   }
-  if (warp == 2) tmem_alloc(tmem_slot, 2 * C1_N);
-  if (threadIdx.x < 32) smem_bias[threadIdx.x] = bias[threadIdx.x];
+  if (warp == 2) tmem_alloc(tmem_slot, C1_NACC * C1_N);
+  // the bias enters through the tensor core (see conv3x3.cu): row n = (dy*2+dx)*32 + co -> bias[co]
+  fill_ones_operand(smem_ones, threadIdx.x, blockDim.x);
+  fill_bias_operand(smem_biasop, bias, C1_N, 32, threadIdx.x, blockDim.x);
+  fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -136,8 +142,11 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
     //    next output-row pair = two image rows down (SBO).  B: canonical no-swizzle, contiguous along K.
     constexpr uint32_t a_hi = desc_hi(2 * C1_ROWB, SW_NONE);
     constexpr uint32_t b_hi = desc_hi(C1_B_SBO, SW_NONE);
+    constexpr uint32_t c_hi = desc_hi(256, SW_NONE);
     const uint32_t a_lo0 = desc_lo(smem_u32(smem_a), 16);
     const uint32_t b_lo0 = desc_lo(smem_u32(smem_b), 128);
+    const uint32_t ones_lo = desc_lo(smem_u32(smem_ones), 128);
+    const uint32_t bias_lo = desc_lo(smem_u32(smem_biasop), 128);
     mbar_wait(wload_bar, 0, 31);
     int stage = 0;
     uint32_t phase = 0;
@@ -156,12 +165,13 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
       if (elect_one()) {
         const uint32_t d_tmem = tmem_base + acc * C1_N;
         const uint32_t a_lo = a_lo0 + stage * (C1_STAGE_STRIDE >> 4);
+        umma_bf16_ss_w(d_tmem, ones_lo, c_hi, bias_lo, c_hi, idesc, 0u);     // D = bias
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
 #pragma unroll
           for (int kk = 0; kk < 2; ++kk) {
             umma_bf16_ss_w(d_tmem, a_lo + r * (C1_ROWB >> 4) + kk * 2, a_hi, b_lo0 + (r * 4 + kk * 2) * 8, b_hi, idesc,
-                           (r | kk) ? 1u : 0u);
+                           1u);
           }
         }
         umma_commit(&empty_bar[stage]);
@@ -169,24 +179,27 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
       }
       __syncwarp();
       if (++stage == C1_NSTAGE) { stage = 0; phase ^= 1; }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == C1_NACC) { acc = 0; acc_phase ^= 1; }
     }
     loop.end();
     if (lane == 0) { wait_acc.store(1); wait_ops.store(2); loop.store(3); }
   } else if (warp >= 4) {
-    // epilogue: thread = one GEMM row = one pooled output pixel, 32 channels
-    const int e = warp - 4;
+    // epilogue: thread = one GEMM row = one pooled output pixel, 32 channels.  Two groups of four warps;
+    // group g owns the tiles with local index j = g, g+2, ...
+    const int group = (warp - 4) >> 2;
+    const int e = (warp - 4) & 3;
     const int Ho = H >> 1, Wo = W >> 1;
     const int yp = 4 * e + (lane >> 3);
     const int xp = lane & 7;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    TileWalker1 t(blockIdx.x, gridDim.x, tiles_x, tiles_y);
+    TileWalker1 t(blockIdx.x + group * gridDim.x, 2 * gridDim.x, tiles_x, tiles_y);
     RoleTimer wait_full, eloop;
     unsigned long long ntiles = 0;
     eloop.begin();
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, t.next()) {
+    int j = group;
+    for (int tile = blockIdx.x + group * gridDim.x; tile < total_tiles; tile += 2 * gridDim.x, t.next(), j += 2) {
       ++ntiles;
+      const int acc = j % C1_NACC;
+      const uint32_t acc_phase = (j / C1_NACC) & 1;
       const int py = t.ty * (C1_TILE_Y / 2) + yp;
       const int px = t.tx * (C1_TILE_X / 2) + xp;
       const bool in_range = py < Ho && px < Wo;
@@ -197,18 +210,19 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
       tc_fence_after_sync();
       const uint32_t t_addr = tmem_base + ((uint32_t)(32 * e) << 16) + acc * C1_N;
 
-      // max over the 2x2 window (4 column groups), + bias, ReLU, bf16; 16 channels -> 2 x 16-byte stores
+      // max over the 2x2 window (4 column groups; the bias is already in the accumulator), ReLU, bf16;
+      // 16 channels -> 2 x 16-byte stores
       auto finish_half = [&](const uint32_t (&q0)[16], const uint32_t (&q1)[16], const uint32_t (&q2)[16],
                              const uint32_t (&q3)[16], int half) {
         uint32_t pk[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int c = 2 * j;
+        for (int c2 = 0; c2 < 8; ++c2) {
+          const int c = 2 * c2;
           const float a = fmaxf(fmaxf(__uint_as_float(q0[c]), __uint_as_float(q1[c])),
                                 fmaxf(__uint_as_float(q2[c]), __uint_as_float(q3[c])));
           const float b = fmaxf(fmaxf(__uint_as_float(q0[c + 1]), __uint_as_float(q1[c + 1])),
                                 fmaxf(__uint_as_float(q2[c + 1]), __uint_as_float(q3[c + 1])));
-          pk[j] = pack_bf16x2(fmaxf(a + smem_bias[16 * half + c], 0.f), fmaxf(b + smem_bias[16 * half + c + 1], 0.f));
+          pk[c2] = max_bf16x2(pack_bf16x2(a, b), 0u);
         }
         if (in_range) {
           opix[2 * half] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -232,7 +246,6 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);   // the whole accumulator is in registers now
       finish_half(b0, b1, b2, b3, 1);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     eloop.end();
     if (warp == 4 && lane == 0) {
@@ -244,7 +257,7 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 2) tmem_free(tmem_base, 2 * C1_N);
+  if (warp == 2) tmem_free(tmem_base, C1_NACC * C1_N);
 }
 
 // [32][3][7][7] fp32 -> B[n = (dy*2+dx)*32 + co][k = r'*32 + xw*4 + c] = W[co][c][r'-dy][xw-dx], bf16, in
@@ -292,7 +305,8 @@ extern "C" int sia_conv7x7_c3_relu_pool2(const void* in_nhwc4, int batch, int h,
   if (rc != 0) return rc;
   const int tiles_y = (h + C1_TILE_Y - 1) / C1_TILE_Y, tiles_x = w / C1_TILE_X;
   const int total = tiles_y * tiles_x * batch;
-  const int smem = 1024 + C1_B_BYTES + C1_NSTAGE * C1_STAGE_STRIDE + 32 * 4 + (2 * C1_NSTAGE + 6) * 8;
+  const int smem = 1024 + C1_B_BYTES + C1_NSTAGE * C1_STAGE_STRIDE + ONES_BYTES + C1_BIAS_BYTES +
+                   (2 * C1_NSTAGE + 2 * C1_NACC + 2) * 8;
   static int configured = 0;
   if (int rc2 = ensure_dynamic_smem(conv1_kernel, smem, &configured)) return rc2;
   const int grid = total < sm_count() ? total : sm_count();

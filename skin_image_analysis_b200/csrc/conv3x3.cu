@@ -31,7 +31,10 @@ constexpr int CV_TILE_X = 8;
 constexpr int CV_HALO_Y = CV_TILE_Y + 2;
 constexpr int CV_HALO_X = CV_TILE_X + 2;
 constexpr int CV_HALO_ROWS = CV_HALO_Y * CV_HALO_X;   // 180 pixels
-constexpr int CV_THREADS = 256;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-7 epilogue
+constexpr int CV_NACC = 4;       // TMEM accumulator ring
+constexpr int CV_THREADS = 384;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle,
+                                 // warps 4-7 epilogue group 0 (even tiles), warps 8-11 group 1 (odd tiles)
+constexpr int ONES_BYTES = 4096;                      // [128 rows][16 k] bf16, no-swizzle core matrices
 
 template <int CIN, int COUT>
 struct ConvCfg {
@@ -46,7 +49,9 @@ struct ConvCfg {
   static constexpr int STAGE_TX_BYTES = NCHUNK * CHUNK_BYTES;
   static constexpr int B_TAP_BYTES = COUT * ROWB;       // one (tap, chunk) weight block
   static constexpr int B_BYTES = 9 * NCHUNK * B_TAP_BYTES;
-  static constexpr int TMEM_COLS = 2 * COUT;
+  static constexpr int BIAS_BYTES = COUT * 32;          // [COUT rows][16 k] bf16: k0 = hi(bias), k1 = lo(bias)
+  static constexpr int TMEM_COLS = CV_NACC * COUT;
+  static_assert(TMEM_COLS <= 512, "accumulator ring does not fit TMEM");
 };
 
 // Decomposes the persistent-CTA tile stride once, so that walking tiles needs no integer division.
@@ -69,6 +74,31 @@ struct TileWalker {
   }
 };
 
+// The bias enters through the tensor core: the first UMMA of every tile multiplies a constant "ones"
+// operand (columns 0,1 = 1) with [hi(bias), lo(bias)] (bias split into two bf16 so that hi+lo carries 16
+// mantissa bits) and INITIALISES the accumulator with it.  The epilogue is left with ReLU + pool + pack.
+__device__ __forceinline__ void fill_ones_operand(uint8_t* ones, int tid, int nthreads) {
+  // element (r,k) at (r/8)*256 + (k/8)*128 + (r%8)*16 + (k%8)*2 ; k in {0,1} -> 1.0
+  for (int i = tid; i < ONES_BYTES / 4; i += nthreads) {
+    const int byte = i * 4;
+    const int k = ((byte >> 7) & 1) * 8 + ((byte & 15) >> 1);
+    reinterpret_cast<uint32_t*>(ones)[i] = (k == 0) ? 0x3F803F80u : 0u;   // bf16 1.0 in k = 0 and k = 1
+  }
+}
+__device__ __forceinline__ void fill_bias_operand(uint8_t* dst, const float* bias, int n_rows, int bias_mod, int tid,
+                                                  int nthreads) {
+  for (int r = tid; r < n_rows; r += nthreads) {
+    const float b = bias[r % bias_mod];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(b);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(b - __bfloat162float(hi));
+    uint32_t* row = reinterpret_cast<uint32_t*>(dst + (r / 8) * 256 + (r % 8) * 16);
+    row[0] = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+    row[1] = row[2] = row[3] = 0u;
+    uint32_t* row_k8 = reinterpret_cast<uint32_t*>(dst + (r / 8) * 256 + 128 + (r % 8) * 16);
+    row_k8[0] = row_k8[1] = row_k8[2] = row_k8[3] = 0u;
+  }
+}
+
 template <int CIN, int COUT, int NSTAGE>
 __global__ void __launch_bounds__(CV_THREADS, 1)
 conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restrict__ w_packed,
@@ -80,14 +110,15 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_b = smem;                               // B_BYTES (multiple of 1024)
   uint8_t* smem_a = smem + C::B_BYTES;                  // NSTAGE * STAGE_STRIDE
-  float* smem_bias = reinterpret_cast<float*>(smem_a + NSTAGE * C::STAGE_STRIDE);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_bias + COUT);
+  uint8_t* smem_ones = smem_a + NSTAGE * C::STAGE_STRIDE;
+  uint8_t* smem_biasop = smem_ones + ONES_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_biasop + C::BIAS_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + NSTAGE;
   uint64_t* tfull_bar = bars + 2 * NSTAGE;
-  uint64_t* tempty_bar = bars + 2 * NSTAGE + 2;
-  uint64_t* wload_bar = bars + 2 * NSTAGE + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 5);
+  uint64_t* tempty_bar = bars + 2 * NSTAGE + CV_NACC;
+  uint64_t* wload_bar = bars + 2 * NSTAGE + 2 * CV_NACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 2 * CV_NACC + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -97,7 +128,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < CV_NACC; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 4);
     }
@@ -106,7 +137,9 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
     tma_prefetch_desc(&tmap_in);
   }
   if (warp == 2) tmem_alloc(tmem_slot, C::TMEM_COLS);
-  for (int i = threadIdx.x; i < COUT; i += blockDim.x) smem_bias[i] = bias[i];
+  fill_ones_operand(smem_ones, threadIdx.x, blockDim.x);
+  fill_bias_operand(smem_biasop, bias, COUT, COUT, threadIdx.x, blockDim.x);
+  fence_proxy_async_smem();      // generic-proxy writes above -> visible to the UMMA operand reads
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -147,8 +180,11 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
     constexpr uint32_t idesc = make_idesc_bf16(128, COUT);
     constexpr uint32_t a_hi = desc_hi(C::GROUP_STRIDE, C::SWZ);   // 8-row groups one halo row apart
     constexpr uint32_t b_hi = desc_hi(8 * C::ROWB, C::SWZ);       // dense rows
+    constexpr uint32_t c_hi = desc_hi(256, SW_NONE);              // ones / bias operands
     const uint32_t a_lo0 = desc_lo(smem_u32(smem_a), 0);
     const uint32_t b_lo0 = desc_lo(smem_u32(smem_b), 0);
+    const uint32_t ones_lo = desc_lo(smem_u32(smem_ones), 128);
+    const uint32_t bias_lo = desc_lo(smem_u32(smem_biasop), 128);
     mbar_wait(wload_bar, 0, 21);
     int stage = 0;
     uint32_t phase = 0;
@@ -167,6 +203,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
       if (elect_one()) {
         const uint32_t d_tmem = tmem_base + acc * COUT;
         const uint32_t a_stage = a_lo0 + stage * (C::STAGE_STRIDE >> 4);
+        umma_bf16_ss_w(d_tmem, ones_lo, c_hi, bias_lo, c_hi, idesc, 0u);     // D = bias
 #pragma unroll
         for (int kc = 0; kc < C::NCHUNK; ++kc) {
 #pragma unroll
@@ -177,7 +214,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
               const uint32_t b_lo = b_lo0 + (((r * 3 + s) * C::NCHUNK + kc) * C::B_TAP_BYTES >> 4);
 #pragma unroll
               for (int kk = 0; kk < C::CK / 16; ++kk) {
-                umma_bf16_ss_w(d_tmem, a_lo + kk * 2, a_hi, b_lo + kk * 2, b_hi, idesc, (kc | r | s | kk) ? 1u : 0u);
+                umma_bf16_ss_w(d_tmem, a_lo + kk * 2, a_hi, b_lo + kk * 2, b_hi, idesc, 1u);
               }
             }
           }
@@ -187,26 +224,29 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
       }
       __syncwarp();
       if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == CV_NACC) { acc = 0; acc_phase ^= 1; }
     }
     loop.end();
     if (lane == 0) { wait_acc.store(1); wait_ops.store(2); loop.store(3); }
   } else if (warp >= 4) {
     // ================================ epilogue ==============================================
-    const int e = warp - 4;                   // TMEM lanes 32e .. 32e+31
+    // two groups of four warps; group g owns the tiles with local index j = g, g+2, g+4, ...
+    const int group = (warp - 4) >> 2;
+    const int e = (warp - 4) & 3;             // TMEM lanes 32e .. 32e+31
     const int Ho = H >> 1, Wo = W >> 1;
     const int ly = lane >> 3;                 // 0..3  (tile row 4e + ly)
     const int lx = lane & 7;                  // tile column
     const bool odd_x = lane & 1;
     const bool odd_y = (lane >> 3) & 1;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    TileWalker t(blockIdx.x, gridDim.x, tiles_x, tiles_y);
+    TileWalker t(blockIdx.x + group * gridDim.x, 2 * gridDim.x, tiles_x, tiles_y);
     RoleTimer wait_full, eloop;
     unsigned long long ntiles = 0;
     eloop.begin();
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, t.next()) {
+    int j = group;
+    for (int tile = blockIdx.x + group * gridDim.x; tile < total_tiles; tile += 2 * gridDim.x, t.next(), j += 2) {
       ++ntiles;
+      const int acc = j % CV_NACC;
+      const uint32_t acc_phase = (j / CV_NACC) & 1;
       const int py = ((t.ty * CV_TILE_Y + 4 * e + ly) >> 1);
       const int px = ((t.tx * CV_TILE_X + lx) >> 1);
       const bool in_range = py < Ho && px < Wo;
@@ -217,28 +257,25 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
       tc_fence_after_sync();
       const uint32_t t_addr = tmem_base + ((uint32_t)(32 * e) << 16) + acc * COUT;
 
-      // bias + ReLU + bf16 + 2x2 max-pool (shuffle reduce-scatter) + 16-byte store of one 32-channel chunk
+      // bf16 + 2x2 max-pool (shuffle reduce-scatter) + ReLU + 16-byte store of one 32-channel chunk
+      // (rounding, max and ReLU commute, so the order is free; the bias is already in the accumulator)
       auto finish_chunk = [&](const uint32_t (&v)[32], int cb) {
         uint32_t pk[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float a = fmaxf(__uint_as_float(v[2 * j]) + smem_bias[cb + 2 * j], 0.f);
-          const float b = fmaxf(__uint_as_float(v[2 * j + 1]) + smem_bias[cb + 2 * j + 1], 0.f);
-          pk[j] = pack_bf16x2(a, b);
-        }
+        for (int q = 0; q < 16; ++q) pk[q] = pack_bf16x2(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]));
         uint32_t h8[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {     // x partner (lane^1): keep 8 of 16 registers, send the other 8
-          const uint32_t keep = odd_x ? pk[8 + j] : pk[j];
-          const uint32_t send = odd_x ? pk[j] : pk[8 + j];
-          h8[j] = max_bf16x2(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+        for (int q = 0; q < 8; ++q) {     // x partner (lane^1): keep 8 of 16 registers, send the other 8
+          const uint32_t keep = odd_x ? pk[8 + q] : pk[q];
+          const uint32_t send = odd_x ? pk[q] : pk[8 + q];
+          h8[q] = max_bf16x2(keep, __shfl_xor_sync(0xffffffffu, send, 1));
         }
         uint32_t q4[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {     // y partner (lane^8): keep 4 of 8
-          const uint32_t keep = odd_y ? h8[4 + j] : h8[j];
-          const uint32_t send = odd_y ? h8[j] : h8[4 + j];
-          q4[j] = max_bf16x2(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+        for (int q = 0; q < 4; ++q) {     // y partner (lane^8): keep 4 of 8, then ReLU
+          const uint32_t keep = odd_y ? h8[4 + q] : h8[q];
+          const uint32_t send = odd_y ? h8[q] : h8[4 + q];
+          q4[q] = max_bf16x2(max_bf16x2(keep, __shfl_xor_sync(0xffffffffu, send, 8)), 0u);
         }
         if (in_range) {
           const int ch = cb + (odd_x ? 16 : 0) + (odd_y ? 8 : 0);
@@ -265,7 +302,6 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
         }
         finish_chunk(vb, cb + 32);
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     eloop.end();
     if (warp == 4 && lane == 0) {
@@ -318,7 +354,8 @@ static int launch_conv3x3(const void* in, int batch, int h, int w, const void* w
   const int tiles_y = (h + CV_TILE_Y - 1) / CV_TILE_Y;
   const int tiles_x = w / CV_TILE_X;
   const int total = tiles_y * tiles_x * batch;
-  const int smem = 1024 + C::B_BYTES + NSTAGE * C::STAGE_STRIDE + COUT * 4 + (2 * NSTAGE + 6) * 8;
+  const int smem = 1024 + C::B_BYTES + NSTAGE * C::STAGE_STRIDE + ONES_BYTES + C::BIAS_BYTES +
+                   (2 * NSTAGE + 2 * CV_NACC + 2) * 8;
   auto kern = conv3x3_kernel<CIN, COUT, NSTAGE>;
   static int configured = 0;
   if (int rc2 = ensure_dynamic_smem(kern, smem, &configured)) return rc2;

@@ -5,6 +5,6 @@
 #include "probe.cu"
 #include "counts.cu"
 #include "preprocess.cu"
-#include "conv1.cu"
 #include "conv3x3.cu"
+#include "conv1.cu"
 #include "linear.cu"
