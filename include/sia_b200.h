@@ -151,10 +151,17 @@ int sia_debug_umma_probe(const void* smem_image, int image_bytes, const uint64_t
 
 /* Debug / bring-up: one TMA tiled load of a bf16 tensor (rank 2..4; dims / box in elements, innermost
  * first; strides in bytes for dims 1..rank-1; swizzle_bytes in {0,32,64,128}) at the given coordinates;
- * `out` receives the box bytes exactly as they landed in shared memory. */
+ * `out` receives the box bytes exactly as they landed in shared memory.  repeat > 1 issues that many
+ * loads back to back (coordinate step_dim advanced by step each time) and reports the SM-clock cycles
+ * until all have landed in cycles_host: the TMA engine's throughput for that box shape. */
 int sia_debug_tma_probe(const void* base, int rank, const uint64_t* dims_host, const uint64_t* strides_bytes_host,
                         const uint32_t* box_host, int swizzle_bytes, const int* coords_host, void* out,
-                        void* stream);
+                        int repeat, int step_dim, int step, long long* cycles_host, void* stream);
+
+/* Debug: event trace of CTA 0 of the conv kernels: 64 tiles x 8 int64 clock64 stamps (producer stage-free /
+ * TMA-issued, MMA accumulator-free / operands-landed / tile-issued, epilogue accumulator-complete / drained /
+ * stored); NULL switches it off (default). */
+int sia_debug_set_trace(long long* device_buffer_or_null);
 
 /* Debug: per-CTA role timing of the conv kernels.  device_buffer holds 8 uint64 per CTA (SM-clock cycles:
  * producer wait-for-stage, MMA wait-for-accumulator, MMA wait-for-operands, MMA loop, epilogue

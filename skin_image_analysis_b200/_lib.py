@@ -42,8 +42,10 @@ SIGNATURES = {
     "sia_debug_umma_probe": (c_int, [_P, c_int, ctypes.POINTER(c_uint64), ctypes.POINTER(c_uint64), c_int, c_int,
                                      _P, c_int, ctypes.POINTER(c_longlong), _P]),
     "sia_debug_tma_probe": (c_int, [_P, c_int, ctypes.POINTER(c_uint64), ctypes.POINTER(c_uint64),
-                                    ctypes.POINTER(ctypes.c_uint32), c_int, ctypes.POINTER(c_int), _P, _P]),
+                                    ctypes.POINTER(ctypes.c_uint32), c_int, ctypes.POINTER(c_int), _P, c_int, c_int,
+                                    c_int, ctypes.POINTER(c_longlong), _P]),
     "sia_debug_set_stats": (c_int, [_P]),
+    "sia_debug_set_trace": (c_int, [_P]),
     "sia_debug_alu_rates": (c_int, [ctypes.POINTER(ctypes.c_double), c_int]),
 }
 

@@ -122,15 +122,18 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
       uint32_t phase = 0;
       TileWalker1 t(blockIdx.x, gridDim.x, tiles_x, tiles_y);
       RoleTimer wait_stage;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, t.next()) {
+      int lt = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, t.next(), ++lt) {
         wait_stage.begin();
         mbar_wait(&empty_bar[stage], phase ^ 1, 30);
         wait_stage.end();
+        trace(lt, 0);
         mbar_arrive_expect_tx(&full_bar[stage], C1_STAGE_BYTES);
         // innermost coordinate is in bf16 elements (4 per pixel) and must be 16-byte aligned for TMA:
         // image pixel x sits in column x+1 of the padded row, so the window start x0-3 is column x0-2
         tma_load_3d(smem_a + stage * C1_STAGE_STRIDE, &tmap_in, &full_bar[stage], (t.tx * C1_TILE_X - 2) * 4,
                     t.ty * C1_TILE_Y - 3, t.n);
+        trace(lt, 1);
         if (++stage == C1_NSTAGE) { stage = 0; phase ^= 1; }
       }
       wait_stage.store(0);
@@ -154,13 +157,16 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
     uint32_t acc_phase = 0;
     RoleTimer wait_acc, wait_ops, loop;
     loop.begin();
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
       wait_acc.begin();
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 32);
       wait_acc.end();
+      if (lane == 0) trace(lt, 2);
       wait_ops.begin();
       mbar_wait(&full_bar[stage], phase, 33);
       wait_ops.end();
+      if (lane == 0) trace(lt, 3);
       tc_fence_after_sync();
       if (elect_one()) {
         const uint32_t d_tmem = tmem_base + acc * C1_N;
@@ -178,6 +184,7 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
         umma_commit(&tfull_bar[acc]);
       }
       __syncwarp();
+      if (lane == 0) trace(lt, 4);
       if (++stage == C1_NSTAGE) { stage = 0; phase ^= 1; }
       if (++acc == C1_NACC) { acc = 0; acc_phase ^= 1; }
     }
@@ -207,6 +214,7 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
       wait_full.begin();
       mbar_wait(&tfull_bar[acc], acc_phase, 34);
       wait_full.end();
+      if (e == 0 && lane == 0) trace(j, 5);
       tc_fence_after_sync();
       const uint32_t t_addr = tmem_base + ((uint32_t)(32 * e) << 16) + acc * C1_N;
 
@@ -245,7 +253,9 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);   // the whole accumulator is in registers now
+      if (e == 0 && lane == 0) trace(j, 6);
       finish_half(b0, b1, b2, b3, 1);
+      if (e == 0 && lane == 0) trace(j, 7);
     }
     eloop.end();
     if (warp == 4 && lane == 0) {

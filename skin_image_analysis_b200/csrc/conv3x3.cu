@@ -159,16 +159,19 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
       uint32_t phase = 0;
       TileWalker t(blockIdx.x, gridDim.x, tiles_x, tiles_y);
       RoleTimer wait_stage;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, t.next()) {
+      int lt = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, t.next(), ++lt) {
         wait_stage.begin();
         mbar_wait(&empty_bar[stage], phase ^ 1, 20);
         wait_stage.end();
+        trace(lt, 0);
         mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_TX_BYTES);
 #pragma unroll
         for (int kc = 0; kc < C::NCHUNK; ++kc) {
           tma_load_4d(smem_a + stage * C::STAGE_STRIDE + kc * C::CHUNK_STRIDE, &tmap_in, &full_bar[stage],
                       kc * C::CK, t.tx * CV_TILE_X - 1, t.ty * CV_TILE_Y - 1, t.n);
         }
+        trace(lt, 1);
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
       }
       wait_stage.store(0);
@@ -192,13 +195,16 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
     uint32_t acc_phase = 0;
     RoleTimer wait_acc, wait_ops, loop;
     loop.begin();
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
       wait_acc.begin();
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 22);
       wait_acc.end();
+      if (lane == 0) trace(lt, 2);
       wait_ops.begin();
       mbar_wait(&full_bar[stage], phase, 23);
       wait_ops.end();
+      if (lane == 0) trace(lt, 3);
       tc_fence_after_sync();
       if (elect_one()) {
         const uint32_t d_tmem = tmem_base + acc * COUT;
@@ -223,6 +229,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
         umma_commit(&tfull_bar[acc]);     // accumulator complete -> epilogue
       }
       __syncwarp();
+      if (lane == 0) trace(lt, 4);
       if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
       if (++acc == CV_NACC) { acc = 0; acc_phase ^= 1; }
     }
@@ -254,6 +261,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
       wait_full.begin();
       mbar_wait(&tfull_bar[acc], acc_phase, 24);
       wait_full.end();
+      if (e == 0 && lane == 0) trace(j, 5);
       tc_fence_after_sync();
       const uint32_t t_addr = tmem_base + ((uint32_t)(32 * e) << 16) + acc * COUT;
 
@@ -299,9 +307,11 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
           tc_fence_before_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          if (e == 0 && lane == 0) trace(j, 6);
         }
         finish_chunk(vb, cb + 32);
       }
+      if (e == 0 && lane == 0) trace(j, 7);
     }
     eloop.end();
     if (warp == 4 && lane == 0) {

@@ -25,6 +25,11 @@ int ensure_watchdog() {
 
 }  // namespace sia
 
+extern "C" int sia_debug_set_trace(long long* device_buffer_or_null) {
+  cudaError_t e = cudaMemcpyToSymbol(sia::g_trace, &device_buffer_or_null, sizeof(device_buffer_or_null));
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
 extern "C" int sia_debug_set_stats(unsigned long long* device_buffer_or_null) {
   cudaError_t e = cudaMemcpyToSymbol(sia::g_stats, &device_buffer_or_null, sizeof(device_buffer_or_null));
   return e == cudaSuccess ? 0 : (int)e;

@@ -133,11 +133,14 @@ struct TmaProbeParams {
   int rank;
   int coords[5];
   uint32_t box_bytes;
+  int repeat;          // > 1: throughput mode -- `repeat` loads in flight on one barrier, 4 rotating buffers
+  int step_dim;        // coordinate advanced by step per repeat (so successive boxes differ)
+  int step;
 };
 
 __global__ void __launch_bounds__(128, 1)
 tma_probe_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TmaProbeParams p,
-                 uint8_t* __restrict__ out) {
+                 uint8_t* __restrict__ out, long long* __restrict__ cycles) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ uint64_t bar;
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -151,10 +154,19 @@ tma_probe_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
   fence_proxy_async_smem();
   __syncthreads();
   if (threadIdx.x == 0) {
-    mbar_arrive_expect_tx(&bar, p.box_bytes);
-    if (p.rank == 2) tma_load_2d(base, &tmap, &bar, p.coords[0], p.coords[1]);
-    if (p.rank == 3) tma_load_3d(base, &tmap, &bar, p.coords[0], p.coords[1], p.coords[2]);
-    if (p.rank == 4) tma_load_4d(base, &tmap, &bar, p.coords[0], p.coords[1], p.coords[2], p.coords[3]);
+    const uint32_t stride = (p.box_bytes + 1023u) & ~1023u;
+    const long long t0 = clock64();
+    mbar_arrive_expect_tx(&bar, p.box_bytes * (uint32_t)p.repeat);
+    for (int i = 0; i < p.repeat; ++i) {
+      int c[5] = {p.coords[0], p.coords[1], p.coords[2], p.coords[3], p.coords[4]};
+      c[p.step_dim] += i * p.step;
+      uint8_t* dst = base + (p.repeat > 1 ? (uint32_t)(i & 3) * stride : 0u);
+      if (p.rank == 2) tma_load_2d(dst, &tmap, &bar, c[0], c[1]);
+      if (p.rank == 3) tma_load_3d(dst, &tmap, &bar, c[0], c[1], c[2]);
+      if (p.rank == 4) tma_load_4d(dst, &tmap, &bar, c[0], c[1], c[2], c[3]);
+    }
+    mbar_wait(&bar, 0, 5);
+    if (cycles) *cycles = clock64() - t0;
   }
   mbar_wait(&bar, 0, 5);
   for (uint32_t i = threadIdx.x * 16; i < p.box_bytes; i += blockDim.x * 16) {
@@ -166,10 +178,12 @@ tma_probe_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
 
 extern "C" int sia_debug_tma_probe(const void* base, int rank, const uint64_t* dims_host,
                                    const uint64_t* strides_bytes_host, const uint32_t* box_host, int swizzle_bytes,
-                                   const int* coords_host, void* out, void* stream) {
+                                   const int* coords_host, void* out, int repeat, int step_dim, int step,
+                                   long long* cycles_host, void* stream) {
   using namespace sia;
   SIA_REQUIRE(base && dims_host && strides_bytes_host && box_host && coords_host && out);
-  SIA_REQUIRE(rank >= 2 && rank <= 4 && aligned(base, 16) && aligned(out, 16));
+  SIA_REQUIRE(rank >= 2 && rank <= 4 && aligned(base, 16) && aligned(out, 16) && repeat >= 1);
+  SIA_REQUIRE(step_dim >= 0 && step_dim < rank);
   if (int wrc = ensure_watchdog()) return wrc;
   CUtensorMapSwizzle sw = swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
                           : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
@@ -180,18 +194,32 @@ extern "C" int sia_debug_tma_probe(const void* base, int rank, const uint64_t* d
   if (rc != 0) return rc;
   TmaProbeParams p;
   p.rank = rank;
+  p.repeat = repeat;
+  p.step_dim = step_dim;
+  p.step = step;
   uint64_t bytes = 2;
+  for (int i = 0; i < 5; ++i) p.coords[i] = 0;
   for (int i = 0; i < rank; ++i) {
     p.coords[i] = coords_host[i];
     bytes *= box_host[i];
   }
-  SIA_REQUIRE(bytes % 16 == 0 && bytes <= 200 * 1024);
+  SIA_REQUIRE(bytes % 16 == 0 && bytes <= 48 * 1024 && bytes * (uint64_t)repeat < (1u << 20));
   p.box_bytes = (uint32_t)bytes;
-  const int smem = (int)bytes + 1024;
+  const int smem = 4 * (((int)bytes + 1023) & ~1023) + 1024;
   static int configured = 0;
   if (int rc2 = ensure_dynamic_smem(tma_probe_kernel, smem, &configured)) return rc2;
-  tma_probe_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(tmap, p, static_cast<uint8_t*>(out));
-  return launch_status();
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  long long* d_cycles = nullptr;
+  if (cycles_host) SIA_CUDA_OK(cudaMalloc(&d_cycles, sizeof(long long)));
+  tma_probe_kernel<<<1, 128, smem, st>>>(tmap, p, static_cast<uint8_t*>(out), d_cycles);
+  rc = launch_status();
+  if (rc == 0 && cycles_host) {
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaMemcpy(cycles_host, d_cycles, sizeof(long long), cudaMemcpyDeviceToHost);
+    rc = (int)e;
+  }
+  if (d_cycles) cudaFree(d_cycles);
+  return rc;
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -25,6 +25,15 @@ static __device__ volatile unsigned int* g_watchdog_word = nullptr;
 //   4 epilogue warp 4: waiting for tfull      5 epilogue warp 4: whole loop      6 tiles done by this CTA
 static __device__ unsigned long long* g_stats = nullptr;
 
+// Optional event trace of CTA 0 (sia_debug_set_trace): clock64 stamps, 8 events x TRACE_TILES tiles.
+//   0 producer: stage free   1 producer: TMA issued   2 MMA: accumulator free   3 MMA: operands landed
+//   4 MMA: tile issued       5 epilogue: accumulator complete   6 epilogue: accumulator drained   7 epilogue: stored
+constexpr int TRACE_TILES = 64;
+static __device__ long long* g_trace = nullptr;
+__device__ __forceinline__ void trace(int local_tile, int event) {
+  if (g_trace != nullptr && blockIdx.x == 0 && local_tile < TRACE_TILES) g_trace[local_tile * 8 + event] = clock64();
+}
+
 struct RoleTimer {
   unsigned long long acc = 0;
   long long t0 = 0;

@@ -253,18 +253,22 @@ def umma_probe(image: torch.Tensor, a_descs, b_descs, n: int, repeat: int = 1, w
     return (out, cyc.value) if want_cycles else out
 
 
-def tma_probe(t: torch.Tensor, dims, strides_bytes, box, swizzle_bytes: int, coords) -> torch.Tensor:
-    """One TMA box load of a bf16 tensor -> the shared-memory bytes as uint8 (bring-up tests)."""
+def tma_probe(t: torch.Tensor, dims, strides_bytes, box, swizzle_bytes: int, coords, repeat: int = 1,
+              step_dim: int = 0, step: int = 0):
+    """One TMA box load of a bf16 tensor -> the shared-memory bytes as uint8 (bring-up tests).  With
+    repeat > 1 returns (bytes, cycles): `repeat` loads in flight, coordinate step_dim advanced by step."""
     _need(t, torch.bfloat16, "t")
     rank = len(dims)
     nbytes = 2
     for b in box:
         nbytes *= int(b)
     out = torch.zeros(nbytes, dtype=torch.uint8, device=t.device)
+    cyc = ctypes.c_longlong(0)
     check(_lib.load().sia_debug_tma_probe(
         ptr(t), rank, (ctypes.c_uint64 * rank)(*[int(d) for d in dims]),
         (ctypes.c_uint64 * max(1, rank - 1))(*[int(s) for s in strides_bytes]),
         (ctypes.c_uint32 * rank)(*[int(b) for b in box]), int(swizzle_bytes),
-        (ctypes.c_int * rank)(*[int(c) for c in coords]), ptr(out), stream_ptr()), "sia_debug_tma_probe")
+        (ctypes.c_int * rank)(*[int(c) for c in coords]), ptr(out), int(repeat), int(step_dim), int(step),
+        ctypes.byref(cyc) if repeat > 1 else None, stream_ptr()), "sia_debug_tma_probe")
     torch.cuda.synchronize()
-    return out
+    return (out, cyc.value) if repeat > 1 else out

@@ -373,3 +373,33 @@ def test_single_halo_copy_taps(row_bytes, layout):
             all_ok &= bool(np.array_equal(got, halo[idx] @ b.T))
     record(f"single_halo_taps_rowbytes{row_bytes}", all_ok, True)
     assert all_ok
+
+
+def test_exploratory_tma_box_throughput():
+    """SM-clock cycles per TMA box (32 boxes in flight from one SM) for the shapes in use and candidates."""
+    from skin_image_analysis_b200 import ops
+    out = {}
+    rep = 32
+    # conv1 patch boxes on a [B, H, WP*4] view of the padded NHWC4 image
+    for name, wp, box_px, rows, c0 in (("conv1_192B_rows_pitch232_start-16B", 232, 24, 38, -8),
+                                       ("conv1_192B_rows_pitch240_start_aligned128", 240, 24, 38, 0),
+                                       ("conv1_256B_rows_pitch256_start_aligned128", 256, 32, 38, 0),
+                                       ("conv1_128B_rows_pitch240_start_aligned128", 240, 16, 38, 0)):
+        b, h = 4, 224
+        t = _coded((b, h, wp * 4), 1)
+        _, cyc = ops.tma_probe(t, (wp * 4, h, b), (wp * 8, h * wp * 8), (box_px * 4, rows, 1), 0, (c0, 0, 0),
+                               repeat=rep, step_dim=1, step=4)
+        out[name] = cyc / rep
+    # conv3x3 halo boxes
+    for name, cin, swz, box in (("conv3_sw128_10x18", 64, 128, (64, 10, 18, 1)), ("conv2_sw64_10x18", 32, 64, (32, 10, 18, 1)),
+                                ("conv3_sw128_8x18", 64, 128, (64, 8, 18, 1)), ("conv3_sw128_16x12", 64, 128, (64, 16, 12, 1))):
+        b, h, w = 2, 112, 112
+        t = _coded((b, h, w, cin), 2)
+        _, cyc = ops.tma_probe(t, (cin, w, h, b), (cin * 2, w * cin * 2, h * w * cin * 2), box, swz, (0, 7, 3, 0),
+                               repeat=rep, step_dim=2, step=2)
+        out[name] = cyc / rep
+    # plain 2-D GEMM tile
+    t = _coded((1024, 4096), 3)
+    _, cyc = ops.tma_probe(t, (4096, 1024), (8192,), (64, 128), 128, (0, 0), repeat=rep, step_dim=0, step=64)
+    out["linear_sw128_64x128"] = cyc / rep
+    record("tma_cycles_per_box", True, False, {k: round(v, 1) for k, v in out.items()})
