@@ -10,7 +10,8 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_int32, c_longlong, c_size_t, c_uint, c_uint64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsia_b200.so")
+# SIA_LIB_PATH: A/B a differently built library (tools/stage_times.py); never a fallback -- it must exist
+LIB_PATH = os.environ.get("SIA_LIB_PATH") or os.path.join(HERE, "libsia_b200.so")
 
 LAYOUT_NCHW_F32 = 0
 LAYOUT_NCHW_BF16 = 1

@@ -36,8 +36,19 @@ constexpr int C1_N = 128;
 constexpr int C1_K = 256;                    // 8 window rows * 32
 constexpr int C1_B_BYTES = C1_N * C1_K * 2;  // 65536
 constexpr int C1_B_SBO = (C1_K / 8) * 128;   // 4096: next group of 8 B rows
-constexpr int C1_NACC = 4;                   // TMEM accumulator ring (4 x 128 columns)
-constexpr int C1_THREADS = 384;              // warps 0-3 TMA / MMA / TMEM alloc / idle, 4-7 and 8-11 epilogue groups
+#ifndef SIA_C1_NACC
+#define SIA_C1_NACC 4
+#endif
+#ifndef SIA_C1_EPI_GROUPS
+#define SIA_C1_EPI_GROUPS 2
+#endif
+#ifndef SIA_C1_BIAS_UMMA
+#define SIA_C1_BIAS_UMMA 1
+#endif
+constexpr int C1_NACC = SIA_C1_NACC;         // TMEM accumulator ring (NACC x 128 columns)
+constexpr int C1_EPI_GROUPS = SIA_C1_EPI_GROUPS;
+constexpr int C1_THREADS = 128 + 128 * C1_EPI_GROUPS;  // warps 0-3 TMA / MMA / TMEM alloc / idle, then epilogue groups
+constexpr bool C1_BIAS_UMMA = SIA_C1_BIAS_UMMA != 0;
 constexpr int C1_BIAS_BYTES = C1_N * 32;
 
 struct TileWalker1 {
@@ -106,13 +117,18 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
   }
   if (warp == 2) tmem_alloc(tmem_slot, C1_NACC * C1_N);
   // the bias enters through the tensor core (see conv3x3.cu): row n = (dy*2+dx)*32 + co -> bias[co]
-  fill_ones_operand(smem_ones, threadIdx.x, blockDim.x);
-  fill_bias_operand(smem_biasop, bias, C1_N, 32, threadIdx.x, blockDim.x);
+  if (C1_BIAS_UMMA) {
+    fill_ones_operand(smem_ones, threadIdx.x, blockDim.x);
+    fill_bias_operand(smem_biasop, bias, C1_N, 32, threadIdx.x, blockDim.x);
+  } else if (threadIdx.x < 32) {
+    reinterpret_cast<float*>(smem_biasop)[threadIdx.x] = bias[threadIdx.x];
+  }
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = bcast0(*tmem_slot);
+  const float* smem_bias = reinterpret_cast<const float*>(smem_biasop);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -171,13 +187,13 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
       if (elect_one()) {
         const uint32_t d_tmem = tmem_base + acc * C1_N;
         const uint32_t a_lo = a_lo0 + stage * (C1_STAGE_STRIDE >> 4);
-        umma_bf16_ss_w(d_tmem, ones_lo, c_hi, bias_lo, c_hi, idesc, 0u);     // D = bias
+        if (C1_BIAS_UMMA) umma_bf16_ss_w(d_tmem, ones_lo, c_hi, bias_lo, c_hi, idesc, 0u);     // D = bias
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
 #pragma unroll
           for (int kk = 0; kk < 2; ++kk) {
             umma_bf16_ss_w(d_tmem, a_lo + r * (C1_ROWB >> 4) + kk * 2, a_hi, b_lo0 + (r * 4 + kk * 2) * 8, b_hi, idesc,
-                           1u);
+                           (C1_BIAS_UMMA || (r | kk)) ? 1u : 0u);
           }
         }
         umma_commit(&empty_bar[stage]);
@@ -198,12 +214,13 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
     const int Ho = H >> 1, Wo = W >> 1;
     const int yp = 4 * e + (lane >> 3);
     const int xp = lane & 7;
-    TileWalker1 t(blockIdx.x + group * gridDim.x, 2 * gridDim.x, tiles_x, tiles_y);
+    TileWalker1 t(blockIdx.x + group * gridDim.x, C1_EPI_GROUPS * gridDim.x, tiles_x, tiles_y);
     RoleTimer wait_full, eloop;
     unsigned long long ntiles = 0;
     eloop.begin();
     int j = group;
-    for (int tile = blockIdx.x + group * gridDim.x; tile < total_tiles; tile += 2 * gridDim.x, t.next(), j += 2) {
+    for (int tile = blockIdx.x + group * gridDim.x; tile < total_tiles;
+         tile += C1_EPI_GROUPS * gridDim.x, t.next(), j += C1_EPI_GROUPS) {
       ++ntiles;
       const int acc = j % C1_NACC;
       const uint32_t acc_phase = (j / C1_NACC) & 1;
@@ -230,7 +247,11 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
                                 fmaxf(__uint_as_float(q2[c]), __uint_as_float(q3[c])));
           const float b = fmaxf(fmaxf(__uint_as_float(q0[c + 1]), __uint_as_float(q1[c + 1])),
                                 fmaxf(__uint_as_float(q2[c + 1]), __uint_as_float(q3[c + 1])));
-          pk[c2] = max_bf16x2(pack_bf16x2(a, b), 0u);
+          if (C1_BIAS_UMMA) {
+            pk[c2] = max_bf16x2(pack_bf16x2(a, b), 0u);
+          } else {
+            pk[c2] = pack_bf16x2(fmaxf(a + smem_bias[16 * half + c], 0.f), fmaxf(b + smem_bias[16 * half + c + 1], 0.f));
+          }
         }
         if (in_range) {
           opix[2 * half] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -261,7 +282,7 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
     if (warp == 4 && lane == 0) {
       wait_full.store(4);
       eloop.store(5);
-      if (g_stats) g_stats[blockIdx.x * 8 + 6] = ntiles;
+      stats_store(6, ntiles);
     }
   }
 

@@ -317,7 +317,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
     if (warp == 4 && lane == 0) {
       wait_full.store(4);
       eloop.store(5);
-      if (g_stats) g_stats[blockIdx.x * 8 + 6] = ntiles;
+      stats_store(6, ntiles);
     }
   }
 

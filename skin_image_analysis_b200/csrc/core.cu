@@ -26,11 +26,17 @@ int ensure_watchdog() {
 }  // namespace sia
 
 extern "C" int sia_debug_set_trace(long long* device_buffer_or_null) {
+#ifndef SIA_INSTRUMENT
+  if (device_buffer_or_null != nullptr) return SIA_E_UNSUPPORTED;   // needs a -DSIA_INSTRUMENT build
+#endif
   cudaError_t e = cudaMemcpyToSymbol(sia::g_trace, &device_buffer_or_null, sizeof(device_buffer_or_null));
   return e == cudaSuccess ? 0 : (int)e;
 }
 
 extern "C" int sia_debug_set_stats(unsigned long long* device_buffer_or_null) {
+#ifndef SIA_INSTRUMENT
+  if (device_buffer_or_null != nullptr) return SIA_E_UNSUPPORTED;   // needs a -DSIA_INSTRUMENT build
+#endif
   cudaError_t e = cudaMemcpyToSymbol(sia::g_stats, &device_buffer_or_null, sizeof(device_buffer_or_null));
   return e == cudaSuccess ? 0 : (int)e;
 }

@@ -30,6 +30,9 @@ static __device__ unsigned long long* g_stats = nullptr;
 //   4 MMA: tile issued       5 epilogue: accumulator complete   6 epilogue: accumulator drained   7 epilogue: stored
 constexpr int TRACE_TILES = 64;
 static __device__ long long* g_trace = nullptr;
+// Both instruments cost a global load of their switch per call site -- enough to slow the conv kernels by
+// 40-70 % even when switched off -- so they only exist in builds with -DSIA_INSTRUMENT (tools/build_variant.sh).
+#ifdef SIA_INSTRUMENT
 __device__ __forceinline__ void trace(int local_tile, int event) {
   if (g_trace != nullptr && blockIdx.x == 0 && local_tile < TRACE_TILES) g_trace[local_tile * 8 + event] = clock64();
 }
@@ -41,6 +44,18 @@ struct RoleTimer {
   __device__ __forceinline__ void end() { if (g_stats) acc += (unsigned long long)(clock64() - t0); }
   __device__ __forceinline__ void store(int slot) { if (g_stats) g_stats[blockIdx.x * 8 + slot] = acc; }
 };
+__device__ __forceinline__ void stats_store(int slot, unsigned long long v) {
+  if (g_stats) g_stats[blockIdx.x * 8 + slot] = v;
+}
+#else
+__device__ __forceinline__ void trace(int, int) {}
+struct RoleTimer {
+  __device__ __forceinline__ void begin() {}
+  __device__ __forceinline__ void end() {}
+  __device__ __forceinline__ void store(int) {}
+};
+__device__ __forceinline__ void stats_store(int, unsigned long long) {}
+#endif
 
 #ifndef SIA_WATCHDOG_SPINS
 #define SIA_WATCHDOG_SPINS (1u << 24)
