@@ -80,6 +80,24 @@ int sia_preprocess_u8hwc(const uint8_t* src, int batch, int src_h, int src_w, co
                          const int32_t* y_first_last, int out_h, int out_w, const float* out_scale_host,
                          const float* out_bias_host, int layout, int rows_per_cta, void* dst, void* stream);
 
+/* Same operator, tensor-core formulation, SIA_LAYOUT_NHWC4_BF16 output only (csrc/preprocess_tc.cu): the
+ * vertical pass is a tcgen05 GEMM (fp16 copies of the Wy rows x the image bytes widened to fp16, fp32
+ * accumulate in TMEM), the horizontal pass streams the accumulator columns.  Tables come from
+ * resize_weights.build_tc_tables:
+ *   a_packed  [n_tiles][65536]   fp16 Wy rows of each tile of tile_rows output rows, in UMMA K-major order
+ *   lane_scale[n_tiles][128]     sum(w) / sum(fp16(w)) of each output row
+ *   tile_row0 [n_tiles]          first source row of each tile's 256-row window
+ *   items     [n_items][16]      the horizontal schedule, 64 bytes per item: int32 {accumulator column,
+ *                                output column to emit or -1, column block, source pixels consumed}, then
+ *                                3 pixels x 4 slots of fp32 weights
+ *   n_blocks, last_block_cols    column blocks of 240 bytes per image row; MMA N of the last one
+ * Needs (3 * src_w) % 8 == 0, an even src_h and src 16-byte aligned (the images are fetched by TMA as double
+ * rows); SIA_E_UNSUPPORTED otherwise. */
+int sia_preprocess_tc_u8hwc(const uint8_t* src, int batch, int src_h, int src_w, const void* a_packed,
+                            const float* lane_scale, const int32_t* tile_row0, int n_tiles, int tile_rows,
+                            const void* items, int n_items, int n_blocks, int last_block_cols, int out_h, int out_w,
+                            const float* out_scale_host, const float* out_bias_host, void* dst_nhwc4, void* stream);
+
 /* Model boundary: NCHW fp32 [B,3,h,w] (the tensor the reference DataLoader feeds to model(images),
  * src/tone_bias_test.py:190-196) -> padded NHWC4 bf16 [B,h,w+8,4] (SIA_LAYOUT_NHWC4_BF16). */
 int sia_nchw_f32_to_nhwc4_bf16(const float* src, int batch, int h, int w, void* dst, void* stream);
@@ -149,6 +167,13 @@ int sia_debug_umma_probe(const void* smem_image, int image_bytes, const uint64_t
                          const uint64_t* b_desc_host, int n_mma, int n, float* out_128xn, int repeat,
                          long long* cycles_host, void* stream);
 
+/* Same, with the MMA kind (0 = kind::f16 with bf16 inputs, 1 = kind::i8) and the 32-bit instruction
+ * descriptor given by the caller (0 = default bf16 K-major); the accumulator comes back as raw 32-bit words
+ * (fp32 for kind 0, int32 for kind 1). */
+int sia_debug_umma_probe_ex(const void* smem_image, int image_bytes, const uint64_t* a_desc_host,
+                            const uint64_t* b_desc_host, int n_mma, int n, int kind, uint32_t idesc,
+                            void* out_128xn_raw, int repeat, long long* cycles_host, void* stream);
+
 /* Debug / bring-up: one TMA tiled load of a bf16 tensor (rank 2..4; dims / box in elements, innermost
  * first; strides in bytes for dims 1..rank-1; swizzle_bytes in {0,32,64,128}) at the given coordinates;
  * `out` receives the box bytes exactly as they landed in shared memory.  repeat > 1 issues that many
@@ -171,6 +196,10 @@ int sia_debug_set_stats(unsigned long long* device_buffer_or_null);
 /* Debug / bring-up: lane-operations per SM clock (one resident CTA of 1024 threads) for
  * FFMA, PRMT, I2F.U8(+IADD), DP4A, DP2A, IMAD, SHF, FFMA2 -- out_host needs room for 8 doubles. */
 int sia_debug_alu_rates(double* out_host, int n);
+
+/* Debug / bring-up: TMEM read rate in bytes per SM clock of back-to-back tcgen05.ld.32x32b for
+ * (warps, columns per load) = (1,32) (4,32) (8,32) (4,8) (8,8) (4,1) -- out_host needs room for 6 doubles. */
+int sia_debug_tmem_ld_rates(double* out_host, int n);
 
 #ifdef __cplusplus
 }

@@ -28,6 +28,8 @@ SIGNATURES = {
     "sia_debug_watchdog": (c_uint, [c_int]),
     "sia_preprocess_u8hwc": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, c_int, _P, _P, _P, c_int, c_int,
                                      ctypes.POINTER(c_float), ctypes.POINTER(c_float), c_int, c_int, _P, _P]),
+    "sia_preprocess_tc_u8hwc": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, c_int, c_int, _P, c_int, c_int, c_int,
+                                        c_int, c_int, ctypes.POINTER(c_float), ctypes.POINTER(c_float), _P, _P]),
     "sia_nchw_f32_to_nhwc4_bf16": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
     "sia_pack_conv7x7_c3": (c_int, [_P, _P, _P]),
     "sia_pack_conv7x7_c3_bytes": (c_size_t, []),
@@ -42,11 +44,14 @@ SIGNATURES = {
     "sia_confusion_counts": (c_int, [_P, _P, _P, c_longlong, c_longlong, c_int, c_int, _P, _P]),
     "sia_debug_umma_probe": (c_int, [_P, c_int, ctypes.POINTER(c_uint64), ctypes.POINTER(c_uint64), c_int, c_int,
                                      _P, c_int, ctypes.POINTER(c_longlong), _P]),
+    "sia_debug_umma_probe_ex": (c_int, [_P, c_int, ctypes.POINTER(c_uint64), ctypes.POINTER(c_uint64), c_int, c_int,
+                                        c_int, ctypes.c_uint32, _P, c_int, ctypes.POINTER(c_longlong), _P]),
     "sia_debug_tma_probe": (c_int, [_P, c_int, ctypes.POINTER(c_uint64), ctypes.POINTER(c_uint64),
                                     ctypes.POINTER(ctypes.c_uint32), c_int, ctypes.POINTER(c_int), _P, c_int, c_int,
                                     c_int, ctypes.POINTER(c_longlong), _P]),
     "sia_debug_set_stats": (c_int, [_P]),
     "sia_debug_set_trace": (c_int, [_P]),
+    "sia_debug_tmem_ld_rates": (c_int, [ctypes.POINTER(ctypes.c_double), c_int]),
     "sia_debug_alu_rates": (c_int, [ctypes.POINTER(ctypes.c_double), c_int]),
 }
 

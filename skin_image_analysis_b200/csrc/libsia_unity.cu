@@ -5,6 +5,7 @@
 #include "probe.cu"
 #include "counts.cu"
 #include "preprocess.cu"
+#include "preprocess_tc.cu"
 #include "conv3x3.cu"
 #include "conv1.cu"
 #include "linear.cu"

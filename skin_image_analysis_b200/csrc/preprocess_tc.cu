@@ -1,0 +1,439 @@
+// K1-K3 on the tensor cores: the fast path of sia_preprocess_u8hwc for the padded NHWC4 bf16 layout.
+//
+// Same operator as preprocess.cu (out = Wy * img * Wx^T, the reference's float32(u8)/255 +
+// skimage.transform.resize + HWC->CHW, tone_bias_dataset.py:335, :425, :470), split differently:
+//
+//   vertical pass   V[i, k] = sum_r Wy[i, r] * S[r, k]        i = output row, r = source row,
+//                                                            k = byte of the image row (3*x + c)
+//       = ONE GEMM per (image, tile of <=128 output rows): tcgen05.mma kind::f16, fp16 x fp16 -> fp32.
+//         A = the tile's Wy rows (fp16, K-major, resident in shared memory, K = 256 source rows),
+//         B = the image itself: TMA brings raw 64-row x 272-byte windows of the u8 rows into a shared-memory
+//             ring (the decode buffer is viewed as double rows of 2*row_bytes so that the row pitch is a
+//             multiple of 16 bytes; odd rows are fetched from a 16-byte aligned start and read back
+//             row_bytes % 16 bytes further in), converter warps widen the bytes to fp16 (PRMT + HSUB2,
+//             exact) and store them as the MN-major operand (the byte index k is the contiguous one,
+//             so the HWC decode buffer needs no transposition),
+//         D = 128 lanes (output rows) x 256 columns (bytes 240b .. 240b+255 of the row) fp32 in TMEM,
+//             double buffered.
+//   horizontal pass  out[i, j, c] = sum_x Wx[j, x] * V[i, 3x + c]
+//       = the epilogue: thread = TMEM lane = output row.  It executes a static schedule of "items" built
+//         on the host (resize_weights.build_tc_tables): item n loads 16 accumulator columns (<= 3 source
+//         pixels), adds them into 4 accumulator slots with the item's 3 x 4 weights, then emits one output
+//         pixel from slot n % 4 (scale, bias, bf16, 8 bytes of NHWC4) and clears it.  Four items are
+//         unrolled, so every slot index is a compile-time constant: straight-line FFMA code.
+//
+// Why: the CUDA-core kernel is issue-bound (~150 instructions per source row x output column, most of
+// them unpacking interleaved bytes).  Here the 6-tap vertical contraction -- the one with the larger
+// reduction -- costs no issue slots at all, and the horizontal pass touches every V value once.
+// HBM traffic is unchanged: each source byte is read once, each output byte written once.
+//
+// Precision: fp16 weights (11 significant bits; row sums renormalised per lane), exact products, fp32
+// accumulation => <= 1e-4 of full scale; used for the bf16 layout only (tests: <= 1 bf16 ulp).
+#include <cuda_fp16.h>
+
+#include "sia_host.cuh"
+#include "sia_ptx.cuh"
+
+namespace sia {
+
+constexpr int TC_KWIN = 256;                     // source rows per tile window (K of the GEMM)
+constexpr int TC_KSTAGE = 64;                    // source rows per pipeline stage
+constexpr int TC_NQ = TC_KWIN / TC_KSTAGE;       // stages per column block
+constexpr int TC_STRIDE = 240;                   // bytes of the image row between column blocks
+constexpr int TC_COLS = 256;                     // accumulator columns per block (16 bytes of overlap)
+constexpr int TC_UNITS = TC_COLS / 8;            // 16-byte fp16 units along N per stage row (= one per lane)
+constexpr int TC_B_LBO = 128;                    // next group of 8 source rows
+constexpr int TC_B_SBO = (TC_KSTAGE / 8) * 128 + 16;   // next 8 bytes of the row (+16: bank spread for the converter)
+constexpr int TC_STAGE_BYTES = ((TC_UNITS * TC_B_SBO + 127) / 128) * 128;
+constexpr int TC_NSTAGE = 2;                     // fp16 operand stages (converter -> MMA)
+constexpr int TC_NRAW = 4;                       // raw u8 stages (TMA -> converter); 3 when the item table is large
+constexpr int TC_RAW_ROWB = TC_COLS + 16;        // bytes per raw row: odd rows start up to 8 bytes early
+constexpr int TC_RAW_HALF = (TC_KSTAGE / 2) * TC_RAW_ROWB;   // even-row box, then odd-row box
+constexpr int TC_RAW_BYTES = 2 * TC_RAW_HALF;
+constexpr int TC_A_BYTES = 128 * TC_KWIN * 2;    // 65536
+constexpr int TC_A_LBO = 128, TC_A_SBO = (TC_KWIN / 8) * 128;
+constexpr int TC_THREADS = 448;                  // warps 0-3 converters, 4-7 / 8-11 horizontal-pass groups 0 / 1,
+constexpr int TC_WARP_MMA = 12;                  // 12 MMA issuer (+ TMEM alloc), 13 TMA producer
+constexpr int TC_WARP_TMA = 13;
+constexpr int TC_ITEM_BYTES = 64;                // int4 {column, emit, block, n_px} + 3 x float4 weights
+
+struct TcParams {
+  const uint8_t* a_packed;      // [n_tiles][TC_A_BYTES]
+  const float* lane_scale;      // [n_tiles][128]
+  const int32_t* tile_row0;     // [n_tiles]
+  const uint4* items;           // [n_items][4]
+  uint2* dst;                   // [batch][out_h][out_w + 8] NHWC4 bf16
+  int batch, src_h, src_w, out_h, out_w;
+  int n_tiles, tile_rows, n_blocks, last_block_cols, n_items;
+  int odd_shift;                // row_bytes % 16: odd rows are fetched this many bytes early
+  int n_raw;                    // raw stages in use (<= TC_NRAW)
+  float scale[3], bias[3];
+};
+
+// kind::f16, fp16 x fp16 -> fp32, A K-major, B MN-major
+__host__ __device__ constexpr uint32_t tc_idesc(uint32_t n) {
+  return (1u << 4) | (1u << 16) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16p(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// Work of one CTA: its tile (blockIdx.x % n_tiles) of the images img0, img0 + img_step, ...  Two images are in
+// flight at a time -- image 2p + g of the CTA's sequence belongs to horizontal-pass warp group g and to TMEM
+// accumulator g -- and every role walks the same order: for pair p, for block b, for g in {0, 1}.
+__global__ void __launch_bounds__(TC_THREADS, 1)
+preprocess_tc_kernel(const __grid_constant__ CUtensorMap tmap_src, const __grid_constant__ TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* smem_a = smem;                                        // TC_A_BYTES
+  uint8_t* smem_raw_ring = smem + TC_A_BYTES;                    // n_raw * TC_RAW_BYTES
+  uint8_t* smem_b = smem_raw_ring + p.n_raw * TC_RAW_BYTES;      // TC_NSTAGE * TC_STAGE_BYTES
+  uint4* items_s = reinterpret_cast<uint4*>(smem_b + TC_NSTAGE * TC_STAGE_BYTES);   // [n_items][4]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(items_s + 4 * p.n_items);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + TC_NSTAGE;
+  uint64_t* tfull_bar = bars + 2 * TC_NSTAGE;
+  uint64_t* tempty_bar = bars + 2 * TC_NSTAGE + 2;
+  uint64_t* a_bar = bars + 2 * TC_NSTAGE + 4;
+  uint64_t* raw_full = bars + 2 * TC_NSTAGE + 5;
+  uint64_t* raw_empty = raw_full + TC_NRAW;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + TC_NRAW);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tile = blockIdx.x % p.n_tiles;
+  const int img0 = blockIdx.x / p.n_tiles;
+  const int img_step = gridDim.x / p.n_tiles;
+  const int n_img = img0 < p.batch ? (p.batch - img0 + img_step - 1) / img_step : 0;   // images of this CTA
+  const int row_bytes = p.src_w * 3;
+  const int row0 = p.tile_row0[tile];
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < TC_NSTAGE; ++i) {
+      mbar_init(&full_bar[i], 4);      // one arrival per converter warp
+      mbar_init(&empty_bar[i], 1);     // tcgen05.commit
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);    // one arrival per warp of the group
+    }
+    for (int i = 0; i < TC_NRAW; ++i) {
+      mbar_init(&raw_full[i], 1);      // TMA transaction bytes
+      mbar_init(&raw_empty[i], 4);     // one arrival per converter warp
+    }
+    mbar_init(a_bar, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmap_src);
+  }
+  if (warp == TC_WARP_MMA) tmem_alloc(tmem_slot, 512);
+  for (int i = threadIdx.x; i < 4 * p.n_items; i += blockDim.x) items_s[i] = p.items[i];
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = bcast0(*tmem_slot);
+
+  if (warp == TC_WARP_TMA) {
+    // ================================ TMA producer ==========================================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(a_bar, TC_A_BYTES);
+      for (int off = 0; off < TC_A_BYTES; off += 16384)
+        bulk_load_1d(smem_a + off, p.a_packed + (size_t)tile * TC_A_BYTES + off, 16384, a_bar);
+      int rs = 0;
+      uint32_t rphase = 0;
+      for (int k0 = 0; k0 < n_img; k0 += 2) {
+        for (int blk = 0; blk < p.n_blocks; ++blk) {
+          for (int g = 0; g < 2 && k0 + g < n_img; ++g) {
+            const int img = img0 + (k0 + g) * img_step;
+            for (int q = 0; q < TC_NQ; ++q) {
+              const int r0 = row0 + q * TC_KSTAGE;           // first source row of the stage
+              const int even0 = (r0 + 1) >> 1;               // double row of the first even / odd row
+              const int odd0 = r0 >> 1;
+              mbar_wait(&raw_empty[rs], rphase ^ 1, 45);
+              mbar_arrive_expect_tx(&raw_full[rs], TC_RAW_BYTES);
+              uint8_t* dst = smem_raw_ring + rs * TC_RAW_BYTES;
+              // innermost coordinate in 16-bit elements (the tensor map views the bytes as u16 pairs so that a
+              // 272-byte box is legal)
+              tma_load_3d(dst, &tmap_src, &raw_full[rs], (blk * TC_STRIDE) >> 1, even0, img);
+              tma_load_3d(dst + TC_RAW_HALF, &tmap_src, &raw_full[rs],
+                          (row_bytes - p.odd_shift + blk * TC_STRIDE) >> 1, odd0, img);
+              if (++rs == p.n_raw) { rs = 0; rphase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp < 4) {
+    // ================================ converters ============================================
+    // warp w owns rows w, w+4, ... of every 64-row stage (a fixed row parity); lane l owns bytes 8l .. 8l+7.
+    int stage = 0, rs = 0;
+    uint32_t phase = 0, rphase = 0;
+    const uint32_t parity = (uint32_t)(row0 + warp) & 1u;      // absolute parity of this warp's rows
+    const uint32_t ld_lane = parity * (TC_RAW_HALF + (uint32_t)p.odd_shift) + (uint32_t)lane * 8u;
+    const uint32_t st_lane = (uint32_t)lane * TC_B_SBO;
+    const __half2 k1024 = __half2half2(__ushort_as_half((unsigned short)0x6400));
+    const int n_stages = n_img * p.n_blocks * TC_NQ;
+    for (int it0 = 0; it0 < n_stages; ++it0) {
+      mbar_wait(&raw_full[rs], rphase, 46);
+      uint2 v[TC_KSTAGE / 4];
+      {
+        const uint32_t src = smem_u32(smem_raw_ring) + rs * TC_RAW_BYTES + ld_lane;
+#pragma unroll
+        for (int it = 0; it < TC_KSTAGE / 4; ++it) {
+          const int r = warp + 4 * it;
+          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];"
+                       : "=r"(v[it].x), "=r"(v[it].y)
+                       : "r"(src + (uint32_t)(r >> 1) * TC_RAW_ROWB));
+        }
+      }
+      mbar_wait(&empty_bar[stage], phase ^ 1, 40);
+      {
+        const uint32_t base = smem_u32(smem_b) + stage * TC_STAGE_BYTES + st_lane;
+#pragma unroll
+        for (int it = 0; it < TC_KSTAGE / 4; ++it) {
+          const int r = warp + 4 * it;             // row inside the stage
+          // u8 -> fp16, exact: byte b becomes the half 0x6400 | b = 1024 + b, then subtract 1024
+          uint32_t h[4];
+          h[0] = __byte_perm(v[it].x, 0x64646464u, 0x4140);
+          h[1] = __byte_perm(v[it].x, 0x64646464u, 0x4342);
+          h[2] = __byte_perm(v[it].y, 0x64646464u, 0x4140);
+          h[3] = __byte_perm(v[it].y, 0x64646464u, 0x4342);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            __half2 x = __hsub2(*reinterpret_cast<__half2*>(&h[k]), k1024);
+            h[k] = *reinterpret_cast<uint32_t*>(&x);
+          }
+          const uint32_t dst = base + (uint32_t)(r >> 3) * TC_B_LBO + (uint32_t)(r & 7) * 16u;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(h[0]), "r"(h[1]), "r"(h[2]),
+                       "r"(h[3])
+                       : "memory");
+        }
+      }
+      fence_proxy_async_smem();      // generic-proxy stores -> visible to the UMMA operand reads
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&full_bar[stage]);
+        mbar_arrive(&raw_empty[rs]);
+      }
+      if (++stage == TC_NSTAGE) { stage = 0; phase ^= 1; }
+      if (++rs == p.n_raw) { rs = 0; rphase ^= 1; }
+    }
+  } else if (warp == TC_WARP_MMA) {
+    // ================================ MMA issuer ============================================
+    constexpr uint32_t a_hi = desc_hi(TC_A_SBO, SW_NONE);
+    constexpr uint32_t b_hi = desc_hi(TC_B_SBO, SW_NONE);
+    const uint32_t a_lo0 = desc_lo(smem_u32(smem_a), TC_A_LBO);
+    const uint32_t b_lo0 = desc_lo(smem_u32(smem_b), TC_B_LBO);
+    mbar_wait(a_bar, 0, 41);
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t acc_phase[2] = {0u, 0u};
+    for (int k0 = 0; k0 < n_img; k0 += 2) {
+      for (int blk = 0; blk < p.n_blocks; ++blk) {
+        const uint32_t idesc = tc_idesc((uint32_t)(blk == p.n_blocks - 1 ? p.last_block_cols : TC_COLS));
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (k0 + g < n_img) {
+            mbar_wait(&tempty_bar[g], acc_phase[g] ^ 1, 42);
+            acc_phase[g] ^= 1;
+            tc_fence_after_sync();
+            const uint32_t d_tmem = tmem_base + g * TC_COLS;
+            for (int q = 0; q < TC_NQ; ++q) {
+              mbar_wait(&full_bar[stage], phase, 43);
+              tc_fence_after_sync();
+              if (elect_one()) {
+                const uint32_t b_stage = b_lo0 + stage * (TC_STAGE_BYTES >> 4);
+#pragma unroll
+                for (int kk = 0; kk < TC_KSTAGE / 16; ++kk) {
+                  // K = 16 source rows per instruction: two 8-row core-matrix groups of either operand
+                  umma_bf16_ss_w(d_tmem, a_lo0 + (q * (TC_KSTAGE / 16) + kk) * ((2 * TC_A_LBO) >> 4), a_hi,
+                                 b_stage + kk * ((2 * TC_B_LBO) >> 4), b_hi, idesc, (q | kk) ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[stage]);
+                if (q == TC_NQ - 1) umma_commit(&tfull_bar[g]);
+              }
+              __syncwarp();
+              if (++stage == TC_NSTAGE) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp < 12) {
+    // ================================ horizontal pass =======================================
+    const int g = (warp - 4) >> 2;                 // warp group = accumulator = image parity in the CTA's sequence
+    const int e = warp & 3;                        // TMEM lanes 32e .. 32e+31
+    const int l = 32 * e + lane;                   // output row inside the tile
+    const int i = tile * p.tile_rows + l;
+    const bool row_ok = l < p.tile_rows && i < p.out_h;
+    const float ls = p.lane_scale[tile * 128 + l];
+    const float sc0 = p.scale[0] * ls, sc1 = p.scale[1] * ls, sc2 = p.scale[2] * ls;
+    const float bi0 = p.bias[0], bi1 = p.bias[1], bi2 = p.bias[2];
+    const int pitch = p.out_w + SIA_NHWC4_PAD;
+    const uint32_t t_acc = tmem_base + ((uint32_t)(32 * e) << 16) + g * TC_COLS;
+    uint64_t* tfull = &tfull_bar[g];
+    uint64_t* tempty = &tempty_bar[g];
+    uint32_t acc_phase = 0;
+    for (int k = g; k < n_img; k += 2) {
+      const int img = img0 + k * img_step;
+      uint2* orow = p.dst + ((size_t)img * p.out_h + (row_ok ? i : 0)) * pitch;
+      if (row_ok) {                                // zero pad columns of the NHWC4 row
+        orow[0] = make_uint2(0u, 0u);
+#pragma unroll
+        for (int c = 1; c < SIA_NHWC4_PAD; ++c) orow[p.out_w + c] = make_uint2(0u, 0u);
+      }
+      float acc[4][3];
+#pragma unroll
+      for (int s = 0; s < 4; ++s) acc[s][0] = acc[s][1] = acc[s][2] = 0.f;
+      int cur_block = -1;
+
+      // makes `block` the accumulator contents being read: every block is waited for and handed back in order
+      auto acquire = [&](int block) {
+        while (cur_block < block) {
+          if (cur_block >= 0) {
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty);
+          }
+          mbar_wait(tfull, acc_phase, 44);
+          acc_phase ^= 1;
+          tc_fence_after_sync();
+          ++cur_block;
+        }
+      };
+
+      // software pipeline over the items (n_items is a multiple of 4, padded with no-op items):
+      //   two items ahead : the item's info word           (LDS)
+      //   one item ahead  : its 16 accumulator columns      (tcgen05.ld) and its 12 weights (LDS)
+      //   this item       : 36 FFMA, one predicated 8-byte store
+      uint32_t va[16], vb[16];
+      float4 wa[3], wb[3];
+      uint4 info_cur = items_s[0];
+      uint4 info_nxt = items_s[4];
+      acquire((int)info_cur.z);
+      tmem_ld16p(t_acc + info_cur.x, va);
+      wa[0] = *reinterpret_cast<const float4*>(&items_s[1]);
+      wa[1] = *reinterpret_cast<const float4*>(&items_s[2]);
+      wa[2] = *reinterpret_cast<const float4*>(&items_s[3]);
+      for (int n0 = 0; n0 < p.n_items; n0 += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int n = n0 + u;
+          uint32_t (&v)[16] = (u & 1) ? vb : va;
+          uint32_t (&vn)[16] = (u & 1) ? va : vb;
+          float4 (&w)[3] = (u & 1) ? wb : wa;
+          float4 (&wn)[3] = (u & 1) ? wa : wb;
+          tmem_ld_wait();                            // v (issued one item ago) has landed
+          const uint4 info_nn = items_s[4 * min(n + 2, p.n_items - 1)];
+          if (n + 1 < p.n_items) {
+            if ((int)info_nxt.z != cur_block) acquire((int)info_nxt.z);
+            tmem_ld16p(t_acc + info_nxt.x, vn);      // in flight while this item is computed
+            wn[0] = *reinterpret_cast<const float4*>(&items_s[4 * (n + 1) + 1]);
+            wn[1] = *reinterpret_cast<const float4*>(&items_s[4 * (n + 1) + 2]);
+            wn[2] = *reinterpret_cast<const float4*>(&items_s[4 * (n + 1) + 3]);
+          }
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float f0 = __uint_as_float(v[c]), f1 = __uint_as_float(v[3 + c]), f2 = __uint_as_float(v[6 + c]);
+            acc[0][c] = fmaf(w[2].x, f2, fmaf(w[1].x, f1, fmaf(w[0].x, f0, acc[0][c])));
+            acc[1][c] = fmaf(w[2].y, f2, fmaf(w[1].y, f1, fmaf(w[0].y, f0, acc[1][c])));
+            acc[2][c] = fmaf(w[2].z, f2, fmaf(w[1].z, f1, fmaf(w[0].z, f0, acc[2][c])));
+            acc[3][c] = fmaf(w[2].w, f2, fmaf(w[1].w, f1, fmaf(w[0].w, f0, acc[3][c])));
+          }
+          {                                          // slot u is complete: one NHWC4 pixel (predicated store)
+            const int j = (int)info_cur.y;
+            const uint32_t ox = pack_bf16x2(fmaf(acc[u][0], sc0, bi0), fmaf(acc[u][1], sc1, bi1));
+            const uint32_t oy = pack_bf16x2(fmaf(acc[u][2], sc2, bi2), 0.f);
+            const uint32_t ok = (j >= 0 && row_ok) ? 1u : 0u;
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "setp.ne.b32 p, %3, 0;\n\t"
+                "@p st.global.v2.b32 [%0], {%1, %2};\n\t}"
+                ::"l"(orow + (j + 1)), "r"(ox), "r"(oy), "r"(ok)
+                : "memory");
+            acc[u][0] = acc[u][1] = acc[u][2] = 0.f;
+          }
+          info_cur = info_nxt;
+          info_nxt = info_nn;
+        }
+      }
+      // hand the last accumulator(s) of this image back
+      acquire(p.n_blocks - 1);
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty);
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == TC_WARP_MMA) tmem_free(tmem_base, 512);
+}
+
+}  // namespace sia
+
+extern "C" int sia_preprocess_tc_u8hwc(const uint8_t* src, int batch, int src_h, int src_w, const void* a_packed,
+                                       const float* lane_scale, const int32_t* tile_row0, int n_tiles, int tile_rows,
+                                       const void* items, int n_items, int n_blocks, int last_block_cols, int out_h,
+                                       int out_w, const float* out_scale_host, const float* out_bias_host,
+                                       void* dst_nhwc4, void* stream) {
+  using namespace sia;
+  SIA_REQUIRE(src && a_packed && lane_scale && tile_row0 && items && dst_nhwc4 && out_scale_host && out_bias_host);
+  SIA_REQUIRE(batch >= 1 && src_h >= 2 && src_w >= 8 && out_h >= 1 && out_w >= 1 && n_tiles >= 1);
+  SIA_REQUIRE(n_items >= 8 && n_items % 4 == 0);
+  SIA_REQUIRE(tile_rows >= 1 && tile_rows <= 128 && n_tiles * tile_rows >= out_h && n_blocks >= 1);
+  SIA_REQUIRE(last_block_cols >= 16 && last_block_cols <= TC_COLS && last_block_cols % 16 == 0);
+  SIA_REQUIRE(aligned(a_packed, 16) && aligned(items, 16) && aligned(dst_nhwc4, 8));
+  const int row_bytes = src_w * 3;
+  // 8-byte pieces; rows paired for the TMA view; every image 16-byte aligned
+  if (row_bytes % 8 != 0 || src_h % 2 != 0 || !aligned(src, 16) || ((uint64_t)src_h * row_bytes) % 16 != 0)
+    return SIA_E_UNSUPPORTED;
+  if ((n_blocks - 1) * TC_STRIDE >= row_bytes || n_blocks * TC_STRIDE + 16 < row_bytes) return SIA_E_INVALID;
+  if (n_tiles > sm_count()) return SIA_E_UNSUPPORTED;
+  if (int wrc = ensure_watchdog()) return wrc;
+
+  TcParams p;
+  p.a_packed = static_cast<const uint8_t*>(a_packed);
+  p.lane_scale = lane_scale;
+  p.tile_row0 = tile_row0;
+  p.items = static_cast<const uint4*>(items);
+  p.dst = static_cast<uint2*>(dst_nhwc4);
+  p.batch = batch; p.src_h = src_h; p.src_w = src_w; p.out_h = out_h; p.out_w = out_w;
+  p.n_tiles = n_tiles; p.tile_rows = tile_rows; p.n_blocks = n_blocks; p.last_block_cols = last_block_cols;
+  p.n_items = n_items;
+  p.odd_shift = row_bytes % 16;
+  for (int c = 0; c < 3; ++c) { p.scale[c] = out_scale_host[c]; p.bias[c] = out_bias_host[c]; }
+
+  // the decode buffers as [batch][src_h / 2] double rows of row_bytes u16 elements (a pitch TMA accepts)
+  CUtensorMap tmap;
+  const uint64_t dims[3] = {(uint64_t)row_bytes, (uint64_t)src_h / 2, (uint64_t)batch};
+  const uint64_t strides[2] = {(uint64_t)2 * row_bytes, (uint64_t)src_h * row_bytes};
+  const uint32_t box[3] = {TC_RAW_ROWB / 2, TC_KSTAGE / 2, 1};
+  int trc = encode_tmap(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT16, src, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+  if (trc != 0) return trc;
+  int smem = 0;
+  for (p.n_raw = TC_NRAW; p.n_raw >= 2; --p.n_raw) {
+    smem = 1024 + TC_A_BYTES + p.n_raw * TC_RAW_BYTES + TC_NSTAGE * TC_STAGE_BYTES + n_items * TC_ITEM_BYTES +
+           (2 * TC_NSTAGE + 2 * TC_NRAW + 6) * 8;
+    if (smem <= 227 * 1024) break;
+  }
+  if (p.n_raw < 2) return SIA_E_UNSUPPORTED;
+  static int configured = 0;
+  if (int rc2 = ensure_dynamic_smem(preprocess_tc_kernel, smem, &configured)) return rc2;
+  int grid = (sm_count() / n_tiles) * n_tiles;
+  if (grid > batch * n_tiles) grid = batch * n_tiles;
+  preprocess_tc_kernel<<<grid, TC_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(tmap, p);
+  return launch_status();
+}

@@ -16,6 +16,8 @@ struct ProbeParams {
   int n;
   int image_bytes;
   int repeat;
+  int kind;          // 0 = kind::f16 (bf16 inputs, fp32 accumulate), 1 = kind::i8 (s32 accumulate)
+  uint32_t idesc;    // 0 = the default bf16 K-major descriptor for (128, n)
 };
 
 __global__ void __launch_bounds__(128, 1)
@@ -47,7 +49,7 @@ umma_probe_kernel(const uint8_t* __restrict__ image, const __grid_constant__ Pro
   tc_fence_after_sync();
   const uint32_t tmem = bcast0(tmem_slot);
 
-  const uint32_t idesc = make_idesc_bf16(128, p.n);
+  const uint32_t idesc = p.idesc != 0u ? p.idesc : make_idesc_bf16(128, p.n);
   if (threadIdx.x < 32) {
     // warp-uniform control flow (descriptors come from the constant bank); one elected lane issues
     const uint32_t base16 = base_addr >> 4;
@@ -57,7 +59,11 @@ umma_probe_kernel(const uint8_t* __restrict__ image, const __grid_constant__ Pro
       for (int rep = 0; rep < p.repeat; ++rep) {
         for (int i = 0; i < p.n_mma; ++i) {
           // start-address field is relative to the image base (no carry: the image is < 256 KB)
-          umma_bf16_ss(tmem, p.a_desc[i] + base16, p.b_desc[i] + base16, idesc, i > 0 ? 1u : 0u);
+          if (p.kind == 1) {
+            umma_i8_ss(tmem, p.a_desc[i] + base16, p.b_desc[i] + base16, idesc, i > 0 ? 1u : 0u);
+          } else {
+            umma_bf16_ss(tmem, p.a_desc[i] + base16, p.b_desc[i] + base16, idesc, i > 0 ? 1u : 0u);
+          }
         }
       }
       umma_commit(&done_bar);
@@ -91,7 +97,16 @@ umma_probe_kernel(const uint8_t* __restrict__ image, const __grid_constant__ Pro
 extern "C" int sia_debug_umma_probe(const void* smem_image, int image_bytes, const uint64_t* a_desc_host,
                                     const uint64_t* b_desc_host, int n_mma, int n, float* out_128xn, int repeat,
                                     long long* cycles_host, void* stream) {
+  return sia_debug_umma_probe_ex(smem_image, image_bytes, a_desc_host, b_desc_host, n_mma, n, 0, 0u, out_128xn, repeat,
+                                 cycles_host, stream);
+}
+
+extern "C" int sia_debug_umma_probe_ex(const void* smem_image, int image_bytes, const uint64_t* a_desc_host,
+                                       const uint64_t* b_desc_host, int n_mma, int n, int kind, uint32_t idesc,
+                                       void* out_128xn_raw, int repeat, long long* cycles_host, void* stream) {
   using namespace sia;
+  float* out_128xn = static_cast<float*>(out_128xn_raw);
+  SIA_REQUIRE(kind == 0 || kind == 1);
   SIA_REQUIRE(smem_image && a_desc_host && b_desc_host && out_128xn);
   SIA_REQUIRE(n_mma >= 1 && n_mma <= PROBE_MAX_MMA && n >= 16 && n <= 256 && n % 16 == 0);
   SIA_REQUIRE(image_bytes > 0 && image_bytes % 16 == 0 && image_bytes <= 200 * 1024);
@@ -106,6 +121,8 @@ extern "C" int sia_debug_umma_probe(const void* smem_image, int image_bytes, con
   p.n = n;
   p.image_bytes = image_bytes;
   p.repeat = repeat;
+  p.kind = kind;
+  p.idesc = idesc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   long long* d_cycles = nullptr;
   if (cycles_host) SIA_CUDA_OK(cudaMalloc(&d_cycles, sizeof(long long)));
@@ -325,4 +342,86 @@ extern "C" int sia_debug_alu_rates(double* out_host, int n) {
   const double ops = 1024.0 * RATE_ITERS * RATE_CHAINS;
   for (int k = 0; k < RATE_KINDS; ++k) out_host[k] = ops / (double)h[k];
   return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// TMEM read-rate probe: bytes per SM clock of back-to-back tcgen05.ld for 1 / 4 / 8 warps and the
+// x32 / x8 / x1 shapes (what bounds an epilogue that streams accumulator columns).
+// ----------------------------------------------------------------------------------------------
+namespace sia {
+
+__global__ void __launch_bounds__(256, 1) tmem_rate_kernel(long long* cycles, int n_warps, int shape, uint32_t* sink) {
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) tmem_alloc(&slot, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t base = slot + ((uint32_t)(32 * (warp & 3)) << 16);
+  uint32_t acc = 0;
+  __syncthreads();
+  const long long t0 = clock64();
+  if (warp < n_warps) {
+    for (int it = 0; it < 64; ++it) {
+      if (shape == 32) {
+        uint32_t v[32];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          tmem_ld32(base + ((it * 8 + k) * 32) % 480, v);
+          acc += v[0];
+        }
+      } else if (shape == 8) {
+        uint32_t v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                       : "r"(base + ((it * 8 + k) * 9) % 500)
+                       : "memory");
+          acc += v[0];
+        }
+      } else {
+        uint32_t v;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(base + ((it * 8 + k) * 9) % 500)
+                       : "memory");
+          acc += v;
+        }
+      }
+    }
+    tmem_ld_wait();
+  }
+  const long long t1 = clock64();
+  if (acc == 0x12345u) *sink = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) *cycles = t1 - t0;
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_free(slot, 512);
+}
+
+}  // namespace sia
+
+// out_host[i] = bytes per SM clock for (warps, shape) in {(1,32), (4,32), (8,32), (4,8), (8,8), (4,1)}
+extern "C" int sia_debug_tmem_ld_rates(double* out_host, int n) {
+  using namespace sia;
+  SIA_REQUIRE(out_host && n >= 6);
+  long long* d = nullptr;
+  uint32_t* sink = nullptr;
+  SIA_CUDA_OK(cudaMalloc(&d, sizeof(long long)));
+  SIA_CUDA_OK(cudaMalloc(&sink, sizeof(uint32_t)));
+  const int warps[6] = {1, 4, 8, 4, 8, 4};
+  const int shapes[6] = {32, 32, 32, 8, 8, 1};
+  int rc = 0;
+  for (int i = 0; i < 6 && rc == 0; ++i) {
+    for (int rep = 0; rep < 2; ++rep) tmem_rate_kernel<<<1, 256>>>(d, warps[i], shapes[i], sink);
+    long long h = 0;
+    cudaError_t e = cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { rc = (int)e; break; }
+    out_host[i] = (double)warps[i] * 64 * 8 * shapes[i] * 32 * 4 / (double)h;
+  }
+  cudaFree(d);
+  cudaFree(sink);
+  return rc;
 }

@@ -59,4 +59,8 @@ inline int ensure_dynamic_smem(Kernel kern, int bytes, int* configured) {
 int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle);
 
+// Same for any element type (dims / box in elements of that type).
+int encode_tmap(CUtensorMap* map, CUtensorMapDataType dtype, const void* base, int rank, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle);
+
 }  // namespace sia

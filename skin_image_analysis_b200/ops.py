@@ -53,19 +53,41 @@ def _tables(device_index: int, src_h: int, src_w: int, out_h: int, out_w: int, s
     return _DeviceTables(t, torch.device("cuda", device_index))
 
 
+class _DeviceTcTables:
+    def __init__(self, t: _rw.TcTables, device):
+        self.host = t
+        self.a_packed = torch.from_numpy(t.a_packed).to(device)
+        self.lane_scale = torch.from_numpy(t.lane_scale).to(device)
+        self.tile_row0 = torch.from_numpy(t.tile_row0).to(device)
+        self.items = torch.from_numpy(t.items).to(device)
+
+
+@lru_cache(maxsize=64)
+def _tc_tables(device_index: int, src_h: int, src_w: int, out_h: int, out_w: int, antialias):
+    """Tables of the tensor-core kernel, or None when the geometry does not fit it."""
+    try:
+        t = _rw.build_tc_tables(src_h, src_w, out_h, out_w, antialias=antialias)
+    except ValueError:
+        return None
+    return _DeviceTcTables(t, torch.device("cuda", device_index))
+
+
 _LAYOUT_DTYPE = {LAYOUT_NCHW_F32: torch.float32, LAYOUT_NCHW_BF16: torch.bfloat16, LAYOUT_NHWC4_BF16: torch.bfloat16}
 
 
 def preprocess_u8hwc(src: torch.Tensor, size, layout: int = LAYOUT_NCHW_F32, mean=(0.0, 0.0, 0.0),
                      std=(1.0, 1.0, 1.0), scale: float = 1.0 / 255.0, antialias="skimage",
                      rows_per_cta: int = 32, out: torch.Tensor | None = None,
-                     fixed_point: bool = True) -> torch.Tensor:
+                     fixed_point: bool = True, impl: str = "auto") -> torch.Tensor:
     """[B,H,W,3] uint8 -> resized / scaled / normalised batch in ``layout``.
 
     Defaults reproduce the reference transform exactly: ``float32(u8)/255`` (tone_bias_dataset.py:335),
     ``skimage.transform.resize`` (:425), no mean/std, CHW (:470).  ``fixed_point`` lets the bf16 layouts
     use the 15-bit integer-dot-product horizontal pass (<= 0.03 bf16 ulp from the fp32 pass); the fp32
-    layout always uses fp32 arithmetic.
+    layout always uses fp32 arithmetic.  ``impl``: "cuda_core" (csrc/preprocess.cu), "tensor_core"
+    (csrc/preprocess_tc.cu: vertical pass as a tcgen05 GEMM; NHWC4 layout, src_w % 8 == 0, <= 256 source rows
+    per 128 output rows) or "auto" = tensor_core whenever it applies and ``fixed_point`` allows a reduced-
+    precision pass.
     """
     _need(src, torch.uint8, "src")
     if src.dim() != 4 or src.shape[3] != 3:
@@ -82,6 +104,19 @@ def preprocess_u8hwc(src: torch.Tensor, size, layout: int = LAYOUT_NCHW_F32, mea
             raise ValueError(f"out must have shape {shape}")
     osc = (ctypes.c_float * 3)(*[1.0 / float(s) for s in std])
     obi = (ctypes.c_float * 3)(*[-float(m) / float(s) for m, s in zip(mean, std)])
+    if impl not in ("auto", "cuda_core", "tensor_core"):
+        raise ValueError("impl must be 'auto', 'cuda_core' or 'tensor_core'")
+    if impl == "tensor_core" or (impl == "auto" and fixed_point and layout == LAYOUT_NHWC4_BF16):
+        tc = _tc_tables(src.device.index, sh, sw, oh, ow, antialias) if layout == LAYOUT_NHWC4_BF16 else None
+        if tc is not None and src.data_ptr() % 16 == 0:
+            tsc = (ctypes.c_float * 3)(*[float(scale) / float(s) for s in std])
+            check(_lib.load().sia_preprocess_tc_u8hwc(
+                ptr(src), b, sh, sw, ptr(tc.a_packed), ptr(tc.lane_scale), ptr(tc.tile_row0), tc.host.n_tiles,
+                tc.host.tile_rows, ptr(tc.items), tc.host.n_items, tc.host.n_blocks, tc.host.last_block_cols, oh, ow,
+                tsc, obi, ptr(out), stream_ptr()), "sia_preprocess_tc_u8hwc")
+            return out
+        if impl == "tensor_core":
+            raise SiaError("tensor-core preprocess does not support this geometry / layout")
     check(_lib.load().sia_preprocess_u8hwc(
         ptr(src), b, sh, sw, ptr(tab.x_off), ptr(tab.x_w), ptr(tab.x_wq) if fixed_point else 0, tab.host.x_taps,
         ptr(tab.row_w), ptr(tab.row_emit),
@@ -249,6 +284,22 @@ def umma_probe(image: torch.Tensor, a_descs, b_descs, n: int, repeat: int = 1, w
     check(_lib.load().sia_debug_umma_probe(ptr(image), image.numel(), a, b, k, n, ptr(out), repeat,
                                            ctypes.byref(cyc) if want_cycles else None, stream_ptr()),
           "sia_debug_umma_probe")
+    torch.cuda.synchronize()
+    return (out, cyc.value) if want_cycles else out
+
+
+def umma_probe_i8(image: torch.Tensor, a_descs, b_descs, n: int, idesc: int, repeat: int = 1,
+                  want_cycles: bool = False):
+    """kind::i8 variant of ``umma_probe``: returns the 128 x n int32 accumulator."""
+    _need(image, torch.uint8, "image")
+    k = len(a_descs)
+    a = (ctypes.c_uint64 * k)(*[int(d) for d in a_descs])
+    b = (ctypes.c_uint64 * k)(*[int(d) for d in b_descs])
+    out = torch.zeros((128, n), dtype=torch.int32, device=image.device)
+    cyc = ctypes.c_longlong(0)
+    check(_lib.load().sia_debug_umma_probe_ex(ptr(image), image.numel(), a, b, k, n, 1, int(idesc), ptr(out), repeat,
+                                              ctypes.byref(cyc) if want_cycles else None, stream_ptr()),
+          "sia_debug_umma_probe_ex")
     torch.cuda.synchronize()
     return (out, cyc.value) if want_cycles else out
 

@@ -178,3 +178,154 @@ def rescale_size(h: int, w: int, output_size) -> tuple[int, int]:
     else:
         new_h, new_w = output_size
     return int(new_h), int(new_w)
+
+
+# -------------------------------------------------------------------------------------------------
+# Tables of the tensor-core kernel (csrc/preprocess_tc.cu)
+# -------------------------------------------------------------------------------------------------
+TC_LANES = 128            # output rows per tile = TMEM lanes of one accumulator
+TC_KWIN = 256             # source rows one tile may read (K of the vertical GEMM)
+TC_BLOCK_STRIDE = 240     # image-row bytes between column blocks (multiple of 16)
+TC_BLOCK_COLS = 256       # accumulator columns per block (the 16-byte overlap keeps every item in one block)
+TC_ITEM_PX = 3            # source pixels one schedule item may consume
+TC_ITEM_LOAD = 16         # accumulator columns one item loads (>= 3 * TC_ITEM_PX)
+TC_A_LBO, TC_A_SBO = 128, (TC_KWIN // 8) * 128     # K-major, no swizzle: 8 x 16-byte core matrices
+
+
+@dataclass
+class TcTables:
+    """Vertical operator as per-tile fp16 A operands (already in shared-memory order) + the horizontal
+    operator as a static schedule of items.  Item i consumes up to 3 consecutive source pixels, adds them
+    into the 4 accumulator slots with the item's weights, then emits output column ``emit`` (or nothing)
+    from slot i % 4 and clears that slot."""
+    n_tiles: int
+    tile_rows: int
+    tile_row0: np.ndarray      # int32 [n_tiles]: first source row of the tile's K window
+    a_packed: np.ndarray       # uint8 [n_tiles, 128*256*2]: fp16 weights in UMMA K-major core-matrix order
+    a_dense: np.ndarray        # float64 [n_tiles, 128, 256]: the same weights (fp16-rounded) for tests
+    lane_scale: np.ndarray     # float32 [n_tiles, 128]: sum(w) / sum(fp16(w)) per output row (1 for unused lanes)
+    items: np.ndarray          # float32-viewed [n_items, 16]: (col, emit, block, n_px) as int32, then 3 x 4 weights
+    item_px0: np.ndarray       # int32 [n_items]: first source pixel of each item (tests / emulation)
+    n_blocks: int
+    last_block_cols: int       # MMA N of the last block (multiple of 16)
+
+    @property
+    def n_items(self) -> int:
+        return self.items.shape[0]
+
+
+def build_tc_tables(src_h: int, src_w: int, out_h: int, out_w: int, antialias: str | bool = "skimage") -> TcTables:
+    """Raises ValueError when the geometry does not fit the tensor-core kernel (the caller then uses the
+    CUDA-core kernel): K window > 256 rows per tile, an output column that is live for more than 4
+    schedule items, a row length that is not a multiple of 8 bytes, or an odd number of source rows (the
+    kernel's TMA view pairs rows)."""
+    if antialias == "skimage":
+        aa = out_h < src_h or out_w < src_w
+    else:
+        aa = bool(antialias)
+    if (src_w * 3) % 8 != 0 or src_h % 2 != 0:
+        raise ValueError("tensor-core preprocess needs src_w % 8 == 0 and an even src_h")
+    n_tiles = -(-out_h // TC_LANES)
+    tile_rows = -(-out_h // n_tiles)
+    rows_y = axis_operator_rows(src_h, out_h, aa)
+    tile_row0 = np.zeros(n_tiles, np.int32)
+    a_dense = np.zeros((n_tiles, TC_LANES, TC_KWIN), np.float64)
+    lane_scale = np.ones((n_tiles, TC_LANES), np.float32)
+    for t in range(n_tiles):
+        lo_i, hi_i = t * tile_rows, min(out_h, (t + 1) * tile_rows)
+        r_lo = min(min(rows_y[i]) for i in range(lo_i, hi_i))
+        r_hi = max(max(rows_y[i]) for i in range(lo_i, hi_i))
+        if r_hi - r_lo + 1 > TC_KWIN:
+            raise ValueError(f"vertical window of {r_hi - r_lo + 1} source rows per {tile_rows}-row tile exceeds {TC_KWIN}")
+        tile_row0[t] = r_lo
+        for i in range(lo_i, hi_i):
+            exact = 0.0
+            for r, v in rows_y[i].items():
+                a_dense[t, i - lo_i, r - r_lo] = np.float64(np.float16(v))
+                exact += v
+            lane_scale[t, i - lo_i] = exact / a_dense[t, i - lo_i].sum()
+    # shared-memory image of each A operand: (l, k) at (l/8)*SBO + (k/8)*LBO + (l%8)*16 + (k%8)*2
+    a16 = a_dense.astype(np.float16)
+    a_packed = np.zeros((n_tiles, TC_LANES * TC_KWIN), np.float16)
+    l = np.arange(TC_LANES)[:, None]
+    k = np.arange(TC_KWIN)[None, :]
+    dst = ((l // 8) * TC_A_SBO + (k // 8) * TC_A_LBO + (l % 8) * 16 + (k % 8) * 2) // 2
+    for t in range(n_tiles):
+        a_packed[t, dst.reshape(-1)] = a16[t].reshape(-1)
+
+    # ---- horizontal schedule ------------------------------------------------------------------------
+    rows_x = axis_operator_rows(src_w, out_w, aa)
+    first = [min(r) for r in rows_x]
+    last = [max(r) for r in rows_x]
+    if any(first[j] < first[j - 1] or last[j] < last[j - 1] for j in range(1, out_w)):
+        raise ValueError("horizontal windows are not monotonic")
+    px0, npx, emit = [], [], []
+    cur = 0
+    for j in range(out_w):
+        n = min(last[j], src_w - 1) - cur + 1
+        n = max(n, 0)                      # columns ending on an already consumed pixel (mirror folding): 0-px item
+        while n > TC_ITEM_PX:
+            px0.append(cur); npx.append(TC_ITEM_PX); emit.append(-1)
+            cur += TC_ITEM_PX
+            n -= TC_ITEM_PX
+        px0.append(cur); npx.append(n); emit.append(j)
+        cur += n
+    while len(px0) % 4 != 0 or len(px0) < 8:          # the kernel unrolls 4 items: pad with no-op items
+        px0.append(cur); npx.append(0); emit.append(-1)
+    n_items = len(px0)
+    item_of_col = {e: i for i, e in enumerate(emit) if e >= 0}
+    item_of_px = np.zeros(src_w, np.int64)
+    for i in range(n_items):
+        item_of_px[px0[i]:px0[i] + npx[i]] = i
+    w = np.zeros((n_items, TC_ITEM_PX, N_SLOTS), np.float64)
+    for j, r in enumerate(rows_x):
+        ij = item_of_col[j]
+        for x, v in r.items():
+            it = int(item_of_px[x])
+            if x >= cur or not (ij - (N_SLOTS - 1) <= it <= ij):
+                raise ValueError("an output column is live for more than 4 schedule items")
+            w[it, x - px0[it], ij % N_SLOTS] += v
+    row_bytes = src_w * 3
+    items = np.zeros((n_items, 16), np.float32)
+    info = items.view(np.int32)
+    block = 0
+    for i in range(n_items):
+        if npx[i] > 0:
+            block = (3 * px0[i]) // TC_BLOCK_STRIDE
+            col = 3 * px0[i] - block * TC_BLOCK_STRIDE
+        else:
+            col = 0                        # loads nothing it uses; stay in the current block
+        assert 0 <= col and col + TC_ITEM_LOAD <= TC_BLOCK_COLS
+        info[i, 0:4] = (col, emit[i], block, npx[i])
+        items[i, 4:16] = w[i].reshape(-1)
+    n_blocks = block + 1
+    last_cols = min(TC_BLOCK_COLS, -(-(row_bytes - (n_blocks - 1) * TC_BLOCK_STRIDE) // 16) * 16)
+    return TcTables(n_tiles, tile_rows, tile_row0, a_packed.view(np.uint8).reshape(n_tiles, -1), a_dense, lane_scale,
+                    items, np.asarray(px0, np.int32), n_blocks, last_cols)
+
+
+def tc_emulate(u8: np.ndarray, t: TcTables, out_h: int, out_w: int, scale: float = 1.0 / 255.0) -> np.ndarray:
+    """numpy model of the tensor-core kernel's arithmetic (fp16 vertical weights, exact products, fp32
+    horizontal pass driven by the item schedule) -> [out_h, out_w, 3] float32.  Pins the tables on the CPU."""
+    src_h, src_w, _ = u8.shape
+    s = u8.reshape(src_h, src_w * 3).astype(np.float64)
+    out = np.full((out_h, out_w, 3), np.nan, np.float32)
+    info = t.items.view(np.int32)
+    for tile in range(t.n_tiles):
+        rows = np.clip(t.tile_row0[tile] + np.arange(TC_KWIN), 0, src_h - 1)
+        v = (t.a_dense[tile] @ s[rows]).astype(np.float32)              # [128, row_bytes]
+        v = np.concatenate([v, np.zeros((TC_LANES, 3 * TC_ITEM_PX), np.float32)], axis=1)
+        acc = np.zeros((TC_LANES, N_SLOTS, 3), np.float32)
+        lanes = min(t.tile_rows, out_h - tile * t.tile_rows)
+        for i in range(t.n_items):
+            col, emit, block, _n = (int(z) for z in info[i, :4])
+            base = block * TC_BLOCK_STRIDE + col
+            wts = t.items[i, 4:16].reshape(TC_ITEM_PX, N_SLOTS)
+            for kk in range(TC_ITEM_PX):
+                px = v[:, base + 3 * kk: base + 3 * kk + 3]
+                acc += wts[kk][None, :, None] * px[:, None, :]
+            if emit >= 0:
+                o = acc[:lanes, i % N_SLOTS] * (t.lane_scale[tile, :lanes, None] * np.float32(scale))
+                out[tile * t.tile_rows: tile * t.tile_rows + lanes, emit] = o
+            acc[:, i % N_SLOTS] = 0
+    return out

@@ -109,3 +109,55 @@ def test_rescale_dropin_tuple_semantics():
     assert (label, idx) == (1, 42) and img.shape == (64, 86, 3) and img.dtype == np.float32
     t, _, _ = ToTensor()((img, label, idx))
     assert np.abs(t.numpy() - R.transform_u8(u8, 64)).max() <= F32_TOL
+
+
+@pytest.mark.parametrize("src_hw,size,batch", [((450, 600), (224, 224), 5), ((480, 640), (224, 224), 2),
+                                               ((450, 600), (512, 512), 2), ((300, 400), (224, 224), 3)])
+def test_tensor_core_pass_matches_oracle(src_hw, size, batch):
+    """csrc/preprocess_tc.cu (vertical pass as a tcgen05 GEMM): within one bf16 ulp of the bf16-rounded
+    oracle, <= 2.5e-4 of full scale before rounding, bit-identical to the numpy model of its arithmetic
+    up to fp32 summation order, and batch / CTA-assignment independent."""
+    from skin_image_analysis_b200 import ops
+    from skin_image_analysis_b200 import resize_weights as rw
+    kinds = ["noise", "smooth", "extremes", "noise", "smooth"]
+    imgs = [helpers.synthetic_u8_image(src_hw[0], src_hw[1], 300 + i, kinds[i]) for i in range(batch)]
+    got = _gpu(imgs, size, ops.LAYOUT_NHWC4_BF16, impl="tensor_core").float().cpu().numpy()
+    assert got.shape == (batch, size[0], size[1] + ops.NHWC4_PAD, 4)
+    assert np.all(got[..., 3] == 0) and np.all(got[:, :, 0] == 0) and np.all(got[:, :, size[1] + 1:] == 0)
+    want = np.stack([R.transform_u8(im, size) for im in imgs]).transpose(0, 2, 3, 1)
+    want_bf = torch.from_numpy(want).to(torch.bfloat16).float().numpy()
+    px = got[:, :, 1:size[1] + 1, :3]
+    ulp = np.maximum(np.abs(want_bf), 2.0 ** -126) * 2.0 ** -7
+    assert np.all(np.abs(px - want_bf) <= ulp)
+    assert np.abs(px - want).max() <= 2.0 ** -8 + 2.5e-4
+    assert (px != want_bf).mean() < 0.05
+    t = rw.build_tc_tables(src_hw[0], src_hw[1], size[0], size[1])
+    model = rw.tc_emulate(imgs[0], t, size[0], size[1])
+    model_bf = torch.from_numpy(model).to(torch.bfloat16).float().numpy()
+    assert (px[0] != model_bf).mean() < 1e-3            # fp32 summation order only
+    old = _gpu(imgs, size, ops.LAYOUT_NHWC4_BF16, impl="cuda_core").float().cpu().numpy()
+    assert np.all(np.abs(got - old) <= np.maximum(np.abs(old), 2.0 ** -126) * 2.0 ** -7)
+    single = _gpu(imgs[-1:], size, ops.LAYOUT_NHWC4_BF16, impl="tensor_core").float().cpu().numpy()
+    assert np.array_equal(single[0], got[-1])
+
+
+def test_tensor_core_pass_large_batch_and_mean_std():
+    """More images than CTAs per tile (every CTA loops), non-trivial mean / std, flat images exact."""
+    from skin_image_analysis_b200 import ops
+    rng = np.random.default_rng(5)
+    base = [helpers.synthetic_u8_image(450, 600, 400 + i, "noise") for i in range(4)]
+    idx = rng.integers(0, 4, 170)
+    x = torch.from_numpy(np.stack(base)).cuda()[torch.from_numpy(idx).cuda()]
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    got = ops.preprocess_u8hwc(x, (224, 224), ops.LAYOUT_NHWC4_BF16, mean=mean, std=std, impl="tensor_core")
+    ref = ops.preprocess_u8hwc(torch.from_numpy(np.stack(base)).cuda(), (224, 224), ops.LAYOUT_NHWC4_BF16,
+                               mean=mean, std=std, impl="tensor_core")
+    assert torch.equal(got, ref[torch.from_numpy(idx).cuda()])
+    want = np.stack([R.transform_u8(im, (224, 224)) for im in base]).transpose(0, 2, 3, 1)
+    want = (want - np.float32(mean)) / np.float32(std)
+    px = ref[:, :, 1:225, :3].float().cpu().numpy()
+    assert np.abs(px - want).max() <= 2.0 ** -6 + 2e-3          # bf16 rounding at |v| <= 2.7 + the fp16 weights
+    for v in (0, 1, 127, 200, 255):
+        const = np.full((450, 600, 3), v, np.uint8)
+        out = _gpu([const], (224, 224), ops.LAYOUT_NHWC4_BF16, impl="tensor_core")[0, :, 1:225, :3].float().cpu().numpy()
+        assert np.all(out == torch.tensor(np.float32(v) / 255.0).to(torch.bfloat16).float().item()), v

@@ -150,3 +150,39 @@ def test_no_cuda_no_fallback():
         tt.analyse_predictions(helpers.synthetic_instances(10, 1, False))
     with pytest.raises(SiaError):
         Rescale((8, 8))((np.zeros((16, 16, 3), np.float32), 0, 0))
+
+
+@pytest.mark.parametrize("shape", [(450, 600, 224, 224), (450, 600, 512, 512), (96, 128, 40, 56), (100, 64, 50, 30)])
+def test_tensor_core_tables_reproduce_the_oracle_operator(shape):
+    """The numpy model of csrc/preprocess_tc.cu (fp16 vertical weights, 4-slot horizontal schedule) stays
+    within 2.5e-4 of full scale of the oracle resize, and every output pixel is emitted exactly once."""
+    import numpy as np
+    from oracle import resize as R
+    from skin_image_analysis_b200 import resize_weights as rw
+    h, w, oh, ow = shape
+    t = rw.build_tc_tables(h, w, oh, ow)
+    assert t.n_tiles * t.tile_rows >= oh and t.tile_rows <= 128
+    info = t.items.view(np.int32)
+    emitted = info[info[:, 1] >= 0, 1]
+    assert np.array_equal(emitted, np.arange(ow))                 # every output column exactly once, in order
+    assert np.all(info[:, 0] >= 0) and np.all(info[:, 0] + rw.TC_ITEM_LOAD <= rw.TC_BLOCK_COLS)
+    assert np.all(np.diff(info[:, 2]) >= 0) and info[-1, 2] == t.n_blocks - 1 and np.all(info[:, 3] <= rw.TC_ITEM_PX)
+    assert info[:, 3].sum() == w                                   # every source pixel consumed exactly once
+    assert t.a_packed.shape == (t.n_tiles, 128 * 256 * 2)
+    rng = np.random.default_rng(h + ow)
+    im = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    got = rw.tc_emulate(im, t, oh, ow)
+    want = R.transform_u8(im, (oh, ow)).transpose(1, 2, 0)
+    assert np.abs(got - want).max() <= 2.5e-4
+    # A operand image: element (l, k) of tile 0 sits where the UMMA K-major core-matrix layout expects it
+    a = t.a_packed[0].view(np.float16)
+    for l, k in ((0, 0), (5, 3), (9, 17), (127, 255), (64, 100)):
+        off = ((l // 8) * rw.TC_A_SBO + (k // 8) * rw.TC_A_LBO + (l % 8) * 16 + (k % 8) * 2) // 2
+        assert float(a[off]) == t.a_dense[0, l, k]
+
+
+def test_tensor_core_tables_reject_unsupported_geometry():
+    from skin_image_analysis_b200 import resize_weights as rw
+    for shape in ((97, 131, 64, 86), (1024, 1024, 224, 224), (64, 64, 128, 128), (450, 601, 224, 224)):
+        with pytest.raises(ValueError):
+            rw.build_tc_tables(*shape)
