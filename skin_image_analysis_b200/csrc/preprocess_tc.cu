@@ -17,10 +17,12 @@
 //             double buffered.
 //   horizontal pass  out[i, j, c] = sum_x Wx[j, x] * V[i, 3x + c]
 //       = the epilogue: thread = TMEM lane = output row.  It executes a static schedule of "items" built
-//         on the host (resize_weights.build_tc_tables): item n loads 16 accumulator columns (<= 3 source
+//         on the host (resize_weights.build_tc_tables): item n loads 9 accumulator columns (<= 3 source
 //         pixels), adds them into 4 accumulator slots with the item's 3 x 4 weights, then emits one output
 //         pixel from slot n % 4 (scale, bias, bf16, 8 bytes of NHWC4) and clears it.  Four items are
-//         unrolled, so every slot index is a compile-time constant: straight-line FFMA code.
+//         unrolled, so every slot index is a compile-time constant: straight-line FFMA code.  Two images
+//         are in flight per CTA, one per warp group and TMEM accumulator, because a single warp per
+//         scheduler cannot hide the TMEM-load latency.
 //
 // Why: the CUDA-core kernel is issue-bound (~150 instructions per source row x output column, most of
 // them unpacking interleaved bytes).  Here the 6-tap vertical contraction -- the one with the larger
@@ -46,7 +48,7 @@ constexpr int TC_B_LBO = 128;                    // next group of 8 source rows
 constexpr int TC_B_SBO = (TC_KSTAGE / 8) * 128 + 16;   // next 8 bytes of the row (+16: bank spread for the converter)
 constexpr int TC_STAGE_BYTES = ((TC_UNITS * TC_B_SBO + 127) / 128) * 128;
 constexpr int TC_NSTAGE = 2;                     // fp16 operand stages (converter -> MMA)
-constexpr int TC_NRAW = 4;                       // raw u8 stages (TMA -> converter); 3 when the item table is large
+constexpr int TC_NRAW = 4;                       // raw u8 stages (TMA -> converter); fewer when the item table is large
 constexpr int TC_RAW_ROWB = TC_COLS + 16;        // bytes per raw row: odd rows start up to 8 bytes early
 constexpr int TC_RAW_HALF = (TC_KSTAGE / 2) * TC_RAW_ROWB;   // even-row box, then odd-row box
 constexpr int TC_RAW_BYTES = 2 * TC_RAW_HALF;
@@ -54,7 +56,9 @@ constexpr int TC_A_BYTES = 128 * TC_KWIN * 2;    // 65536
 constexpr int TC_A_LBO = 128, TC_A_SBO = (TC_KWIN / 8) * 128;
 constexpr int TC_THREADS = 448;                  // warps 0-3 converters, 4-7 / 8-11 horizontal-pass groups 0 / 1,
 constexpr int TC_WARP_MMA = 12;                  // 12 MMA issuer (+ TMEM alloc), 13 TMA producer
-constexpr int TC_WARP_TMA = 13;
+constexpr int TC_WARP_TMA = 13;                  // (16 warps x 128 registers is what one SM sub-partition quartet holds)
+constexpr int TC_CONV_GROUPS = 1;                // converter groups of 4 warps taking alternate stages
+constexpr int TC_WARP_CONV1 = 14;                // first warp of converter group 1 (if any)
 constexpr int TC_ITEM_BYTES = 64;                // int4 {column, emit, block, n_px} + 3 x float4 weights
 
 struct TcParams {
@@ -80,6 +84,9 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                : "r"(taddr)
                : "memory");
+}
+__device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t& v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld16p(uint32_t taddr, uint32_t* v) {
   asm volatile(
@@ -157,11 +164,13 @@ preprocess_tc_kernel(const __grid_constant__ CUtensorMap tmap_src, const __grid_
         for (int blk = 0; blk < p.n_blocks; ++blk) {
           for (int g = 0; g < 2 && k0 + g < n_img; ++g) {
             const int img = img0 + (k0 + g) * img_step;
+            const int seq = ((k0 >> 1) * p.n_blocks + blk) * 2 + g;
             for (int q = 0; q < TC_NQ; ++q) {
               const int r0 = row0 + q * TC_KSTAGE;           // first source row of the stage
               const int even0 = (r0 + 1) >> 1;               // double row of the first even / odd row
               const int odd0 = r0 >> 1;
               mbar_wait(&raw_empty[rs], rphase ^ 1, 45);
+              if (q == 0) trace(seq, 0);
               mbar_arrive_expect_tx(&raw_full[rs], TC_RAW_BYTES);
               uint8_t* dst = smem_raw_ring + rs * TC_RAW_BYTES;
               // innermost coordinate in 16-bit elements (the tensor map views the bytes as u16 pairs so that a
@@ -169,30 +178,36 @@ preprocess_tc_kernel(const __grid_constant__ CUtensorMap tmap_src, const __grid_
               tma_load_3d(dst, &tmap_src, &raw_full[rs], (blk * TC_STRIDE) >> 1, even0, img);
               tma_load_3d(dst + TC_RAW_HALF, &tmap_src, &raw_full[rs],
                           (row_bytes - p.odd_shift + blk * TC_STRIDE) >> 1, odd0, img);
+              if (q == TC_NQ - 1) trace(seq, 1);
               if (++rs == p.n_raw) { rs = 0; rphase ^= 1; }
             }
           }
         }
       }
     }
-  } else if (warp < 4) {
+  } else if (warp < 4 || (TC_CONV_GROUPS > 1 && warp >= TC_WARP_CONV1)) {
     // ================================ converters ============================================
-    // warp w owns rows w, w+4, ... of every 64-row stage (a fixed row parity); lane l owns bytes 8l .. 8l+7.
-    int stage = 0, rs = 0;
-    uint32_t phase = 0, rphase = 0;
-    const uint32_t parity = (uint32_t)(row0 + warp) & 1u;      // absolute parity of this warp's rows
+    // Two groups of four warps take alternate stages.  Inside a stage warp w owns rows w, w+4, ... (a fixed row
+    // parity); lane l owns bytes 8l .. 8l+7 of the block.
+    const int cgroup = warp < 4 ? 0 : 1;
+    const int cw = warp < 4 ? warp : warp - TC_WARP_CONV1;    // warp inside the group
+    const uint32_t parity = (uint32_t)(row0 + cw) & 1u;        // absolute parity of this warp's rows
     const uint32_t ld_lane = parity * (TC_RAW_HALF + (uint32_t)p.odd_shift) + (uint32_t)lane * 8u;
     const uint32_t st_lane = (uint32_t)lane * TC_B_SBO;
     const __half2 k1024 = __half2half2(__ushort_as_half((unsigned short)0x6400));
     const int n_stages = n_img * p.n_blocks * TC_NQ;
-    for (int it0 = 0; it0 < n_stages; ++it0) {
+    // ring positions of stage `cgroup`, advanced by the number of groups per iteration
+    int stage = cgroup % TC_NSTAGE, rs = cgroup % p.n_raw;
+    uint32_t phase = 0, rphase = 0;
+    for (int it0 = cgroup; it0 < n_stages; it0 += TC_CONV_GROUPS) {
       mbar_wait(&raw_full[rs], rphase, 46);
+      if (cw == 0 && lane == 0 && (it0 & (TC_NQ - 1)) == 0) trace(it0 / TC_NQ, 2);
       uint2 v[TC_KSTAGE / 4];
       {
         const uint32_t src = smem_u32(smem_raw_ring) + rs * TC_RAW_BYTES + ld_lane;
 #pragma unroll
         for (int it = 0; it < TC_KSTAGE / 4; ++it) {
-          const int r = warp + 4 * it;
+          const int r = cw + 4 * it;
           asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];"
                        : "=r"(v[it].x), "=r"(v[it].y)
                        : "r"(src + (uint32_t)(r >> 1) * TC_RAW_ROWB));
@@ -203,7 +218,7 @@ preprocess_tc_kernel(const __grid_constant__ CUtensorMap tmap_src, const __grid_
         const uint32_t base = smem_u32(smem_b) + stage * TC_STAGE_BYTES + st_lane;
 #pragma unroll
         for (int it = 0; it < TC_KSTAGE / 4; ++it) {
-          const int r = warp + 4 * it;             // row inside the stage
+          const int r = cw + 4 * it;               // row inside the stage
           // u8 -> fp16, exact: byte b becomes the half 0x6400 | b = 1024 + b, then subtract 1024
           uint32_t h[4];
           h[0] = __byte_perm(v[it].x, 0x64646464u, 0x4140);
@@ -226,9 +241,12 @@ preprocess_tc_kernel(const __grid_constant__ CUtensorMap tmap_src, const __grid_
       if (lane == 0) {
         mbar_arrive(&full_bar[stage]);
         mbar_arrive(&raw_empty[rs]);
+        if (cw == 0 && (it0 & (TC_NQ - 1)) == TC_NQ - 1) trace(it0 / TC_NQ, 3);
       }
-      if (++stage == TC_NSTAGE) { stage = 0; phase ^= 1; }
-      if (++rs == p.n_raw) { rs = 0; rphase ^= 1; }
+      stage += TC_CONV_GROUPS;
+      if (stage >= TC_NSTAGE) { stage -= TC_NSTAGE; phase ^= 1; }
+      rs += TC_CONV_GROUPS;
+      if (rs >= p.n_raw) { rs -= p.n_raw; rphase ^= 1; }
     }
   } else if (warp == TC_WARP_MMA) {
     // ================================ MMA issuer ============================================
@@ -246,9 +264,13 @@ preprocess_tc_kernel(const __grid_constant__ CUtensorMap tmap_src, const __grid_
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           if (k0 + g < n_img) {
+            const int seq = ((k0 >> 1) * p.n_blocks + blk) * 2 + g;
+#ifndef SIA_TC_FREE
             mbar_wait(&tempty_bar[g], acc_phase[g] ^ 1, 42);
+#endif
             acc_phase[g] ^= 1;
             tc_fence_after_sync();
+            if (lane == 0) trace(seq, 4);
             const uint32_t d_tmem = tmem_base + g * TC_COLS;
             for (int q = 0; q < TC_NQ; ++q) {
               mbar_wait(&full_bar[stage], phase, 43);
@@ -267,6 +289,7 @@ preprocess_tc_kernel(const __grid_constant__ CUtensorMap tmap_src, const __grid_
               __syncwarp();
               if (++stage == TC_NSTAGE) { stage = 0; phase ^= 1; }
             }
+            if (lane == 0) trace(seq, 5);
           }
         }
       }
@@ -303,71 +326,98 @@ preprocess_tc_kernel(const __grid_constant__ CUtensorMap tmap_src, const __grid_
       auto acquire = [&](int block) {
         while (cur_block < block) {
           if (cur_block >= 0) {
+            tmem_ld_wait();                        // loads of the block being handed back may still be in flight
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty);
+            if (e == 0 && lane == 0) trace(((k >> 1) * p.n_blocks + cur_block) * 2 + g, 7);
           }
+#ifndef SIA_TC_FREE
           mbar_wait(tfull, acc_phase, 44);
+#endif
           acc_phase ^= 1;
           tc_fence_after_sync();
           ++cur_block;
+          if (e == 0 && lane == 0) trace(((k >> 1) * p.n_blocks + cur_block) * 2 + g, 6);
         }
       };
 
-      // software pipeline over the items (n_items is a multiple of 4, padded with no-op items):
-      //   two items ahead : the item's info word           (LDS)
-      //   one item ahead  : its 16 accumulator columns      (tcgen05.ld) and its 12 weights (LDS)
-      //   this item       : 36 FFMA, one predicated 8-byte store
-      uint32_t va[16], vb[16];
-      float4 wa[3], wb[3];
-      uint4 info_cur = items_s[0];
-      uint4 info_nxt = items_s[4];
-      acquire((int)info_cur.z);
-      tmem_ld16p(t_acc + info_cur.x, va);
-      wa[0] = *reinterpret_cast<const float4*>(&items_s[1]);
-      wa[1] = *reinterpret_cast<const float4*>(&items_s[2]);
-      wa[2] = *reinterpret_cast<const float4*>(&items_s[3]);
-      for (int n0 = 0; n0 < p.n_items; n0 += 4) {
+      // Items are processed in groups of 4 (n_items is a multiple of 8, padded with no-op items).  tcgen05.wait::ld
+      // waits for EVERY outstanding load, so loads are pipelined a whole group ahead: the 4 x 9 accumulator columns
+      // of group m+1 are requested right after the wait that delivers group m and land while group m is computed
+      // (~36 FFMA + one predicated 8-byte store per item).
+      uint32_t va[4][9], vb[4][9];
+      auto load_group = [&](int n0, uint32_t (&v)[4][9]) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int n = n0 + u;
-          uint32_t (&v)[16] = (u & 1) ? vb : va;
-          uint32_t (&vn)[16] = (u & 1) ? va : vb;
-          float4 (&w)[3] = (u & 1) ? wb : wa;
-          float4 (&wn)[3] = (u & 1) ? wa : wb;
-          tmem_ld_wait();                            // v (issued one item ago) has landed
-          const uint4 info_nn = items_s[4 * min(n + 2, p.n_items - 1)];
-          if (n + 1 < p.n_items) {
-            if ((int)info_nxt.z != cur_block) acquire((int)info_nxt.z);
-            tmem_ld16p(t_acc + info_nxt.x, vn);      // in flight while this item is computed
-            wn[0] = *reinterpret_cast<const float4*>(&items_s[4 * (n + 1) + 1]);
-            wn[1] = *reinterpret_cast<const float4*>(&items_s[4 * (n + 1) + 2]);
-            wn[2] = *reinterpret_cast<const float4*>(&items_s[4 * (n + 1) + 3]);
+          const uint4 info = items_s[4 * (n0 + u)];
+          if ((int)info.z != cur_block) acquire((int)info.z);
+          tmem_ld8(t_acc + info.x, v[u]);
+          tmem_ld1(t_acc + info.x + 8, v[u][8]);
+        }
+      };
+      auto compute_group = [&](int n0, const uint32_t (&v)[4][9]) {
+        uint4 it[4];                                 // info + weights of the item being computed
+        float4 w_next[3];
+        int emit_next;
+        {
+          const uint4 i0 = items_s[4 * n0];
+          emit_next = (int)i0.y;
+#pragma unroll
+          for (int q = 0; q < 3; ++q) w_next[q] = *reinterpret_cast<const float4*>(&items_s[4 * n0 + 1 + q]);
+        }
+        (void)it;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float4 w0 = w_next[0], w1 = w_next[1], w2 = w_next[2];
+          const int j = emit_next;
+          if (u < 3) {                               // next item's table entry in flight during this item's FFMAs
+            emit_next = (int)items_s[4 * (n0 + u + 1)].y;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) w_next[q] = *reinterpret_cast<const float4*>(&items_s[4 * (n0 + u + 1) + 1 + q]);
           }
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
-            const float f0 = __uint_as_float(v[c]), f1 = __uint_as_float(v[3 + c]), f2 = __uint_as_float(v[6 + c]);
-            acc[0][c] = fmaf(w[2].x, f2, fmaf(w[1].x, f1, fmaf(w[0].x, f0, acc[0][c])));
-            acc[1][c] = fmaf(w[2].y, f2, fmaf(w[1].y, f1, fmaf(w[0].y, f0, acc[1][c])));
-            acc[2][c] = fmaf(w[2].z, f2, fmaf(w[1].z, f1, fmaf(w[0].z, f0, acc[2][c])));
-            acc[3][c] = fmaf(w[2].w, f2, fmaf(w[1].w, f1, fmaf(w[0].w, f0, acc[3][c])));
+            const float f0 = __uint_as_float(v[u][c]), f1 = __uint_as_float(v[u][3 + c]),
+                        f2 = __uint_as_float(v[u][6 + c]);
+            acc[0][c] = fmaf(w2.x, f2, fmaf(w1.x, f1, fmaf(w0.x, f0, acc[0][c])));
+            acc[1][c] = fmaf(w2.y, f2, fmaf(w1.y, f1, fmaf(w0.y, f0, acc[1][c])));
+            acc[2][c] = fmaf(w2.z, f2, fmaf(w1.z, f1, fmaf(w0.z, f0, acc[2][c])));
+            acc[3][c] = fmaf(w2.w, f2, fmaf(w1.w, f1, fmaf(w0.w, f0, acc[3][c])));
           }
-          {                                          // slot u is complete: one NHWC4 pixel (predicated store)
-            const int j = (int)info_cur.y;
-            const uint32_t ox = pack_bf16x2(fmaf(acc[u][0], sc0, bi0), fmaf(acc[u][1], sc1, bi1));
-            const uint32_t oy = pack_bf16x2(fmaf(acc[u][2], sc2, bi2), 0.f);
-            const uint32_t ok = (j >= 0 && row_ok) ? 1u : 0u;
-            asm volatile(
-                "{\n\t.reg .pred p;\n\t"
-                "setp.ne.b32 p, %3, 0;\n\t"
-                "@p st.global.v2.b32 [%0], {%1, %2};\n\t}"
-                ::"l"(orow + (j + 1)), "r"(ox), "r"(oy), "r"(ok)
-                : "memory");
-            acc[u][0] = acc[u][1] = acc[u][2] = 0.f;
-          }
-          info_cur = info_nxt;
-          info_nxt = info_nn;
+          // slot u is complete: one NHWC4 pixel (predicated store), then the slot restarts
+          const uint32_t ox = pack_bf16x2(fmaf(acc[u][0], sc0, bi0), fmaf(acc[u][1], sc1, bi1));
+          const uint32_t oy = pack_bf16x2(fmaf(acc[u][2], sc2, bi2), 0.f);
+#ifdef SIA_TC_NOSTORE
+          const uint32_t ok = (j == 123456 && row_ok) ? 1u : 0u;
+#else
+          const uint32_t ok = (j >= 0 && row_ok) ? 1u : 0u;
+#endif
+          asm volatile(
+              "{\n\t.reg .pred p;\n\t"
+              "setp.ne.b32 p, %3, 0;\n\t"
+              "@p st.global.v2.b32 [%0], {%1, %2};\n\t}"
+              ::"l"(orow + (j + 1)), "r"(ox), "r"(oy), "r"(ok)
+              : "memory");
+          acc[u][0] = acc[u][1] = acc[u][2] = 0.f;
         }
+      };
+
+#ifdef SIA_TC_NOEPI
+      for (int bb = 0; bb < p.n_blocks; ++bb) acquire(bb);
+      if (false)
+#endif
+      load_group(0, va);
+#ifdef SIA_TC_NOEPI
+      if (false)
+#endif
+      for (int n0 = 0; n0 < p.n_items; n0 += 8) {
+        tmem_ld_wait();                              // group n0 has landed
+        load_group(n0 + 4, vb);
+        compute_group(n0, va);
+        tmem_ld_wait();                              // group n0 + 4 has landed
+        if (n0 + 8 < p.n_items) load_group(n0 + 8, va);
+        compute_group(n0 + 4, vb);
       }
       // hand the last accumulator(s) of this image back
       acquire(p.n_blocks - 1);
@@ -392,7 +442,7 @@ extern "C" int sia_preprocess_tc_u8hwc(const uint8_t* src, int batch, int src_h,
   using namespace sia;
   SIA_REQUIRE(src && a_packed && lane_scale && tile_row0 && items && dst_nhwc4 && out_scale_host && out_bias_host);
   SIA_REQUIRE(batch >= 1 && src_h >= 2 && src_w >= 8 && out_h >= 1 && out_w >= 1 && n_tiles >= 1);
-  SIA_REQUIRE(n_items >= 8 && n_items % 4 == 0);
+  SIA_REQUIRE(n_items >= 8 && n_items % 8 == 0);
   SIA_REQUIRE(tile_rows >= 1 && tile_rows <= 128 && n_tiles * tile_rows >= out_h && n_blocks >= 1);
   SIA_REQUIRE(last_block_cols >= 16 && last_block_cols <= TC_COLS && last_block_cols % 16 == 0);
   SIA_REQUIRE(aligned(a_packed, 16) && aligned(items, 16) && aligned(dst_nhwc4, 8));

@@ -270,7 +270,7 @@ def build_tc_tables(src_h: int, src_w: int, out_h: int, out_w: int, antialias: s
             n -= TC_ITEM_PX
         px0.append(cur); npx.append(n); emit.append(j)
         cur += n
-    while len(px0) % 4 != 0 or len(px0) < 8:          # the kernel unrolls 4 items: pad with no-op items
+    while len(px0) % 8 != 0:                          # the kernel works on groups of 4 + 4 items: pad with no-ops
         px0.append(cur); npx.append(0); emit.append(-1)
     n_items = len(px0)
     item_of_col = {e: i for i, e in enumerate(emit) if e >= 0}
