@@ -119,7 +119,7 @@ int sia_pack_linear_chw_to_hwc(const float* w, int n, int c, int hw, void* packe
  * K4  convolution blocks: conv + bias + ReLU + 2x2/2 max-pool, bf16 in / fp32 accumulate / bf16 out.
  *   in  : padded NHWC4 bf16 [B,h,w+8,4] (conv7x7_c3)  or NHWC bf16 [B,h,w,cin] (conv3x3)
  *   out : NHWC bf16 [B,h/2,w/2,cout]
- * h must be even; conv7x7_c3 needs w%16==0; conv3x3 needs w%8==0.
+ * h and w must be even; conv7x7_c3 needs w%16==0 (conv3x3 tiles past the right / bottom edge are masked).
  * Supported (cin,cout): (32,64), (64,128), (128,256).
  * ------------------------------------------------------------------------------------------ */
 int sia_conv7x7_c3_relu_pool2(const void* in_nhwc4, int batch, int h, int w, const void* w_packed,

@@ -50,8 +50,7 @@ struct ConvCfg {
   static constexpr int B_TAP_BYTES = COUT * ROWB;       // one (tap, chunk) weight block
   static constexpr int B_BYTES = 9 * NCHUNK * B_TAP_BYTES;
   static constexpr int BIAS_BYTES = COUT * 32;          // [COUT rows][16 k] bf16: k0 = hi(bias), k1 = lo(bias)
-  static constexpr int TMEM_COLS = CV_NACC * COUT;
-  static_assert(TMEM_COLS <= 512, "accumulator ring does not fit TMEM");
+  static constexpr int TMEM_COLS = CV_NACC * COUT;     // resident-weight kernel: ring of CV_NACC accumulators
 };
 
 // Decomposes the persistent-CTA tile stride once, so that walking tiles needs no integer division.
@@ -105,6 +104,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
                const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int H, int W, int tiles_y,
                int tiles_x, int total_tiles) {
   using C = ConvCfg<CIN, COUT>;
+  static_assert(C::TMEM_COLS <= 512, "accumulator ring does not fit TMEM");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // keep the shared address space visible to the compiler (offset arithmetic, no integer round trip)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -326,6 +326,219 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
   if (warp == 2) tmem_free(tmem_base, C::TMEM_COLS);
 }
 
+
+// ------------------------------- streamed-weight variant --------------------------------------
+// Conv2d(128, 256, 3): 9 * 128 * 256 bf16 weights = 576 KB do not fit in shared memory, so they stream from L2
+// through a ring of (tap, 64-channel chunk) blocks of 32 KB while TWO tiles stay resident: both halo buffers in
+// shared memory, both 128 x 256 fp32 accumulators in TMEM (all 512 columns).  Every weight block is used by both
+// tiles, which halves the L2 traffic per FLOP.  Epilogue group t (four warps) drains accumulator t; the MMA warp
+// starts the next pair once both are drained.
+constexpr int CS_NB = 3;            // weight-block ring
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(CV_THREADS, 1)
+conv3x3_stream_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restrict__ w_packed,
+                      const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int H, int W, int tiles_y,
+                      int tiles_x, int total_tiles) {
+  using C = ConvCfg<CIN, COUT>;
+  static_assert(2 * COUT <= 512, "two accumulators must fit TMEM");
+  constexpr int NBLK = 9 * C::NCHUNK;                  // weight blocks per tile pair
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* smem_b = smem;                               // CS_NB * B_TAP_BYTES
+  uint8_t* smem_a = smem + CS_NB * C::B_TAP_BYTES;      // 2 * STAGE_STRIDE
+  uint8_t* smem_ones = smem_a + 2 * C::STAGE_STRIDE;
+  uint8_t* smem_biasop = smem_ones + ONES_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_biasop + C::BIAS_BYTES);
+  uint64_t* b_full = bars;                 // [CS_NB]
+  uint64_t* b_empty = bars + CS_NB;        // [CS_NB]
+  uint64_t* a_full = bars + 2 * CS_NB;     // both halos landed
+  uint64_t* a_empty = a_full + 1;          // MMAs of the pair have read them
+  uint64_t* tfull_bar = a_full + 2;        // accumulators complete
+  uint64_t* tempty_bar = a_full + 3;       // [2] drained by epilogue group t
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 5);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_pairs = (total_tiles + 1) / 2;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < CS_NB; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    mbar_init(a_full, 1);
+    mbar_init(a_empty, 1);
+    mbar_init(tfull_bar, 1);
+    mbar_init(&tempty_bar[0], 4);
+    mbar_init(&tempty_bar[1], 4);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmap_in);
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  fill_ones_operand(smem_ones, threadIdx.x, blockDim.x);
+  fill_bias_operand(smem_biasop, bias, COUT, COUT, threadIdx.x, blockDim.x);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = bcast0(*tmem_slot);
+  const int tiles_per_img = tiles_x * tiles_y;
+
+  if (warp == 0) {
+    // ================================ producer ==============================================
+    if (lane == 0) {
+      int bs = 0;
+      uint32_t bphase = 0, pphase = 0;
+      for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+        mbar_wait(a_empty, pphase ^ 1, 25);
+        const int n_tiles = (2 * pair + 1 < total_tiles) ? 2 : 1;
+        mbar_arrive_expect_tx(a_full, n_tiles * C::STAGE_TX_BYTES);
+        for (int t = 0; t < n_tiles; ++t) {
+          const int tile = 2 * pair + t;
+          const int n = tile / tiles_per_img, rem = tile % tiles_per_img;
+          const int ty = rem / tiles_x, tx = rem % tiles_x;
+#pragma unroll
+          for (int kc = 0; kc < C::NCHUNK; ++kc) {
+            tma_load_4d(smem_a + t * C::STAGE_STRIDE + kc * C::CHUNK_STRIDE, &tmap_in, a_full, kc * C::CK,
+                        tx * CV_TILE_X - 1, ty * CV_TILE_Y - 1, n);
+          }
+        }
+        pphase ^= 1;
+        for (int blk = 0; blk < NBLK; ++blk) {
+          mbar_wait(&b_empty[bs], bphase ^ 1, 26);
+          mbar_arrive_expect_tx(&b_full[bs], C::B_TAP_BYTES);
+          constexpr int PIECE = 16384;
+#pragma unroll
+          for (int off = 0; off < C::B_TAP_BYTES; off += PIECE) {
+            bulk_load_1d(smem_b + bs * C::B_TAP_BYTES + off, w_packed + (size_t)blk * C::B_TAP_BYTES + off, PIECE,
+                         &b_full[bs]);
+          }
+          if (++bs == CS_NB) { bs = 0; bphase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ============================================
+    constexpr uint32_t idesc = make_idesc_bf16(128, COUT);
+    constexpr uint32_t a_hi = desc_hi(C::GROUP_STRIDE, C::SWZ);
+    constexpr uint32_t b_hi = desc_hi(8 * C::ROWB, C::SWZ);
+    constexpr uint32_t c_hi = desc_hi(256, SW_NONE);
+    const uint32_t a_lo0 = desc_lo(smem_u32(smem_a), 0);
+    const uint32_t b_lo0 = desc_lo(smem_u32(smem_b), 0);
+    const uint32_t ones_lo = desc_lo(smem_u32(smem_ones), 128);
+    const uint32_t bias_lo = desc_lo(smem_u32(smem_biasop), 128);
+    int bs = 0;
+    uint32_t bphase = 0, pphase = 0;
+    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      const int n_tiles = (2 * pair + 1 < total_tiles) ? 2 : 1;
+      mbar_wait(&tempty_bar[0], pphase ^ 1, 27);
+      mbar_wait(&tempty_bar[1], pphase ^ 1, 27);
+      mbar_wait(a_full, pphase, 28);
+      tc_fence_after_sync();
+      if (elect_one()) {
+        for (int t = 0; t < n_tiles; ++t)
+          umma_bf16_ss_w(tmem_base + t * COUT, ones_lo, c_hi, bias_lo, c_hi, idesc, 0u);     // D = bias
+      }
+      __syncwarp();
+      for (int blk = 0; blk < NBLK; ++blk) {
+        // block order of the packed weights: (tap, chunk) with the chunk fastest
+        const int tap = blk / C::NCHUNK, kc = blk % C::NCHUNK;
+        const int r = tap / 3, s = tap % 3;
+        mbar_wait(&b_full[bs], bphase, 29);
+        tc_fence_after_sync();
+        if (elect_one()) {
+          const uint32_t b_lo = b_lo0 + bs * (C::B_TAP_BYTES >> 4);
+          for (int t = 0; t < n_tiles; ++t) {
+            const uint32_t a_lo = a_lo0 + ((t * C::STAGE_STRIDE + kc * C::CHUNK_STRIDE + (r * CV_HALO_X + s) * C::ROWB) >> 4);
+#pragma unroll
+            for (int kk = 0; kk < C::CK / 16; ++kk) {
+              umma_bf16_ss_w(tmem_base + t * COUT, a_lo + kk * 2, a_hi, b_lo + kk * 2, b_hi, idesc, 1u);
+            }
+          }
+          umma_commit(&b_empty[bs]);
+          if (blk == NBLK - 1) {
+            umma_commit(a_empty);
+            umma_commit(tfull_bar);
+          }
+        }
+        __syncwarp();
+        if (++bs == CS_NB) { bs = 0; bphase ^= 1; }
+      }
+      pphase ^= 1;
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue ==============================================
+    const int group = (warp - 4) >> 2;        // tile of the pair
+    const int e = (warp - 4) & 3;             // TMEM lanes 32e .. 32e+31
+    const int Ho = H >> 1, Wo = W >> 1;
+    const int ly = lane >> 3;
+    const int lx = lane & 7;
+    const bool odd_x = lane & 1;
+    const bool odd_y = (lane >> 3) & 1;
+    uint32_t pphase = 0;
+    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      const int tile = 2 * pair + group;
+      const bool have = tile < total_tiles;
+      const int n = tile / tiles_per_img, rem = tile % tiles_per_img;
+      const int ty = rem / tiles_x, tx = rem % tiles_x;
+      const int py = ((ty * CV_TILE_Y + 4 * e + ly) >> 1);
+      const int px = ((tx * CV_TILE_X + lx) >> 1);
+      const bool in_range = have && py < Ho && px < Wo;
+      __nv_bfloat16* orow = out + (((size_t)n * Ho + py) * Wo + px) * COUT;
+      mbar_wait(tfull_bar, pphase, 24);
+      pphase ^= 1;
+      tc_fence_after_sync();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(32 * e) << 16) + group * COUT;
+
+      auto finish_chunk = [&](const uint32_t (&v)[32], int cb) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) pk[q] = pack_bf16x2(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]));
+        uint32_t h8[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const uint32_t keep = odd_x ? pk[8 + q] : pk[q];
+          const uint32_t send = odd_x ? pk[q] : pk[8 + q];
+          h8[q] = max_bf16x2(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+        }
+        uint32_t q4[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t keep = odd_y ? h8[4 + q] : h8[q];
+          const uint32_t send = odd_y ? h8[q] : h8[4 + q];
+          q4[q] = max_bf16x2(max_bf16x2(keep, __shfl_xor_sync(0xffffffffu, send, 8)), 0u);
+        }
+        if (in_range) {
+          const int ch = cb + (odd_x ? 16 : 0) + (odd_y ? 8 : 0);
+          *reinterpret_cast<uint4*>(orow + ch) = make_uint4(q4[0], q4[1], q4[2], q4[3]);
+        }
+      };
+
+      if (have) {
+        uint32_t va[32], vb[32];
+        tmem_ld32(t_addr, va);
+#pragma unroll
+        for (int cb = 0; cb < COUT; cb += 64) {
+          tmem_ld_wait();
+          tmem_ld32(t_addr + cb + 32, vb);
+          finish_chunk(va, cb);
+          tmem_ld_wait();
+          if (cb + 64 < COUT) tmem_ld32(t_addr + cb + 64, va);
+          finish_chunk(vb, cb + 32);
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[group]);
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tmem_free(tmem_base, 512);
+}
+
 // ------------------------------- weight packing ----------------------------------------------
 // [cout][cin][3][3] fp32 -> for tap (r,s), chunk kc: [cout rows][CK channels] bf16, K-major, with the
 // 16-byte units of each row XOR-swizzled by the row index exactly as TMA / UMMA swizzle modes do
@@ -362,7 +575,7 @@ static int launch_conv3x3(const void* in, int batch, int h, int w, const void* w
                             C::ROWB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc != 0) return rc;
   const int tiles_y = (h + CV_TILE_Y - 1) / CV_TILE_Y;
-  const int tiles_x = w / CV_TILE_X;
+  const int tiles_x = (w + CV_TILE_X - 1) / CV_TILE_X;      // TMA zero-fills past the image: 'same' padding
   const int total = tiles_y * tiles_x * batch;
   const int smem = 1024 + C::B_BYTES + NSTAGE * C::STAGE_STRIDE + ONES_BYTES + C::BIAS_BYTES +
                    (2 * NSTAGE + 2 * CV_NACC + 2) * 8;
@@ -370,6 +583,32 @@ static int launch_conv3x3(const void* in, int batch, int h, int w, const void* w
   static int configured = 0;
   if (int rc2 = ensure_dynamic_smem(kern, smem, &configured)) return rc2;
   const int grid = total < sm_count() ? total : sm_count();
+  kern<<<grid, CV_THREADS, smem, st>>>(tmap, static_cast<const uint8_t*>(w_packed), bias,
+                                       static_cast<__nv_bfloat16*>(out), h, w, tiles_y, tiles_x, total);
+  return launch_status();
+}
+
+
+template <int CIN, int COUT>
+static int launch_conv3x3_stream(const void* in, int batch, int h, int w, const void* w_packed, const float* bias,
+                                 void* out, cudaStream_t st) {
+  using C = ConvCfg<CIN, COUT>;
+  if (int wrc = ensure_watchdog()) return wrc;
+  CUtensorMap tmap;
+  const uint64_t dims[4] = {(uint64_t)CIN, (uint64_t)w, (uint64_t)h, (uint64_t)batch};
+  const uint64_t strides[3] = {(uint64_t)CIN * 2, (uint64_t)w * CIN * 2, (uint64_t)h * w * CIN * 2};
+  const uint32_t box[4] = {(uint32_t)C::CK, CV_HALO_X, CV_HALO_Y, 1};
+  int rc = encode_tmap_bf16(&tmap, in, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc != 0) return rc;
+  const int tiles_y = (h + CV_TILE_Y - 1) / CV_TILE_Y;
+  const int tiles_x = (w + CV_TILE_X - 1) / CV_TILE_X;
+  const int total = tiles_y * tiles_x * batch;
+  const int pairs = (total + 1) / 2;
+  const int smem = 1024 + CS_NB * C::B_TAP_BYTES + 2 * C::STAGE_STRIDE + ONES_BYTES + C::BIAS_BYTES + (2 * CS_NB + 6) * 8;
+  auto kern = conv3x3_stream_kernel<CIN, COUT>;
+  static int configured = 0;
+  if (int rc2 = ensure_dynamic_smem(kern, smem, &configured)) return rc2;
+  const int grid = pairs < sm_count() ? pairs : sm_count();
   kern<<<grid, CV_THREADS, smem, st>>>(tmap, static_cast<const uint8_t*>(w_packed), bias,
                                        static_cast<__nv_bfloat16*>(out), h, w, tiles_y, tiles_x, total);
   return launch_status();
@@ -392,11 +631,12 @@ extern "C" int sia_pack_conv3x3(const float* w_oihw, int cin, int cout, void* pa
 extern "C" int sia_conv3x3_relu_pool2(const void* in_nhwc, int batch, int h, int w, int cin, int cout,
                                       const void* w_packed, const float* bias, void* out_nhwc, void* stream) {
   using namespace sia;
-  SIA_REQUIRE(in_nhwc && w_packed && bias && out_nhwc && batch >= 1 && h >= 2 && w >= 8);
+  SIA_REQUIRE(in_nhwc && w_packed && bias && out_nhwc && batch >= 1 && h >= 2 && w >= 2);
   SIA_REQUIRE(aligned(in_nhwc, 16) && aligned(w_packed, 16) && aligned(out_nhwc, 16));
-  if (h % 2 != 0 || w % CV_TILE_X != 0) return SIA_E_UNSUPPORTED;
+  if (h % 2 != 0 || w % 2 != 0) return SIA_E_UNSUPPORTED;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (cin == 32 && cout == 64) return launch_conv3x3<32, 64, 6>(in_nhwc, batch, h, w, w_packed, bias, out_nhwc, st);
   if (cin == 64 && cout == 128) return launch_conv3x3<64, 128, 3>(in_nhwc, batch, h, w, w_packed, bias, out_nhwc, st);
+  if (cin == 128 && cout == 256) return launch_conv3x3_stream<128, 256>(in_nhwc, batch, h, w, w_packed, bias, out_nhwc, st);
   return SIA_E_UNSUPPORTED;
 }

@@ -47,7 +47,12 @@ def test_conv7x7_block(batch, h, w):
 
 
 @pytest.mark.parametrize("cin,cout,batch,h,w", [(32, 64, 1, 16, 8), (32, 64, 2, 112, 112), (64, 128, 3, 56, 56),
-                                                (64, 128, 1, 30, 24), (32, 64, 1, 18, 40)])
+                                                (64, 128, 1, 30, 24), (32, 64, 1, 18, 40), (64, 128, 2, 28, 28),
+                                                (32, 64, 1, 10, 6),
+                                                # streamed-weight kernel (conv4 of SkinCancerModel): even / odd tile
+                                                # counts, partial tiles on both edges, more pairs than SMs
+                                                (128, 256, 1, 16, 8), (128, 256, 3, 28, 28), (128, 256, 1, 18, 12),
+                                                (128, 256, 40, 28, 28)])
 def test_conv3x3_block(cin, cout, batch, h, w):
     from skin_image_analysis_b200 import ops
     g = torch.Generator(device="cuda").manual_seed(cin + h)
@@ -105,7 +110,7 @@ def test_head_tail_matches_torch():
     assert torch.equal(counts, ops.confusion_counts(pred, label, groups, 6))
 
 
-@pytest.mark.parametrize("kind", [om.LIST_MODEL])
+@pytest.mark.parametrize("kind", [om.LIST_MODEL, om.FOUR_CONV_MODEL])
 def test_module_forward_matches_reference_fixture(golden_dir, kind):
     """Same weights + input as tests/golden/model_<kind>.npz (produced by the reference's own class)."""
     from skin_image_analysis_b200 import tone_bias_model as tm
@@ -194,3 +199,21 @@ def test_engine_end_to_end_counts_bit_exact_given_predictions():
         assert counts[0].tolist() == tab["skin_type"]
         assert counts[1, :2].tolist() == tab["sex"] and counts[2, :2].tolist() == tab["control"]
         assert int(counts[0].sum()) == batch
+
+
+def test_four_conv_model_batch_vs_oracle():
+    """SkinCancerModel (= jgi_hiba_2022_model, reference :155-299): 4 conv blocks, conv4 through the
+    streamed-weight kernel; same tolerance and margin rule as the list model."""
+    from skin_image_analysis_b200 import tone_bias_model as tm
+    state = om.synthetic_state_dict(om.FOUR_CONV_MODEL, seed=4)
+    x = helpers.synthetic_batch_f32(24, 224, seed=6)
+    ref = om.forward(om.FOUR_CONV_MODEL, {k: v.cuda() for k, v in state.items()}, x.cuda()).cpu()
+    state["fc6.bias"][1] -= float((ref[:, 1] - ref[:, 0]).median())
+    ref = om.forward(om.FOUR_CONV_MODEL, {k: v.cuda() for k, v in state.items()}, x.cuda()).cpu()
+    model = tm.create_model(helpers.CLASS_NAMES)
+    assert isinstance(model, tm.SkinCancerModel)
+    model.load_state_dict(state)
+    got = model.cuda().eval()(x.cuda()).cpu()
+    assert (got - ref).abs().max().item() <= LOGP_TOL
+    safe = (ref[:, 1] - ref[:, 0]).abs() > 2 * LOGP_TOL
+    assert torch.equal(got.argmax(1)[safe], ref.argmax(1)[safe])
