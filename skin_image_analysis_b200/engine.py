@@ -50,6 +50,9 @@ class EvalEngine:
         self.n_slots = n_slots
         with torch.cuda.device(self.device):
             self.plan = plan_from_state_dict(state_dict, self.device)
+            if self.plan.image_size != out_size:
+                raise SiaError(f"state_dict is for {self.plan.image_size}x{self.plan.image_size} inputs, "
+                               f"out_size is {out_size}")
             d = self.device
             self.u8 = [torch.empty((batch, src_hw[0], src_hw[1], 3), dtype=torch.uint8, device=d)
                        for _ in range(n_slots)]

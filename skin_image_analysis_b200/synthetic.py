@@ -32,3 +32,33 @@ def device_u8_batches(n_batches: int, batch: int, h: int, w: int, seed: int, dev
     g = torch.Generator(device=device).manual_seed(seed)
     return [torch.randint(0, 256, (batch, h, w, 3), dtype=torch.uint8, device=device, generator=g)
             for _ in range(n_batches)]
+
+
+ARCHS = {   # reference state_dict prefixes (tone_bias_model.py:56-152 and :155-299) and layer widths
+    "SkinCancerListModel": dict(convs=[("layers.0", 32, 3, 7), ("layers.3", 64, 32, 3), ("layers.6", 128, 64, 3)],
+                                linears=[("layers.10", 512), ("layers.13", 256), ("layers.16", 2)]),
+    "SkinCancerModel": dict(convs=[("conv1", 32, 3, 7), ("conv2", 64, 32, 3), ("conv3", 128, 64, 3),
+                                   ("conv4", 256, 128, 3)],
+                            linears=[("fc4", 512), ("fc5", 256), ("fc6", 2)]),
+}
+
+
+def random_state_dict(kind: str, image_size: int = 224, seed: int = 0) -> dict:
+    """Random-init weights of a reference architecture with the reference's init (xavier_normal_ weights,
+    tone_bias_model.py:136-137; torch-default uniform biases) for any input size: the reference hard-codes 224
+    (:69-70), for other sizes only the first Linear's in_features changes."""
+    import math
+    g = torch.Generator().manual_seed(seed)
+    out, side, ch = {}, image_size, 3
+    for prefix, cout, cin, k in ARCHS[kind]["convs"]:
+        fan_in, fan_out = cin * k * k, cout * k * k
+        out[prefix + ".weight"] = torch.randn((cout, cin, k, k), generator=g) * math.sqrt(2.0 / (fan_in + fan_out))
+        out[prefix + ".bias"] = (torch.rand((cout,), generator=g) * 2 - 1) / math.sqrt(fan_in)
+        side //= 2
+        ch = cout
+    feat = ch * side * side
+    for prefix, width in ARCHS[kind]["linears"]:
+        out[prefix + ".weight"] = torch.randn((width, feat), generator=g) * math.sqrt(2.0 / (feat + width))
+        out[prefix + ".bias"] = (torch.rand((width,), generator=g) * 2 - 1) / math.sqrt(feat)
+        feat = width
+    return out

@@ -27,11 +27,17 @@ class CnnPlan:
     conv_params: [(weight[O,I,k,k], bias[O])...]; fc_params: [(weight, bias)] * 3 (reference layout).
     """
 
-    def __init__(self, conv_params, fc_params, image_size: int = 224):
+    def __init__(self, conv_params, fc_params, image_size: int | None = None):
         dev = conv_params[0][0].device
         if dev.type != "cuda":
             raise SiaError("CnnPlan needs CUDA parameters (there is no CPU fallback)")
         self.device = dev
+        if image_size is None:
+            # the reference hard-codes 224 (tone_bias_model.py:69-70); other sizes follow from the first Linear:
+            # in_features = c_last * (image_size / 2^n_conv)^2
+            c_last = conv_params[-1][0].shape[0]
+            side = int(round((fc_params[0][0].shape[1] / c_last) ** 0.5))
+            image_size = side << len(conv_params)
         self.image_size = image_size
         self.convs = []
         side = image_size
@@ -124,10 +130,11 @@ class _B200Eval(nn.Module):
                            "(the reference does, tone_bias_test.py:175)")
         if not isinstance(x, torch.Tensor) or not x.is_cuda:
             raise SiaError("model input must be a CUDA tensor: the sm_100a path has no CPU fallback")
-        if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != 224 or x.shape[3] != 224:
-            raise ValueError("expected input [B,3,224,224] (the reference hard-codes 224, tone_bias_model.py:69-70)")
         with torch.no_grad():
             plan = self._plan()
+            if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != plan.image_size or x.shape[3] != plan.image_size:
+                raise ValueError(f"expected input [B,3,{plan.image_size},{plan.image_size}] (the reference hard-codes "
+                                 "224, tone_bias_model.py:69-70; the size follows from the first Linear)")
             x4 = ops.nchw_f32_to_nhwc4(x.float().contiguous())
             logp, _pred = plan.forward_nhwc4(x4)
             return logp.clone()

@@ -217,3 +217,23 @@ def test_four_conv_model_batch_vs_oracle():
     assert (got - ref).abs().max().item() <= LOGP_TOL
     safe = (ref[:, 1] - ref[:, 0]).abs() > 2 * LOGP_TOL
     assert torch.equal(got.argmax(1)[safe], ref.argmax(1)[safe])
+
+
+def test_engine_high_resolution_512():
+    """BASELINE configs[4] shape: 512x512 output (H axis up-sampled, W axis 1.17x down), first Linear
+    524288 -> 512; engine log-probs vs the fp32 oracle on the oracle's own resize of the same images."""
+    from skin_image_analysis_b200.engine import EvalEngine
+    from skin_image_analysis_b200.synthetic import random_state_dict
+    from oracle import resize as R
+    batch = 3
+    state = random_state_dict(om.LIST_MODEL, 512, seed=2)
+    imgs = np.stack([helpers.synthetic_u8_image(450, 600, 500 + i, "smooth") for i in range(batch)])
+    x_ref = torch.from_numpy(np.stack([R.transform_u8(im, (512, 512)) for im in imgs]))
+    ref = om.forward(om.LIST_MODEL, {k: v.cuda() for k, v in state.items()}, x_ref.cuda()).cpu()
+    eng = EvalEngine(state, batch, (450, 600), 512, use_graph=False)
+    label = torch.zeros(batch, dtype=torch.uint8, device="cuda")
+    groups = torch.zeros((3, batch), dtype=torch.uint8, device="cuda")
+    eng.step(torch.from_numpy(imgs).cuda(), label, groups)
+    eng.synchronize()
+    assert (eng.logp.cpu() - ref).abs().max().item() <= LOGP_TOL
+    assert int(eng.read_counts()[0].sum()) == batch
