@@ -15,6 +15,8 @@ What is pinned
   * transform.npz       : reference ``Rescale`` + ``ToTensor`` (tone_bias_dataset.py:397-473) on seeded
                           u8 images, with ``skimage.transform.resize`` bound to the scipy restatement
                           (scikit-image itself is not installable here -- see oracle/__init__.py).
+  * analysis_experiments.json : synthetic per-epoch result files + the reference's ``tone_bias_analysis``
+                          outputs for them (read_experiment(s), transpose_dict, compute_ci; :12-39, :281-510).
   * notebook_di.json    : hand-transcribed from the reference's saved notebook outputs
                           (notebooks/jgi_hiba_2022_torch.ipynb raw 3591-3617, 3643-3669, 3318-3322,
                           3433-3434, 3178); written by this script so the provenance is in one place.
@@ -154,9 +156,63 @@ def gen_notebook():
         json.dump(nb, f, indent=1, sort_keys=True)
 
 
+def experiment_lines():
+    """The JSON-lines result files of three synthetic experiment folders (what tone_bias_train.py:410-424 appends
+    after every epoch), built from the reference's own analyse_predictions on seeded instances."""
+    ref = ref_import.load()
+    folders = {}
+    for f, (name, n_files, epochs) in enumerate([("balanced_2024-09-21_00-38-39", 2, [3, 2]),
+                                                 ("balanced_2024-09-22_10-18-46", 1, [4]),
+                                                 ("imbalanced_2024-09-23_09-00-00", 1, [2])]):
+        files = {}
+        for k in range(n_files):
+            lines = []
+            for e in range(1, epochs[k] + 1):
+                inst = helpers.synthetic_instances(300 + 20 * e, 1000 + 100 * f + 10 * k + e, with_oddities=(e % 2 == 0))
+                with contextlib.redirect_stdout(io.StringIO()):
+                    res = ref.test.analyse_predictions(inst)
+                res["avg_batch_loss"] = 0.7 / (e + k + f + 1)
+                res["train_accuracy"] = 0.5 + 0.04 * (e + k) + 0.01 * f
+                res["epoch"] = e
+                lines.append(json.dumps(_jsonable(res)))
+            files[f"2024-09-2{1 + f}_0{k}-00-00.json"] = lines
+        folders[name] = files
+    return folders
+
+
+def gen_experiments(ref):
+    """analysis_experiments.json: inputs (the result files) + what the reference's tone_bias_analysis returns
+    for them (read_experiment, read_experiments, transpose_dict, get_measure, compute_ci; :12-39, :281-510)."""
+    import tempfile
+    ana = ref.analysis
+    folders = experiment_lines()
+    out = {"folders": folders, "read_experiment": {}, "read_experiments": {}, "transpose": {}, "compute_ci": []}
+    with tempfile.TemporaryDirectory() as tmp:
+        for name, files in folders.items():
+            os.makedirs(os.path.join(tmp, name))
+            for fname, lines in files.items():
+                with open(os.path.join(tmp, name, fname), "w") as f:
+                    f.write("\n".join(lines) + "\n")
+        with contextlib.redirect_stdout(io.StringIO()):
+            for name in folders:
+                out["read_experiment"][name] = _jsonable(ana.read_experiment(os.path.join(tmp, name)))
+            for prefix in ("balanced", "imbalanced"):
+                avg = ana.read_experiments(tmp, prefix, 2)
+                out["read_experiments"][prefix] = _jsonable(avg)
+                out["transpose"][prefix] = _jsonable(ana.transpose_dict(avg))
+    rng = np.random.default_rng(3)
+    for n, level in [(2, 0.90), (5, 0.95), (30, 0.90), (31, 0.90), (200, 0.99)]:
+        data = rng.normal(0.6, 0.1, n).tolist()
+        lo, hi = ana.compute_ci(data, level)
+        out["compute_ci"].append({"data": data, "level": level, "low": float(lo), "high": float(hi)})
+    with open(os.path.join(HERE, "analysis_experiments.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+
+
 def main():
     ref = ref_import.load()
     gen_notebook()
+    gen_experiments(ref)
     gen_analysis(ref)
     gen_transform(ref)
     gen_model(ref)
