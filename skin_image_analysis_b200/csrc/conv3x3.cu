@@ -21,6 +21,8 @@
 //   The un-pooled activation never leaves the SM.
 //
 // Tensor-core bound; algorithmic FLOPs = 2 * H*W * 9*cin * cout per image.
+#include <stdlib.h>
+
 #include "sia_host.cuh"
 #include "sia_ptx.cuh"
 
@@ -539,6 +541,230 @@ conv3x3_stream_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t
   if (warp == 2) tmem_free(tmem_base, 512);
 }
 
+// ------------------------------- pixel-pair variant (cin = 32) --------------------------------
+// With cout = 64 the plain kernel issues N = 64 UMMAs, and a kind::f16 UMMA costs 64 clocks for any N <= 128
+// (measured, tests/test_umma_probe.py / tools/probe_i8_timing.py): half of the tensor pipe idles.  Here one GEMM
+// row computes TWO horizontally adjacent output pixels (x, x+1), as conv1.cu does for 2 x 2:
+//     N = 2 * 64 (dx, co),   K = 3 rows * 4 pixels * 32 ch = 384,   B[(dx, co), (r, xw, c)] = W[co, c, r, xw - dx]
+// 75 % of the issued MACs are useful and every UMMA runs at N = 128: 25 UMMAs per 256 output pixels instead of
+// 2 * 19.  Two 32-channel pixels are exactly one 128-byte shared-memory row, so the input is fetched as pixel
+// PAIRS (TMA box [64 elem, 10 pairs, 18 rows], 128B swizzle) and the 4-pixel window of a row pair is the 256
+// contiguous bytes starting 64 bytes into the pair to its left -- again only descriptor start offsets, no im2col.
+// The 2 x 2 max-pool is a max over the two column halves of one accumulator row (x) and one shuffle (y).
+constexpr int CP_TILE_Y = 16, CP_TILE_XP = 8;                 // 16 rows x 8 pixel pairs = 256 output pixels
+constexpr int CP_HALO_Y = CP_TILE_Y + 2, CP_HALO_XP = CP_TILE_XP + 2;
+constexpr int CP_ROWB = 128;                                   // one pixel pair
+constexpr int CP_STAGE_BYTES = CP_HALO_Y * CP_HALO_XP * CP_ROWB;           // 23040
+constexpr int CP_STAGE_STRIDE = (CP_STAGE_BYTES + 1023) / 1024 * 1024;
+constexpr int CP_N = 128, CP_K = 384;
+constexpr int CP_B_CHUNK = CP_N * 128;                          // 64 k-elements of all 128 rows
+constexpr int CP_B_BYTES = (CP_K / 64) * CP_B_CHUNK;            // 98304
+constexpr int CP_NSTAGE = 4;
+constexpr int CP_BIAS_BYTES = CP_N * 32;
+
+__global__ void __launch_bounds__(CV_THREADS, 1)
+conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restrict__ w_packed,
+                    const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int H, int W, int tiles_y,
+                    int tiles_x, int total_tiles) {
+  constexpr int COUT = 64;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* smem_b = smem;                               // CP_B_BYTES
+  uint8_t* smem_a = smem + CP_B_BYTES;                  // CP_NSTAGE * CP_STAGE_STRIDE
+  uint8_t* smem_ones = smem_a + CP_NSTAGE * CP_STAGE_STRIDE;
+  uint8_t* smem_biasop = smem_ones + ONES_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_biasop + CP_BIAS_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + CP_NSTAGE;
+  uint64_t* tfull_bar = bars + 2 * CP_NSTAGE;
+  uint64_t* tempty_bar = bars + 2 * CP_NSTAGE + CV_NACC;
+  uint64_t* wload_bar = bars + 2 * CP_NSTAGE + 2 * CV_NACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * CP_NSTAGE + 2 * CV_NACC + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < CP_NSTAGE; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < CV_NACC; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    mbar_init(wload_bar, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmap_in);
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, CV_NACC * CP_N);
+  fill_ones_operand(smem_ones, threadIdx.x, blockDim.x);
+  fill_bias_operand(smem_biasop, bias, CP_N, COUT, threadIdx.x, blockDim.x);    // row (dx, co) -> bias[co]
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = bcast0(*tmem_slot);
+
+  if (warp == 0) {
+    // ================================ TMA producer ==========================================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(wload_bar, CP_B_BYTES);
+      for (int off = 0; off < CP_B_BYTES; off += 16384) bulk_load_1d(smem_b + off, w_packed + off, 16384, wload_bar);
+      int stage = 0;
+      uint32_t phase = 0;
+      TileWalker t(blockIdx.x, gridDim.x, tiles_x, tiles_y);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, t.next()) {
+        mbar_wait(&empty_bar[stage], phase ^ 1, 50);
+        mbar_arrive_expect_tx(&full_bar[stage], CP_STAGE_BYTES);
+        // coordinates: (element in the pair, pixel pair, row, image); the halo starts one pair / one row early
+        tma_load_4d(smem_a + stage * CP_STAGE_STRIDE, &tmap_in, &full_bar[stage], 0, t.tx * CP_TILE_XP - 1,
+                    t.ty * CP_TILE_Y - 1, t.n);
+        if (++stage == CP_NSTAGE) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ============================================
+    constexpr uint32_t idesc = make_idesc_bf16(128, CP_N);
+    constexpr uint32_t a_hi = desc_hi(CP_HALO_XP * CP_ROWB, SW_128B);   // 8-row groups = tile rows, one halo row apart
+    constexpr uint32_t b_hi = desc_hi(8 * 128, SW_128B);
+    constexpr uint32_t c_hi = desc_hi(256, SW_NONE);
+    const uint32_t a_lo0 = desc_lo(smem_u32(smem_a), 0);
+    const uint32_t b_lo0 = desc_lo(smem_u32(smem_b), 0);
+    const uint32_t ones_lo = desc_lo(smem_u32(smem_ones), 128);
+    const uint32_t bias_lo = desc_lo(smem_u32(smem_biasop), 128);
+    mbar_wait(wload_bar, 0, 51);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 52);
+      mbar_wait(&full_bar[stage], phase, 53);
+      tc_fence_after_sync();
+      if (elect_one()) {
+        const uint32_t d_tmem = tmem_base + acc * CP_N;
+        const uint32_t a_stage = a_lo0 + stage * (CP_STAGE_STRIDE >> 4);
+        umma_bf16_ss_w(d_tmem, ones_lo, c_hi, bias_lo, c_hi, idesc, 0u);     // D = bias
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            // window of output pair (row y, pair xp): halo row y + r, starting 64 bytes into halo pair xp
+            const uint32_t a_lo = a_stage + ((r * CP_HALO_XP * CP_ROWB + 64 + kk * 32) >> 4);
+            const uint32_t b_lo = b_lo0 + (((r * 2 + kk / 4) * CP_B_CHUNK + (kk % 4) * 32) >> 4);
+            umma_bf16_ss_w(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, 1u);
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+        umma_commit(&tfull_bar[acc]);
+      }
+      __syncwarp();
+      if (++stage == CP_NSTAGE) { stage = 0; phase ^= 1; }
+      if (++acc == CV_NACC) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue ==============================================
+    const int group = (warp - 4) >> 2;
+    const int e = (warp - 4) & 3;             // TMEM lanes 32e .. 32e+31 = tile rows 4e .. 4e+3
+    const int Ho = H >> 1, Wo = W >> 1;
+    const int ly = lane >> 3;
+    const int xp = lane & 7;                  // pixel pair = pooled output column inside the tile
+    const bool odd_y = (lane >> 3) & 1;
+    TileWalker t(blockIdx.x + group * gridDim.x, 2 * gridDim.x, tiles_x, tiles_y);
+    int j = group;
+    for (int tile = blockIdx.x + group * gridDim.x; tile < total_tiles; tile += 2 * gridDim.x, t.next(), j += 2) {
+      const int acc = j % CV_NACC;
+      const uint32_t acc_phase = (j / CV_NACC) & 1;
+      const int py = (t.ty * CP_TILE_Y + 4 * e + ly) >> 1;
+      const int px = t.tx * CP_TILE_XP + xp;
+      const bool in_range = py < Ho && px < Wo;
+      __nv_bfloat16* opix = out + (((size_t)t.n * Ho + py) * Wo + px) * COUT;
+      mbar_wait(&tfull_bar[acc], acc_phase, 54);
+      tc_fence_after_sync();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(32 * e) << 16) + acc * CP_N;
+
+      // 32 channels: max over dx (columns cb and 64 + cb), bf16, y partner (lane ^ 8) reduce-scatter, ReLU
+      auto finish = [&](const uint32_t (&v0)[32], const uint32_t (&v1)[32], int cb) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          pk[q] = pack_bf16x2(fmaxf(__uint_as_float(v0[2 * q]), __uint_as_float(v1[2 * q])),
+                              fmaxf(__uint_as_float(v0[2 * q + 1]), __uint_as_float(v1[2 * q + 1])));
+        }
+        uint32_t h8[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const uint32_t keep = odd_y ? pk[8 + q] : pk[q];
+          const uint32_t send = odd_y ? pk[q] : pk[8 + q];
+          h8[q] = max_bf16x2(max_bf16x2(keep, __shfl_xor_sync(0xffffffffu, send, 8)), 0u);
+        }
+        if (in_range) {
+          uint4* dst = reinterpret_cast<uint4*>(opix + cb + (odd_y ? 16 : 0));
+          dst[0] = make_uint4(h8[0], h8[1], h8[2], h8[3]);
+          dst[1] = make_uint4(h8[4], h8[5], h8[6], h8[7]);
+        }
+      };
+
+      uint32_t a0[32], a1[32], b0[32], b1[32];
+      tmem_ld32(t_addr, a0);
+      tmem_ld32(t_addr + 64, a1);
+      tmem_ld_wait();
+      tmem_ld32(t_addr + 32, b0);
+      tmem_ld32(t_addr + 96, b1);
+      finish(a0, a1, 0);
+      tmem_ld_wait();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);     // the whole accumulator is in registers
+      finish(b0, b1, 32);
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tmem_free(tmem_base, CV_NACC * CP_N);
+}
+
+// [64][32][3][3] fp32 -> B[n = dx*64 + co][k = r*128 + xw*32 + c] = W[co][c][r][xw - dx] (0 outside 0..2), bf16, as six
+// 128-row x 128-byte blocks (64 k each) with the 16-byte units of every row XOR-swizzled by the row index.
+__global__ void pack_conv3x3_pair_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < CP_N * CP_K; i += gridDim.x * blockDim.x) {
+    const int n = i / CP_K, k = i % CP_K;
+    const int dx = n / 64, co = n % 64;
+    const int r = k / 128, xw = (k % 128) / 32, c = k % 32;
+    const int s = xw - dx;
+    float v = 0.f;
+    if (s >= 0 && s < 3) v = w[((co * 32 + c) * 3 + r) * 3 + s];
+    const int chunk = k / 64, kq = k % 64;
+    const int unit = (kq / 8) ^ (n & 7);
+    dst[(size_t)chunk * (CP_B_CHUNK / 2) + n * 64 + unit * 8 + (kq & 7)] = __float2bfloat16_rn(v);
+  }
+}
+
+static int launch_conv3x3_pair(const void* in, int batch, int h, int w, const void* w_packed, const float* bias,
+                               void* out, cudaStream_t st) {
+  if (int wrc = ensure_watchdog()) return wrc;
+  CUtensorMap tmap;
+  // the NHWC input seen as pixel pairs: [64 elements, w/2 pairs, h, batch]
+  const uint64_t dims[4] = {64, (uint64_t)w / 2, (uint64_t)h, (uint64_t)batch};
+  const uint64_t strides[3] = {128, (uint64_t)w * 64, (uint64_t)h * w * 64};
+  const uint32_t box[4] = {64, CP_HALO_XP, CP_HALO_Y, 1};
+  int rc = encode_tmap_bf16(&tmap, in, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc != 0) return rc;
+  const int tiles_y = (h + CP_TILE_Y - 1) / CP_TILE_Y;
+  const int tiles_x = (w / 2 + CP_TILE_XP - 1) / CP_TILE_XP;
+  const int total = tiles_y * tiles_x * batch;
+  const int smem = 1024 + CP_B_BYTES + CP_NSTAGE * CP_STAGE_STRIDE + ONES_BYTES + CP_BIAS_BYTES +
+                   (2 * CP_NSTAGE + 2 * CV_NACC + 2) * 8;
+  static int configured = 0;
+  if (int rc2 = ensure_dynamic_smem(conv3x3_pair_kernel, smem, &configured)) return rc2;
+  const int grid = total < sm_count() ? total : sm_count();
+  conv3x3_pair_kernel<<<grid, CV_THREADS, smem, st>>>(tmap, static_cast<const uint8_t*>(w_packed), bias,
+                                                      static_cast<__nv_bfloat16*>(out), h, w, tiles_y, tiles_x, total);
+  return launch_status();
+}
+
 // ------------------------------- weight packing ----------------------------------------------
 // [cout][cin][3][3] fp32 -> for tap (r,s), chunk kc: [cout rows][CK channels] bf16, K-major, with the
 // 16-byte units of each row XOR-swizzled by the row index exactly as TMA / UMMA swizzle modes do
@@ -616,12 +842,30 @@ static int launch_conv3x3_stream(const void* in, int batch, int h, int w, const 
 
 }  // namespace sia
 
-extern "C" size_t sia_pack_conv3x3_bytes(int cin, int cout) { return (size_t)9 * cin * cout * 2; }
+// (32, 64) uses the pixel-pair operand (conv3x3_pair_kernel); SIA_CONV2_PLAIN=1 in the environment keeps the plain
+// 9-tap operand and kernel for A/B comparisons.
+static bool use_pair_variant(int cin, int cout) {
+  static int plain = -1;
+  if (plain < 0) {
+    const char* e = getenv("SIA_CONV2_PLAIN");
+    plain = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return cin == 32 && cout == 64 && plain == 0;
+}
+
+extern "C" size_t sia_pack_conv3x3_bytes(int cin, int cout) {
+  return use_pair_variant(cin, cout) ? (size_t)sia::CP_B_BYTES : (size_t)9 * cin * cout * 2;
+}
 
 extern "C" int sia_pack_conv3x3(const float* w_oihw, int cin, int cout, void* packed, void* stream) {
   using namespace sia;
   SIA_REQUIRE(w_oihw && packed && cin >= 32 && cout >= 8);
   if (!((cin == 32) || (cin % 64 == 0))) return SIA_E_UNSUPPORTED;
+  if (use_pair_variant(cin, cout)) {
+    pack_conv3x3_pair_kernel<<<(CP_N * CP_K + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        w_oihw, static_cast<__nv_bfloat16*>(packed));
+    return launch_status();
+  }
   const int total = 9 * cin * cout;
   pack_conv3x3_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       w_oihw, cin, cout, static_cast<__nv_bfloat16*>(packed));
@@ -635,6 +879,7 @@ extern "C" int sia_conv3x3_relu_pool2(const void* in_nhwc, int batch, int h, int
   SIA_REQUIRE(aligned(in_nhwc, 16) && aligned(w_packed, 16) && aligned(out_nhwc, 16));
   if (h % 2 != 0 || w % 2 != 0) return SIA_E_UNSUPPORTED;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (use_pair_variant(cin, cout)) return launch_conv3x3_pair(in_nhwc, batch, h, w, w_packed, bias, out_nhwc, st);
   if (cin == 32 && cout == 64) return launch_conv3x3<32, 64, 6>(in_nhwc, batch, h, w, w_packed, bias, out_nhwc, st);
   if (cin == 64 && cout == 128) return launch_conv3x3<64, 128, 3>(in_nhwc, batch, h, w, w_packed, bias, out_nhwc, st);
   if (cin == 128 && cout == 256) return launch_conv3x3_stream<128, 256>(in_nhwc, batch, h, w, w_packed, bias, out_nhwc, st);
