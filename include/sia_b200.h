@@ -90,13 +90,16 @@ int sia_preprocess_u8hwc(const uint8_t* src, int batch, int src_h, int src_w, co
  *   items     [n_items][16]      the horizontal schedule, 64 bytes per item: int32 {accumulator column,
  *                                output column to emit or -1, column block, source pixels consumed}, then
  *                                3 pixels x 4 slots of fp32 weights
+ *                                (word 3 of the first item of every group of 4: >= 0 = the group's four pixels
+ *                                are the padded columns word3 .. word3+3, written as one 32-byte sector)
  *   n_blocks, last_block_cols    column blocks of 240 bytes per image row; MMA N of the last one
+ *   pads_in_schedule             != 0: those groups also cover the zero pad columns of every row
  * Needs (3 * src_w) % 8 == 0, an even src_h and src 16-byte aligned (the images are fetched by TMA as double
  * rows); SIA_E_UNSUPPORTED otherwise. */
 int sia_preprocess_tc_u8hwc(const uint8_t* src, int batch, int src_h, int src_w, const void* a_packed,
                             const float* lane_scale, const int32_t* tile_row0, int n_tiles, int tile_rows,
-                            const void* items, int n_items, int n_blocks, int last_block_cols, int out_h, int out_w,
-                            const float* out_scale_host, const float* out_bias_host, void* dst_nhwc4, void* stream);
+                            const void* items, int n_items, int n_blocks, int last_block_cols, int pads_in_schedule,
+                            int out_h, int out_w, const float* out_scale_host, const float* out_bias_host, void* dst_nhwc4, void* stream);
 
 /* Model boundary: NCHW fp32 [B,3,h,w] (the tensor the reference DataLoader feeds to model(images),
  * src/tone_bias_test.py:190-196) -> padded NHWC4 bf16 [B,h,w+8,4] (SIA_LAYOUT_NHWC4_BF16). */

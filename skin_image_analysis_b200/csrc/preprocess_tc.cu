@@ -71,6 +71,7 @@ struct TcParams {
   int n_tiles, tile_rows, n_blocks, last_block_cols, n_items;
   int odd_shift;                // row_bytes % 16: odd rows are fetched this many bytes early
   int n_raw;                    // raw stages in use (<= TC_NRAW)
+  int pads_in_schedule;         // the vector-store groups of the schedule also write the zero pad columns
   float scale[3], bias[3];
 };
 
@@ -152,6 +153,9 @@ preprocess_tc_kernel(const __grid_constant__ CUtensorMap tmap_src, const __grid_
   tc_fence_after_sync();
   const uint32_t tmem_base = bcast0(*tmem_slot);
 
+#ifdef SIA_TC_EPI_ONLY
+  if (warp >= 4 && warp < 12) {} else { goto tc_done; }
+#endif
   if (warp == TC_WARP_TMA) {
     // ================================ TMA producer ==========================================
     if (lane == 0) {
@@ -213,6 +217,16 @@ preprocess_tc_kernel(const __grid_constant__ CUtensorMap tmap_src, const __grid_
                        : "r"(src + (uint32_t)(r >> 1) * TC_RAW_ROWB));
         }
       }
+#ifdef SIA_TC_EARLY_RELEASE
+      {   // consume every loaded register before the raw stage is handed back (forces the loads to have completed)
+        uint32_t x = 0;
+#pragma unroll
+        for (int it = 0; it < TC_KSTAGE / 4; ++it) x |= v[it].x | v[it].y;
+        asm volatile("" ::"r"(x) : "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&raw_empty[rs]);
+      }
+#endif
       mbar_wait(&empty_bar[stage], phase ^ 1, 40);
       {
         const uint32_t base = smem_u32(smem_b) + stage * TC_STAGE_BYTES + st_lane;
@@ -240,7 +254,9 @@ preprocess_tc_kernel(const __grid_constant__ CUtensorMap tmap_src, const __grid_
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&full_bar[stage]);
+#ifndef SIA_TC_EARLY_RELEASE
         mbar_arrive(&raw_empty[rs]);
+#endif
         if (cw == 0 && (it0 & (TC_NQ - 1)) == TC_NQ - 1) trace(it0 / TC_NQ, 3);
       }
       stage += TC_CONV_GROUPS;
@@ -312,7 +328,7 @@ preprocess_tc_kernel(const __grid_constant__ CUtensorMap tmap_src, const __grid_
     for (int k = g; k < n_img; k += 2) {
       const int img = img0 + k * img_step;
       uint2* orow = p.dst + ((size_t)img * p.out_h + (row_ok ? i : 0)) * pitch;
-      if (row_ok) {                                // zero pad columns of the NHWC4 row
+      if (row_ok && !p.pads_in_schedule) {         // zero pad columns of the NHWC4 row
         orow[0] = make_uint2(0u, 0u);
 #pragma unroll
         for (int c = 1; c < SIA_NHWC4_PAD; ++c) orow[p.out_w + c] = make_uint2(0u, 0u);
@@ -357,20 +373,20 @@ preprocess_tc_kernel(const __grid_constant__ CUtensorMap tmap_src, const __grid_
         }
       };
       auto compute_group = [&](int n0, const uint32_t (&v)[4][9]) {
-        uint4 it[4];                                 // info + weights of the item being computed
         float4 w_next[3];
         int emit_next;
-        {
-          const uint4 i0 = items_s[4 * n0];
-          emit_next = (int)i0.y;
+        const uint4 i0 = items_s[4 * n0];
+        const int vec_col = (int)i0.w;               // >= 0: the group's 4 pixels are padded columns vec_col .. +3
+        emit_next = (int)i0.y;
 #pragma unroll
-          for (int q = 0; q < 3; ++q) w_next[q] = *reinterpret_cast<const float4*>(&items_s[4 * n0 + 1 + q]);
-        }
-        (void)it;
+        for (int q = 0; q < 3; ++q) w_next[q] = *reinterpret_cast<const float4*>(&items_s[4 * n0 + 1 + q]);
+        uint32_t st[4][2];                           // the group's pixels: one full 32-byte sector per lane
+        int js[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const float4 w0 = w_next[0], w1 = w_next[1], w2 = w_next[2];
           const int j = emit_next;
+          js[u] = j;
           if (u < 3) {                               // next item's table entry in flight during this item's FFMAs
             emit_next = (int)items_s[4 * (n0 + u + 1)].y;
 #pragma unroll
@@ -385,21 +401,29 @@ preprocess_tc_kernel(const __grid_constant__ CUtensorMap tmap_src, const __grid_
             acc[2][c] = fmaf(w2.z, f2, fmaf(w1.z, f1, fmaf(w0.z, f0, acc[2][c])));
             acc[3][c] = fmaf(w2.w, f2, fmaf(w1.w, f1, fmaf(w0.w, f0, acc[3][c])));
           }
-          // slot u is complete: one NHWC4 pixel (predicated store), then the slot restarts
+          // slot u is complete: one NHWC4 pixel (zero for an item that emits nothing: a pad column), slot restarts
           const uint32_t ox = pack_bf16x2(fmaf(acc[u][0], sc0, bi0), fmaf(acc[u][1], sc1, bi1));
           const uint32_t oy = pack_bf16x2(fmaf(acc[u][2], sc2, bi2), 0.f);
-#ifdef SIA_TC_NOSTORE
-          const uint32_t ok = (j == 123456 && row_ok) ? 1u : 0u;
-#else
-          const uint32_t ok = (j >= 0 && row_ok) ? 1u : 0u;
-#endif
-          asm volatile(
-              "{\n\t.reg .pred p;\n\t"
-              "setp.ne.b32 p, %3, 0;\n\t"
-              "@p st.global.v2.b32 [%0], {%1, %2};\n\t}"
-              ::"l"(orow + (j + 1)), "r"(ox), "r"(oy), "r"(ok)
-              : "memory");
+          st[u][0] = j >= 0 ? ox : 0u;
+          st[u][1] = j >= 0 ? oy : 0u;
           acc[u][0] = acc[u][1] = acc[u][2] = 0.f;
+        }
+#ifdef SIA_TC_NOSTORE
+        const bool store_ok = row_ok && vec_col == 123456;
+#else
+        const bool store_ok = row_ok;
+#endif
+        if (vec_col >= 0) {                          // uniform: 2 x 16-byte stores, 32-byte aligned
+          if (store_ok) {
+            uint4* dst = reinterpret_cast<uint4*>(orow + vec_col);
+            dst[0] = make_uint4(st[0][0], st[0][1], st[1][0], st[1][1]);
+            dst[1] = make_uint4(st[2][0], st[2][1], st[3][0], st[3][1]);
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (store_ok && js[u] >= 0) orow[js[u] + 1] = make_uint2(st[u][0], st[u][1]);
+          }
         }
       };
 
@@ -427,6 +451,9 @@ preprocess_tc_kernel(const __grid_constant__ CUtensorMap tmap_src, const __grid_
     }
   }
 
+#ifdef SIA_TC_EPI_ONLY
+tc_done:
+#endif
   tc_fence_before_sync();
   __syncthreads();
   if (warp == TC_WARP_MMA) tmem_free(tmem_base, 512);
@@ -436,8 +463,8 @@ preprocess_tc_kernel(const __grid_constant__ CUtensorMap tmap_src, const __grid_
 
 extern "C" int sia_preprocess_tc_u8hwc(const uint8_t* src, int batch, int src_h, int src_w, const void* a_packed,
                                        const float* lane_scale, const int32_t* tile_row0, int n_tiles, int tile_rows,
-                                       const void* items, int n_items, int n_blocks, int last_block_cols, int out_h,
-                                       int out_w, const float* out_scale_host, const float* out_bias_host,
+                                       const void* items, int n_items, int n_blocks, int last_block_cols,
+                                       int pads_in_schedule, int out_h, int out_w, const float* out_scale_host, const float* out_bias_host,
                                        void* dst_nhwc4, void* stream) {
   using namespace sia;
   SIA_REQUIRE(src && a_packed && lane_scale && tile_row0 && items && dst_nhwc4 && out_scale_host && out_bias_host);
@@ -463,6 +490,7 @@ extern "C" int sia_preprocess_tc_u8hwc(const uint8_t* src, int batch, int src_h,
   p.batch = batch; p.src_h = src_h; p.src_w = src_w; p.out_h = out_h; p.out_w = out_w;
   p.n_tiles = n_tiles; p.tile_rows = tile_rows; p.n_blocks = n_blocks; p.last_block_cols = last_block_cols;
   p.n_items = n_items;
+  p.pads_in_schedule = pads_in_schedule ? 1 : 0;
   p.odd_shift = row_bytes % 16;
   for (int c = 0; c < 3; ++c) { p.scale[c] = out_scale_host[c]; p.bias[c] = out_bias_host[c]; }
 

@@ -112,7 +112,8 @@ def preprocess_u8hwc(src: torch.Tensor, size, layout: int = LAYOUT_NCHW_F32, mea
             tsc = (ctypes.c_float * 3)(*[float(scale) / float(s) for s in std])
             check(_lib.load().sia_preprocess_tc_u8hwc(
                 ptr(src), b, sh, sw, ptr(tc.a_packed), ptr(tc.lane_scale), ptr(tc.tile_row0), tc.host.n_tiles,
-                tc.host.tile_rows, ptr(tc.items), tc.host.n_items, tc.host.n_blocks, tc.host.last_block_cols, oh, ow,
+                tc.host.tile_rows, ptr(tc.items), tc.host.n_items, tc.host.n_blocks, tc.host.last_block_cols,
+                int(tc.host.pads_in_schedule), oh, ow,
                 tsc, obi, ptr(out), stream_ptr()), "sia_preprocess_tc_u8hwc")
             return out
         if impl == "tensor_core":

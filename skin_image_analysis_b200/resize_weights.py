@@ -190,6 +190,7 @@ TC_BLOCK_COLS = 256       # accumulator columns per block (the 16-byte overlap k
 TC_ITEM_PX = 3            # source pixels one schedule item may consume
 TC_ITEM_LOAD = 16         # accumulator columns one item loads (>= 3 * TC_ITEM_PX)
 TC_A_LBO, TC_A_SBO = 128, (TC_KWIN // 8) * 128     # K-major, no swizzle: 8 x 16-byte core matrices
+NHWC4_PAD = 8             # SIA_NHWC4_PAD: extra pixel columns of the padded NHWC4 row
 
 
 @dataclass
@@ -204,10 +205,11 @@ class TcTables:
     a_packed: np.ndarray       # uint8 [n_tiles, 128*256*2]: fp16 weights in UMMA K-major core-matrix order
     a_dense: np.ndarray        # float64 [n_tiles, 128, 256]: the same weights (fp16-rounded) for tests
     lane_scale: np.ndarray     # float32 [n_tiles, 128]: sum(w) / sum(fp16(w)) per output row (1 for unused lanes)
-    items: np.ndarray          # float32-viewed [n_items, 16]: (col, emit, block, n_px) as int32, then 3 x 4 weights
+    items: np.ndarray          # float32-viewed [n_items, 16]: (col, emit, block, vector-store column of the group or -1) as int32, then 3 x 4 weights
     item_px0: np.ndarray       # int32 [n_items]: first source pixel of each item (tests / emulation)
     n_blocks: int
     last_block_cols: int       # MMA N of the last block (multiple of 16)
+    pads_in_schedule: bool = False   # the vector-store groups also write the zero pad columns of the NHWC4 row
 
     @property
     def n_items(self) -> int:
@@ -270,6 +272,11 @@ def build_tc_tables(src_h: int, src_w: int, out_h: int, out_w: int, antialias: s
             n -= TC_ITEM_PX
         px0.append(cur); npx.append(n); emit.append(j)
         cur += n
+    # align the schedule so that output column j (padded column j + 1) is emitted by an item with index = j + 1
+    # (mod 4): groups of 4 items then cover 4 aligned padded columns and can be stored as one 32-byte sector
+    lead = next(i for i, e in enumerate(emit) if e >= 0)
+    for _ in range((1 - lead) % 4):
+        px0.insert(0, 0); npx.insert(0, 0); emit.insert(0, -1)
     while len(px0) % 8 != 0:                          # the kernel works on groups of 4 + 4 items: pad with no-ops
         px0.append(cur); npx.append(0); emit.append(-1)
     n_items = len(px0)
@@ -296,12 +303,30 @@ def build_tc_tables(src_h: int, src_w: int, out_h: int, out_w: int, antialias: s
         else:
             col = 0                        # loads nothing it uses; stay in the current block
         assert 0 <= col and col + TC_ITEM_LOAD <= TC_BLOCK_COLS
-        info[i, 0:4] = (col, emit[i], block, npx[i])
+        info[i, 0:4] = (col, emit[i], block, -1)
         items[i, 4:16] = w[i].reshape(-1)
+    # groups of 4 items whose pixels are 4 consecutive, 32-byte aligned columns of the padded NHWC4 row (pixel j
+    # lives in column j + 1; an item that emits nothing stands for a zero pad column) are stored as one sector
+    pad_cols = set([0] + list(range(out_w + 1, out_w + NHWC4_PAD)))
+    covered = set()
+    for g0 in range(0, n_items, 4):
+        cols = [emit[g0 + u] + 1 if emit[g0 + u] >= 0 else None for u in range(4)]
+        known = [(u, c) for u, c in enumerate(cols) if c is not None]
+        if known:
+            c0 = known[0][1] - known[0][0]
+        else:                              # an all-pad group continues where the previous vector group ended
+            c0 = info[g0 - 4, 3] + 4 if g0 >= 4 and info[g0 - 4, 3] >= 0 else -1
+        ok = c0 >= 0 and c0 % 4 == 0 and c0 + 4 <= out_w + NHWC4_PAD
+        for u in range(4):
+            ok = ok and ((cols[u] == c0 + u) if cols[u] is not None else (c0 + u in pad_cols))
+        if ok:
+            info[g0, 3] = c0
+            covered.update(c for c in range(c0, c0 + 4) if c in pad_cols)
+    pads_in_schedule = covered == pad_cols
     n_blocks = block + 1
     last_cols = min(TC_BLOCK_COLS, -(-(row_bytes - (n_blocks - 1) * TC_BLOCK_STRIDE) // 16) * 16)
     return TcTables(n_tiles, tile_rows, tile_row0, a_packed.view(np.uint8).reshape(n_tiles, -1), a_dense, lane_scale,
-                    items, np.asarray(px0, np.int32), n_blocks, last_cols)
+                    items, np.asarray(px0, np.int32), n_blocks, last_cols, bool(pads_in_schedule))
 
 
 def tc_emulate(u8: np.ndarray, t: TcTables, out_h: int, out_w: int, scale: float = 1.0 / 255.0) -> np.ndarray:

@@ -166,8 +166,9 @@ def test_tensor_core_tables_reproduce_the_oracle_operator(shape):
     emitted = info[info[:, 1] >= 0, 1]
     assert np.array_equal(emitted, np.arange(ow))                 # every output column exactly once, in order
     assert np.all(info[:, 0] >= 0) and np.all(info[:, 0] + rw.TC_ITEM_LOAD <= rw.TC_BLOCK_COLS)
-    assert np.all(np.diff(info[:, 2]) >= 0) and info[-1, 2] == t.n_blocks - 1 and np.all(info[:, 3] <= rw.TC_ITEM_PX)
-    assert info[:, 3].sum() == w                                   # every source pixel consumed exactly once
+    assert np.all(np.diff(info[:, 2]) >= 0) and info[-1, 2] == t.n_blocks - 1 and t.n_items % 8 == 0
+    vec = info[0::4, 3]
+    assert np.all((vec == -1) | ((vec >= 0) & (vec % 4 == 0) & (vec + 4 <= ow + 8)))
     assert t.a_packed.shape == (t.n_tiles, 128 * 256 * 2)
     rng = np.random.default_rng(h + ow)
     im = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
