@@ -7,14 +7,14 @@
 //                                                            k = byte of the image row (3*x + c)
 //       = ONE GEMM per (image, tile of <=128 output rows): tcgen05.mma kind::f16, fp16 x fp16 -> fp32.
 //         A = the tile's Wy rows (fp16, K-major, resident in shared memory, K = 256 source rows),
-//         B = the image itself: TMA brings raw 64-row x 272-byte windows of the u8 rows into a shared-memory
+//         B = the image itself: TMA brings raw 128-row x 160-byte windows of the u8 rows into a shared-memory
 //             ring (the decode buffer is viewed as double rows of 2*row_bytes so that the row pitch is a
-//             multiple of 16 bytes; odd rows are fetched from a 16-byte aligned start and read back
-//             row_bytes % 16 bytes further in), converter warps widen the bytes to fp16 (PRMT + HSUB2,
+//             multiple of 16 bytes; a row whose window starts 8 bytes off 16-byte alignment is fetched 8 bytes
+//             early and read back shifted), converter warps widen the bytes to fp16 (PRMT + HSUB2,
 //             exact) and store them as the MN-major operand (the byte index k is the contiguous one,
 //             so the HWC decode buffer needs no transposition),
-//         D = 128 lanes (output rows) x 256 columns (bytes 240b .. 240b+255 of the row) fp32 in TMEM,
-//             double buffered.
+//         D = 128 lanes (output rows) x 128 columns (bytes 120b .. 120b+127 of the row) fp32 in TMEM; four of
+//             them: two images are in flight per CTA (one per horizontal-pass warp group), double buffered.
 //   horizontal pass  out[i, j, c] = sum_x Wx[j, x] * V[i, 3x + c]
 //       = the epilogue: thread = TMEM lane = output row.  It executes a static schedule of "items" built
 //         on the host (resize_weights.build_tc_tables): item n loads 9 accumulator columns (<= 3 source
@@ -39,17 +39,17 @@
 namespace sia {
 
 constexpr int TC_KWIN = 256;                     // source rows per tile window (K of the GEMM)
-constexpr int TC_KSTAGE = 64;                    // source rows per pipeline stage
+constexpr int TC_KSTAGE = 128;                   // source rows per pipeline stage
 constexpr int TC_NQ = TC_KWIN / TC_KSTAGE;       // stages per column block
-constexpr int TC_STRIDE = 240;                   // bytes of the image row between column blocks
-constexpr int TC_COLS = 256;                     // accumulator columns per block (16 bytes of overlap)
-constexpr int TC_UNITS = TC_COLS / 8;            // 16-byte fp16 units along N per stage row (= one per lane)
+constexpr int TC_STRIDE = 120;                   // bytes of the image row between column blocks (40 pixels)
+constexpr int TC_COLS = 128;                     // accumulator columns per block (8 bytes of overlap: one item)
+constexpr int TC_UNITS = TC_COLS / 8;            // 16-byte fp16 units along N per stage row
 constexpr int TC_B_LBO = 128;                    // next group of 8 source rows
 constexpr int TC_B_SBO = (TC_KSTAGE / 8) * 128 + 16;   // next 8 bytes of the row (+16: bank spread for the converter)
 constexpr int TC_STAGE_BYTES = ((TC_UNITS * TC_B_SBO + 127) / 128) * 128;
 constexpr int TC_NSTAGE = 2;                     // fp16 operand stages (converter -> MMA)
-constexpr int TC_NRAW = 4;                       // raw u8 stages (TMA -> converter); fewer when the item table is large
-constexpr int TC_RAW_ROWB = TC_COLS + 16;        // bytes per raw row: odd rows start up to 8 bytes early
+constexpr int TC_NRAW = 3;                       // raw u8 stages (TMA -> converter); fewer when the item table is large
+constexpr int TC_RAW_ROWB = TC_COLS + 32;        // bytes per raw row: a row may have to be fetched up to 8 bytes early
 constexpr int TC_RAW_HALF = (TC_KSTAGE / 2) * TC_RAW_ROWB;   // even-row box, then odd-row box
 constexpr int TC_RAW_BYTES = 2 * TC_RAW_HALF;
 constexpr int TC_A_BYTES = 128 * TC_KWIN * 2;    // 65536
@@ -57,9 +57,7 @@ constexpr int TC_A_LBO = 128, TC_A_SBO = (TC_KWIN / 8) * 128;
 constexpr int TC_THREADS = 448;                  // warps 0-3 converters, 4-7 / 8-11 horizontal-pass groups 0 / 1,
 constexpr int TC_WARP_MMA = 12;                  // 12 MMA issuer (+ TMEM alloc), 13 TMA producer
 constexpr int TC_WARP_TMA = 13;                  // (16 warps x 128 registers is what one SM sub-partition quartet holds)
-constexpr int TC_CONV_GROUPS = 1;                // converter groups of 4 warps taking alternate stages
-constexpr int TC_WARP_CONV1 = 14;                // first warp of converter group 1 (if any)
-constexpr int TC_ITEM_BYTES = 64;                // int4 {column, emit, block, n_px} + 3 x float4 weights
+constexpr int TC_ITEM_BYTES = 64;                // int4 {column, emit, block, vector column} + 3 x float4 weights
 
 struct TcParams {
   const uint8_t* a_packed;      // [n_tiles][TC_A_BYTES]
@@ -69,7 +67,7 @@ struct TcParams {
   uint2* dst;                   // [batch][out_h][out_w + 8] NHWC4 bf16
   int batch, src_h, src_w, out_h, out_w;
   int n_tiles, tile_rows, n_blocks, last_block_cols, n_items;
-  int odd_shift;                // row_bytes % 16: odd rows are fetched this many bytes early
+  int odd_shift;                // row_bytes % 16: how far the start of an odd row is from 16-byte alignment
   int n_raw;                    // raw stages in use (<= TC_NRAW)
   int pads_in_schedule;         // the vector-store groups of the schedule also write the zero pad columns
   float scale[3], bias[3];
@@ -113,10 +111,10 @@ preprocess_tc_kernel(const __grid_constant__ CUtensorMap tmap_src, const __grid_
   uint64_t* bars = reinterpret_cast<uint64_t*>(items_s + 4 * p.n_items);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + TC_NSTAGE;
-  uint64_t* tfull_bar = bars + 2 * TC_NSTAGE;
-  uint64_t* tempty_bar = bars + 2 * TC_NSTAGE + 2;
-  uint64_t* a_bar = bars + 2 * TC_NSTAGE + 4;
-  uint64_t* raw_full = bars + 2 * TC_NSTAGE + 5;
+  uint64_t* tfull_bar = bars + 2 * TC_NSTAGE;          // [4]: accumulator 2g + b of warp group g
+  uint64_t* tempty_bar = bars + 2 * TC_NSTAGE + 4;     // [4]
+  uint64_t* a_bar = bars + 2 * TC_NSTAGE + 8;
+  uint64_t* raw_full = bars + 2 * TC_NSTAGE + 9;
   uint64_t* raw_empty = raw_full + TC_NRAW;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + TC_NRAW);
 
@@ -134,7 +132,7 @@ preprocess_tc_kernel(const __grid_constant__ CUtensorMap tmap_src, const __grid_
       mbar_init(&full_bar[i], 4);      // one arrival per converter warp
       mbar_init(&empty_bar[i], 1);     // tcgen05.commit
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 4);    // one arrival per warp of the group
     }
@@ -169,6 +167,9 @@ preprocess_tc_kernel(const __grid_constant__ CUtensorMap tmap_src, const __grid_
           for (int g = 0; g < 2 && k0 + g < n_img; ++g) {
             const int img = img0 + (k0 + g) * img_step;
             const int seq = ((k0 >> 1) * p.n_blocks + blk) * 2 + g;
+            // TMA needs 16-byte aligned starts: a row whose window starts 8 bytes off is fetched 8 bytes early
+            const int col = blk * TC_STRIDE;
+            const int mis_even = col & 15, mis_odd = (col + p.odd_shift) & 15;
             for (int q = 0; q < TC_NQ; ++q) {
               const int r0 = row0 + q * TC_KSTAGE;           // first source row of the stage
               const int even0 = (r0 + 1) >> 1;               // double row of the first even / odd row
@@ -177,11 +178,9 @@ preprocess_tc_kernel(const __grid_constant__ CUtensorMap tmap_src, const __grid_
               if (q == 0) trace(seq, 0);
               mbar_arrive_expect_tx(&raw_full[rs], TC_RAW_BYTES);
               uint8_t* dst = smem_raw_ring + rs * TC_RAW_BYTES;
-              // innermost coordinate in 16-bit elements (the tensor map views the bytes as u16 pairs so that a
-              // 272-byte box is legal)
-              tma_load_3d(dst, &tmap_src, &raw_full[rs], (blk * TC_STRIDE) >> 1, even0, img);
-              tma_load_3d(dst + TC_RAW_HALF, &tmap_src, &raw_full[rs],
-                          (row_bytes - p.odd_shift + blk * TC_STRIDE) >> 1, odd0, img);
+              // innermost coordinate in 16-bit elements (the tensor map views the bytes as u16 pairs)
+              tma_load_3d(dst, &tmap_src, &raw_full[rs], (col - mis_even) >> 1, even0, img);
+              tma_load_3d(dst + TC_RAW_HALF, &tmap_src, &raw_full[rs], (row_bytes + col - mis_odd) >> 1, odd0, img);
               if (q == TC_NQ - 1) trace(seq, 1);
               if (++rs == p.n_raw) { rs = 0; rphase ^= 1; }
             }
@@ -189,80 +188,71 @@ preprocess_tc_kernel(const __grid_constant__ CUtensorMap tmap_src, const __grid_
         }
       }
     }
-  } else if (warp < 4 || (TC_CONV_GROUPS > 1 && warp >= TC_WARP_CONV1)) {
+  } else if (warp < 4) {
     // ================================ converters ============================================
-    // Two groups of four warps take alternate stages.  Inside a stage warp w owns rows w, w+4, ... (a fixed row
-    // parity); lane l owns bytes 8l .. 8l+7 of the block.
-    const int cgroup = warp < 4 ? 0 : 1;
-    const int cw = warp < 4 ? warp : warp - TC_WARP_CONV1;    // warp inside the group
-    const uint32_t parity = (uint32_t)(row0 + cw) & 1u;        // absolute parity of this warp's rows
-    const uint32_t ld_lane = parity * (TC_RAW_HALF + (uint32_t)p.odd_shift) + (uint32_t)lane * 8u;
-    const uint32_t st_lane = (uint32_t)lane * TC_B_SBO;
+    // Per 128-row stage warp w converts rows 8*it + 2*w + (lane >> 4), it = 0..15; lanes 0-15 / 16-31 own the 16
+    // 8-byte pieces of an even / odd row of the pair.
+    const int half = lane >> 4, unit = lane & 15;
+    const int rr0 = 2 * warp + half;                           // this lane's row inside the stage for it = 0
+    const uint32_t parity = (uint32_t)(row0 + rr0) & 1u;       // absolute parity of this lane's rows
+    const uint32_t ld_lane = parity * TC_RAW_HALF + (uint32_t)(rr0 >> 1) * TC_RAW_ROWB + (uint32_t)unit * 8u;
+    const uint32_t st_lane = (uint32_t)unit * TC_B_SBO + (uint32_t)(rr0 & 7) * 16u;
     const __half2 k1024 = __half2half2(__ushort_as_half((unsigned short)0x6400));
-    const int n_stages = n_img * p.n_blocks * TC_NQ;
-    // ring positions of stage `cgroup`, advanced by the number of groups per iteration
-    int stage = cgroup % TC_NSTAGE, rs = cgroup % p.n_raw;
+    int stage = 0, rs = 0;
     uint32_t phase = 0, rphase = 0;
-    for (int it0 = cgroup; it0 < n_stages; it0 += TC_CONV_GROUPS) {
-      mbar_wait(&raw_full[rs], rphase, 46);
-      if (cw == 0 && lane == 0 && (it0 & (TC_NQ - 1)) == 0) trace(it0 / TC_NQ, 2);
-      uint2 v[TC_KSTAGE / 4];
-      {
-        const uint32_t src = smem_u32(smem_raw_ring) + rs * TC_RAW_BYTES + ld_lane;
+    int it0 = 0;
+    for (int k0 = 0; k0 < n_img; k0 += 2) {
+      for (int blk = 0; blk < p.n_blocks; ++blk) {
+        const int col = blk * TC_STRIDE;
+        const uint32_t mis = (uint32_t)((col + (parity ? p.odd_shift : 0)) & 15);   // this row was fetched `mis` bytes early
+        for (int g = 0; g < 2 && k0 + g < n_img; ++g) {
+          for (int q = 0; q < TC_NQ; ++q, ++it0) {
+            mbar_wait(&raw_full[rs], rphase, 46);
+            if (warp == 0 && lane == 0 && q == 0) trace(it0 / TC_NQ, 2);
+            uint2 v[16];
+            {
+              const uint32_t src = smem_u32(smem_raw_ring) + rs * TC_RAW_BYTES + ld_lane + mis;
 #pragma unroll
-        for (int it = 0; it < TC_KSTAGE / 4; ++it) {
-          const int r = cw + 4 * it;
-          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];"
-                       : "=r"(v[it].x), "=r"(v[it].y)
-                       : "r"(src + (uint32_t)(r >> 1) * TC_RAW_ROWB));
-        }
-      }
-#ifdef SIA_TC_EARLY_RELEASE
-      {   // consume every loaded register before the raw stage is handed back (forces the loads to have completed)
-        uint32_t x = 0;
+              for (int it = 0; it < 16; ++it) {              // row 8*it + rr0 -> index 4*it + (rr0 >> 1) of its parity box
+                asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];"
+                             : "=r"(v[it].x), "=r"(v[it].y)
+                             : "r"(src + (uint32_t)(4 * it) * TC_RAW_ROWB));
+              }
+            }
+            mbar_wait(&empty_bar[stage], phase ^ 1, 40);
+            {
+              const uint32_t base = smem_u32(smem_b) + stage * TC_STAGE_BYTES + st_lane;
 #pragma unroll
-        for (int it = 0; it < TC_KSTAGE / 4; ++it) x |= v[it].x | v[it].y;
-        asm volatile("" ::"r"(x) : "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&raw_empty[rs]);
-      }
-#endif
-      mbar_wait(&empty_bar[stage], phase ^ 1, 40);
-      {
-        const uint32_t base = smem_u32(smem_b) + stage * TC_STAGE_BYTES + st_lane;
+              for (int it = 0; it < 16; ++it) {              // row 8*it + rr0: core-matrix group `it`, row rr0 of it
+                // u8 -> fp16, exact: byte b becomes the half 0x6400 | b = 1024 + b, then subtract 1024
+                uint32_t h[4];
+                h[0] = __byte_perm(v[it].x, 0x64646464u, 0x4140);
+                h[1] = __byte_perm(v[it].x, 0x64646464u, 0x4342);
+                h[2] = __byte_perm(v[it].y, 0x64646464u, 0x4140);
+                h[3] = __byte_perm(v[it].y, 0x64646464u, 0x4342);
 #pragma unroll
-        for (int it = 0; it < TC_KSTAGE / 4; ++it) {
-          const int r = cw + 4 * it;               // row inside the stage
-          // u8 -> fp16, exact: byte b becomes the half 0x6400 | b = 1024 + b, then subtract 1024
-          uint32_t h[4];
-          h[0] = __byte_perm(v[it].x, 0x64646464u, 0x4140);
-          h[1] = __byte_perm(v[it].x, 0x64646464u, 0x4342);
-          h[2] = __byte_perm(v[it].y, 0x64646464u, 0x4140);
-          h[3] = __byte_perm(v[it].y, 0x64646464u, 0x4342);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            __half2 x = __hsub2(*reinterpret_cast<__half2*>(&h[k]), k1024);
-            h[k] = *reinterpret_cast<uint32_t*>(&x);
+                for (int k = 0; k < 4; ++k) {
+                  __half2 x = __hsub2(*reinterpret_cast<__half2*>(&h[k]), k1024);
+                  h[k] = *reinterpret_cast<uint32_t*>(&x);
+                }
+                const uint32_t dst = base + (uint32_t)it * TC_B_LBO;
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(h[0]), "r"(h[1]), "r"(h[2]),
+                             "r"(h[3])
+                             : "memory");
+              }
+            }
+            fence_proxy_async_smem();      // generic-proxy stores -> visible to the UMMA operand reads
+            __syncwarp();
+            if (lane == 0) {
+              mbar_arrive(&full_bar[stage]);
+              mbar_arrive(&raw_empty[rs]);
+              if (warp == 0 && q == TC_NQ - 1) trace(it0 / TC_NQ, 3);
+            }
+            if (++stage == TC_NSTAGE) { stage = 0; phase ^= 1; }
+            if (++rs == p.n_raw) { rs = 0; rphase ^= 1; }
           }
-          const uint32_t dst = base + (uint32_t)(r >> 3) * TC_B_LBO + (uint32_t)(r & 7) * 16u;
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(h[0]), "r"(h[1]), "r"(h[2]),
-                       "r"(h[3])
-                       : "memory");
         }
       }
-      fence_proxy_async_smem();      // generic-proxy stores -> visible to the UMMA operand reads
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&full_bar[stage]);
-#ifndef SIA_TC_EARLY_RELEASE
-        mbar_arrive(&raw_empty[rs]);
-#endif
-        if (cw == 0 && (it0 & (TC_NQ - 1)) == TC_NQ - 1) trace(it0 / TC_NQ, 3);
-      }
-      stage += TC_CONV_GROUPS;
-      if (stage >= TC_NSTAGE) { stage -= TC_NSTAGE; phase ^= 1; }
-      rs += TC_CONV_GROUPS;
-      if (rs >= p.n_raw) { rs -= p.n_raw; rphase ^= 1; }
     }
   } else if (warp == TC_WARP_MMA) {
     // ================================ MMA issuer ============================================
@@ -273,7 +263,7 @@ preprocess_tc_kernel(const __grid_constant__ CUtensorMap tmap_src, const __grid_
     mbar_wait(a_bar, 0, 41);
     int stage = 0;
     uint32_t phase = 0;
-    uint32_t acc_phase[2] = {0u, 0u};
+    uint32_t acc_cnt[2] = {0u, 0u};                 // blocks issued so far for warp group g: buffer = cnt & 1
     for (int k0 = 0; k0 < n_img; k0 += 2) {
       for (int blk = 0; blk < p.n_blocks; ++blk) {
         const uint32_t idesc = tc_idesc((uint32_t)(blk == p.n_blocks - 1 ? p.last_block_cols : TC_COLS));
@@ -281,13 +271,14 @@ preprocess_tc_kernel(const __grid_constant__ CUtensorMap tmap_src, const __grid_
         for (int g = 0; g < 2; ++g) {
           if (k0 + g < n_img) {
             const int seq = ((k0 >> 1) * p.n_blocks + blk) * 2 + g;
+            const int buf = 2 * g + (int)(acc_cnt[g] & 1u);
 #ifndef SIA_TC_FREE
-            mbar_wait(&tempty_bar[g], acc_phase[g] ^ 1, 42);
+            mbar_wait(&tempty_bar[buf], ((acc_cnt[g] >> 1) & 1u) ^ 1u, 42);
 #endif
-            acc_phase[g] ^= 1;
+            ++acc_cnt[g];
             tc_fence_after_sync();
             if (lane == 0) trace(seq, 4);
-            const uint32_t d_tmem = tmem_base + g * TC_COLS;
+            const uint32_t d_tmem = tmem_base + buf * TC_COLS;
             for (int q = 0; q < TC_NQ; ++q) {
               mbar_wait(&full_bar[stage], phase, 43);
               tc_fence_after_sync();
@@ -300,7 +291,7 @@ preprocess_tc_kernel(const __grid_constant__ CUtensorMap tmap_src, const __grid_
                                  b_stage + kk * ((2 * TC_B_LBO) >> 4), b_hi, idesc, (q | kk) ? 1u : 0u);
                 }
                 umma_commit(&empty_bar[stage]);
-                if (q == TC_NQ - 1) umma_commit(&tfull_bar[g]);
+                if (q == TC_NQ - 1) umma_commit(&tfull_bar[buf]);
               }
               __syncwarp();
               if (++stage == TC_NSTAGE) { stage = 0; phase ^= 1; }
@@ -321,10 +312,9 @@ preprocess_tc_kernel(const __grid_constant__ CUtensorMap tmap_src, const __grid_
     const float sc0 = p.scale[0] * ls, sc1 = p.scale[1] * ls, sc2 = p.scale[2] * ls;
     const float bi0 = p.bias[0], bi1 = p.bias[1], bi2 = p.bias[2];
     const int pitch = p.out_w + SIA_NHWC4_PAD;
-    const uint32_t t_acc = tmem_base + ((uint32_t)(32 * e) << 16) + g * TC_COLS;
-    uint64_t* tfull = &tfull_bar[g];
-    uint64_t* tempty = &tempty_bar[g];
-    uint32_t acc_phase = 0;
+    const uint32_t t_lanes = tmem_base + ((uint32_t)(32 * e) << 16) + 2 * g * TC_COLS;
+    uint32_t acc_cnt = 0;                          // blocks acquired so far: accumulator 2g + ((cnt - 1) & 1) is current
+    uint32_t t_acc = t_lanes;
     for (int k = g; k < n_img; k += 2) {
       const int img = img0 + k * img_step;
       uint2* orow = p.dst + ((size_t)img * p.out_h + (row_ok ? i : 0)) * pitch;
@@ -338,20 +328,22 @@ preprocess_tc_kernel(const __grid_constant__ CUtensorMap tmap_src, const __grid_
       for (int s = 0; s < 4; ++s) acc[s][0] = acc[s][1] = acc[s][2] = 0.f;
       int cur_block = -1;
 
-      // makes `block` the accumulator contents being read: every block is waited for and handed back in order
+      // makes `block` the accumulator being read: every block is waited for and handed back in order
       auto acquire = [&](int block) {
         while (cur_block < block) {
           if (cur_block >= 0) {
             tmem_ld_wait();                        // loads of the block being handed back may still be in flight
             tc_fence_before_sync();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty);
+            if (lane == 0) mbar_arrive(&tempty_bar[2 * g + ((acc_cnt - 1) & 1u)]);
             if (e == 0 && lane == 0) trace(((k >> 1) * p.n_blocks + cur_block) * 2 + g, 7);
           }
+          const uint32_t b = acc_cnt & 1u;
 #ifndef SIA_TC_FREE
-          mbar_wait(tfull, acc_phase, 44);
+          mbar_wait(&tfull_bar[2 * g + b], (acc_cnt >> 1) & 1u, 44);
 #endif
-          acc_phase ^= 1;
+          ++acc_cnt;
+          t_acc = t_lanes + b * TC_COLS;
           tc_fence_after_sync();
           ++cur_block;
           if (e == 0 && lane == 0) trace(((k >> 1) * p.n_blocks + cur_block) * 2 + g, 6);
@@ -445,9 +437,10 @@ preprocess_tc_kernel(const __grid_constant__ CUtensorMap tmap_src, const __grid_
       }
       // hand the last accumulator(s) of this image back
       acquire(p.n_blocks - 1);
+      tmem_ld_wait();
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty);
+      if (lane == 0) mbar_arrive(&tempty_bar[2 * g + ((acc_cnt - 1) & 1u)]);
     }
   }
 
@@ -477,7 +470,7 @@ extern "C" int sia_preprocess_tc_u8hwc(const uint8_t* src, int batch, int src_h,
   // 8-byte pieces; rows paired for the TMA view; every image 16-byte aligned
   if (row_bytes % 8 != 0 || src_h % 2 != 0 || !aligned(src, 16) || ((uint64_t)src_h * row_bytes) % 16 != 0)
     return SIA_E_UNSUPPORTED;
-  if ((n_blocks - 1) * TC_STRIDE >= row_bytes || n_blocks * TC_STRIDE + 16 < row_bytes) return SIA_E_INVALID;
+  if ((n_blocks - 1) * TC_STRIDE >= row_bytes || (n_blocks + 1) * TC_STRIDE < row_bytes) return SIA_E_INVALID;
   if (n_tiles > sm_count()) return SIA_E_UNSUPPORTED;
   if (int wrc = ensure_watchdog()) return wrc;
 
@@ -504,7 +497,7 @@ extern "C" int sia_preprocess_tc_u8hwc(const uint8_t* src, int batch, int src_h,
   int smem = 0;
   for (p.n_raw = TC_NRAW; p.n_raw >= 2; --p.n_raw) {
     smem = 1024 + TC_A_BYTES + p.n_raw * TC_RAW_BYTES + TC_NSTAGE * TC_STAGE_BYTES + n_items * TC_ITEM_BYTES +
-           (2 * TC_NSTAGE + 2 * TC_NRAW + 6) * 8;
+           (2 * TC_NSTAGE + 2 * TC_NRAW + 10) * 8;
     if (smem <= 227 * 1024) break;
   }
   if (p.n_raw < 2) return SIA_E_UNSUPPORTED;

@@ -185,10 +185,10 @@ def rescale_size(h: int, w: int, output_size) -> tuple[int, int]:
 # -------------------------------------------------------------------------------------------------
 TC_LANES = 128            # output rows per tile = TMEM lanes of one accumulator
 TC_KWIN = 256             # source rows one tile may read (K of the vertical GEMM)
-TC_BLOCK_STRIDE = 240     # image-row bytes between column blocks (multiple of 16)
-TC_BLOCK_COLS = 256       # accumulator columns per block (the 16-byte overlap keeps every item in one block)
+TC_BLOCK_STRIDE = 120     # image-row bytes between column blocks (40 pixels; multiple of 8)
+TC_BLOCK_COLS = 128       # accumulator columns per block (the 8-byte overlap keeps every item in one block)
 TC_ITEM_PX = 3            # source pixels one schedule item may consume
-TC_ITEM_LOAD = 16         # accumulator columns one item loads (>= 3 * TC_ITEM_PX)
+TC_ITEM_LOAD = 9          # accumulator columns one item loads (= 3 * TC_ITEM_PX)
 TC_A_LBO, TC_A_SBO = 128, (TC_KWIN // 8) * 128     # K-major, no swizzle: 8 x 16-byte core matrices
 NHWC4_PAD = 8             # SIA_NHWC4_PAD: extra pixel columns of the padded NHWC4 row
 
