@@ -86,8 +86,8 @@ def preprocess_u8hwc(src: torch.Tensor, size, layout: int = LAYOUT_NCHW_F32, mea
     use the 15-bit integer-dot-product horizontal pass (<= 0.03 bf16 ulp from the fp32 pass); the fp32
     layout always uses fp32 arithmetic.  ``impl``: "cuda_core" (csrc/preprocess.cu), "tensor_core"
     (csrc/preprocess_tc.cu: vertical pass as a tcgen05 GEMM; NHWC4 layout, src_w % 8 == 0, <= 256 source rows
-    per 128 output rows) or "auto" = the faster one for the geometry (today: cuda_core; the tensor-core kernel
-    reaches the same time at the bench shape).
+    per 128 output rows) or "auto" = tensor_core whenever it applies and ``fixed_point`` allows a reduced-
+    precision pass (0.115 ms vs 0.137 ms at the bench shape), else cuda_core.
     """
     _need(src, torch.uint8, "src")
     if src.dim() != 4 or src.shape[3] != 3:
@@ -106,7 +106,7 @@ def preprocess_u8hwc(src: torch.Tensor, size, layout: int = LAYOUT_NCHW_F32, mea
     obi = (ctypes.c_float * 3)(*[-float(m) / float(s) for m, s in zip(mean, std)])
     if impl not in ("auto", "cuda_core", "tensor_core"):
         raise ValueError("impl must be 'auto', 'cuda_core' or 'tensor_core'")
-    if impl == "tensor_core":
+    if impl == "tensor_core" or (impl == "auto" and fixed_point and layout == LAYOUT_NHWC4_BF16):
         tc = _tc_tables(src.device.index, sh, sw, oh, ow, antialias) if layout == LAYOUT_NHWC4_BF16 else None
         if tc is not None and src.data_ptr() % 16 == 0:
             tsc = (ctypes.c_float * 3)(*[float(scale) / float(s) for s in std])
@@ -116,7 +116,7 @@ def preprocess_u8hwc(src: torch.Tensor, size, layout: int = LAYOUT_NCHW_F32, mea
                 int(tc.host.pads_in_schedule), oh, ow,
                 tsc, obi, ptr(out), stream_ptr()), "sia_preprocess_tc_u8hwc")
             return out
-        if impl == "tensor_core":
+        if impl == "tensor_core" or (impl == "auto" and fixed_point and layout == LAYOUT_NHWC4_BF16):
             raise SiaError("tensor-core preprocess does not support this geometry / layout")
     check(_lib.load().sia_preprocess_u8hwc(
         ptr(src), b, sh, sw, ptr(tab.x_off), ptr(tab.x_w), ptr(tab.x_wq) if fixed_point else 0, tab.host.x_taps,

@@ -58,7 +58,8 @@ def test_bf16_layouts_within_one_ulp(fixed_point):
     want = np.stack([R.transform_u8(im, (224, 224)) for im in imgs])
     want_bf = torch.from_numpy(want).to(torch.bfloat16).float().numpy()
     nchw = _gpu(imgs, (224, 224), ops.LAYOUT_NCHW_BF16, fixed_point=fixed_point).float().cpu().numpy()
-    nhwc4 = _gpu(imgs, (224, 224), ops.LAYOUT_NHWC4_BF16, fixed_point=fixed_point).float().cpu().numpy()
+    nhwc4 = _gpu(imgs, (224, 224), ops.LAYOUT_NHWC4_BF16, fixed_point=fixed_point,
+                 impl="cuda_core").float().cpu().numpy()
     assert nhwc4.shape == (2, 224, 224 + ops.NHWC4_PAD, 4) and np.all(nhwc4[..., 3] == 0)
     assert np.all(nhwc4[:, :, 0] == 0) and np.all(nhwc4[:, :, 225:] == 0)        # zero pad columns
     assert np.array_equal(nhwc4[:, :, 1:225, :3].transpose(0, 3, 1, 2), nchw)
