@@ -124,7 +124,7 @@ constexpr int TAIL_IMGS = 4;     // images per CTA (amortises the W2 read)
 constexpr int TAIL_MAX_N1 = 512;
 constexpr int TAIL_MAX_N2 = 256;
 
-__global__ void __launch_bounds__(TAIL_THREADS)
+__global__ void __launch_bounds__(TAIL_THREADS, 1)
 head_tail_kernel(const float* __restrict__ partial, int splits, int M, int n1, int n2, const float* __restrict__ b1,
                  const float* __restrict__ w2t, const float* __restrict__ b2, const float* __restrict__ w3,
                  const float* __restrict__ b3, float* __restrict__ logp, uint8_t* __restrict__ pred,
@@ -142,13 +142,22 @@ head_tail_kernel(const float* __restrict__ partial, int splits, int M, int n1, i
     if (m0 + img < M) {
       const float* src = partial + (size_t)(m0 + img) * n1 + k;
       const size_t step = (size_t)M * n1;
+      // all loads of a batch are issued before the first add (one memory round trip per 16 splits); the adds stay
+      // in split order, so the sum is deterministic
       int sp = 0;
+      for (; sp + 16 <= splits; sp += 16) {
+        float v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) v[u] = __ldg(src + (size_t)(sp + u) * step);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) s += v[u];
+      }
       for (; sp + 4 <= splits; sp += 4) {
-        const float a = src[(size_t)sp * step], b = src[(size_t)(sp + 1) * step];
-        const float c = src[(size_t)(sp + 2) * step], d = src[(size_t)(sp + 3) * step];
+        const float a = __ldg(src + (size_t)sp * step), b = __ldg(src + (size_t)(sp + 1) * step);
+        const float c = __ldg(src + (size_t)(sp + 2) * step), d = __ldg(src + (size_t)(sp + 3) * step);
         s = (((s + a) + b) + c) + d;
       }
-      for (; sp < splits; ++sp) s += src[(size_t)sp * step];
+      for (; sp < splits; ++sp) s += __ldg(src + (size_t)sp * step);
       s = fmaxf(s + b1[k], 0.f);
     }
     h1[img][k] = s;
@@ -166,6 +175,16 @@ head_tail_kernel(const float* __restrict__ partial, int splits, int M, int n1, i
 #pragma unroll
       for (int img = 0; img < TAIL_IMGS; ++img) a[img] = 0.f;
       int k = k_lo;
+      for (; k + 32 <= k_hi; k += 32) {             // 32 weight loads in flight: the loop is L2-latency bound
+        float w[32];
+#pragma unroll
+        for (int u = 0; u < 32; ++u) w[u] = __ldg(w2t + (size_t)(k + u) * n2 + j);
+#pragma unroll
+        for (int u = 0; u < 32; ++u) {
+#pragma unroll
+          for (int img = 0; img < TAIL_IMGS; ++img) a[img] = fmaf(w[u], h1[img][k + u], a[img]);
+        }
+      }
       for (; k + 8 <= k_hi; k += 8) {
         float w[8];
 #pragma unroll

@@ -55,6 +55,14 @@ def main():
     res["conv1"] = timed(lambda: ops.conv7x7_c3_relu_pool2(x4, w1, b1, out=a1))
     res["conv2"] = timed(lambda: ops.conv3x3_relu_pool2(a1, w2, b2, 64, out=a2))
     res["conv3"] = timed(lambda: ops.conv3x3_relu_pool2(a2, w3, b3, 128, out=a3))
+    w_fc = torch.randn(512, 100352, device="cuda", generator=g).to(torch.bfloat16)
+    splits = 18 if b >= 256 else 37
+    part = ops.linear_splitk(a3.view(b, -1), w_fc, splits)
+    b1f, b2f, b3f = torch.zeros(512, device="cuda"), torch.zeros(256, device="cuda"), torch.zeros(2, device="cuda")
+    w2t = torch.randn(512, 256, device="cuda", generator=g) * 0.05
+    w3f = torch.randn(2, 256, device="cuda", generator=g) * 0.05
+    res["fc1"] = timed(lambda: ops.linear_splitk(a3.view(b, -1), w_fc, splits, out=part))
+    res["tail"] = timed(lambda: ops.head_tail(part, b1f, w2t, b2f, w3f, b3f))
     print(json.dumps({k: (round(v, 4) if isinstance(v, float) else v) for k, v in res.items()}))
 
 
