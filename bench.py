@@ -70,6 +70,19 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def ncu_traffic(stage: str, batch: int):
+    """DRAM bytes per launch of `stage` (dram__bytes_read.sum + dram__bytes_write.sum) from the committed
+    `ncu --set full` capture of the same workload (profiles/r01_final_traffic.json, per image there), scaled to
+    this run's batch; None when no capture is committed."""
+    path = os.path.join(ROOT, "profiles", "r01_final_traffic.json")
+    try:
+        with open(path) as f:
+            per_image = json.load(f)["dram_bytes_per_image"]
+        return per_image[stage] * batch
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -375,7 +388,7 @@ def run_ours(args):
     dominant = max((k for k in stages if "bound" in stages[k]), key=lambda k: stages[k]["ms"])
     d = stages[dominant]
     roofline = {"kernel": dominant, "bound": d["bound"], "achieved": d["achieved"], "peak": d["peak"],
-                "unit": d["unit"], "frac": d["frac"], "traffic": None,
+                "unit": d["unit"], "frac": d["frac"], "traffic": ncu_traffic(dominant, batch),
                 "peak_source": peaks["source"] + (" (sustained bf16 GEMM: timed inside whole steps)"
                                                  if d["bound"] == "tensor" else " (copy)"),
                 "kernel_share_of_step": d["ms"] / (1e3 * dt / steps)}

@@ -36,12 +36,36 @@ WANT = [
 ]
 
 
+def traffic_json(rows, hdr, idx, units, batch):
+    """{stage: dram bytes per image} from dram__bytes_read.sum + dram__bytes_write.sum of the FIRST launch of every
+    kernel of the step (bench.py reports it as roofline.traffic)."""
+    import json
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    stage_of = (("preprocess", "preprocess"), ("conv1_kernel", "conv1"), ("conv3x3_pair", "conv2"),
+                ("conv3x3_kernel<32", "conv2"), ("conv3x3_kernel<64", "conv3"), ("conv3x3_stream", "conv4"),
+                ("linear_splitk", "fc1"), ("head_tail", "tail"))
+    out = {}
+    for row in rows:
+        name = row[idx["Kernel Name"]]
+        for key, stage in stage_of:
+            if key in name and stage not in out:
+                total = 0.0
+                for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    total += float(row[idx[m]].replace(",", "")) * scale.get(units[idx[m]], 1.0)
+                out[stage] = total / batch
+    return json.dumps({"batch": batch, "source": "ncu --set full, first launch of each kernel", "dram_bytes_per_image": out},
+                      indent=1)
+
+
 def main():
     rep = sys.argv[1]
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
+    if len(sys.argv) > 3 and sys.argv[2] == "--traffic":
+        print(traffic_json(rows[2:], hdr, idx, units, int(sys.argv[3])))
+        return
     for row in rows[2:]:
         name = row[idx["Kernel Name"]].split("(")[0].replace("void ", "")
         print(f"== {name}  grid {row[idx['Grid Size']]} block {row[idx['Block Size']]}")
