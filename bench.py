@@ -251,15 +251,12 @@ def stage_breakdown(eng, batch, peaks, iters=12):
         ops.preprocess_u8hwc(eng.u8[slot], (size, size), ops.LAYOUT_NHWC4_BF16, out=eng.x4)
         ev[k].record(eng.stream); k += 1
         h = eng.x4
-        for i, (packed, bias, _cin, cout) in enumerate(plan.convs):
-            if i == 0:
-                h = ops.conv7x7_c3_relu_pool2(h, packed, bias, out=acts[0])
-            else:
-                h = ops.conv3x3_relu_pool2(h, packed, bias, cout, out=acts[i])
+        for i in range(len(plan.convs)):
+            h = plan.conv_block(i, h, acts[i])
             ev[k].record(eng.stream); k += 1
         ops.linear_splitk(h.view(batch, -1), plan.w1, ws["splits"], out=ws["partial"])
         ev[k].record(eng.stream); k += 1
-        ops.head_tail(ws["partial"], plan.b1, plan.w2t, plan.b2, plan.w3, plan.b3, logp=ws["logp"], pred=ws["pred"])
+        plan.tail(ws["partial"], logp=ws["logp"], pred=ws["pred"])
         ev[k].record(eng.stream)
 
     total = dict.fromkeys(names, 0.0)
@@ -278,10 +275,12 @@ def stage_breakdown(eng, batch, peaks, iters=12):
                          "frac": gbs / peaks["hbm_gbs"]}
     side = size
     flops = {}
-    for i, (_p, _b, cin, cout) in enumerate(plan.convs):
+    cin = 3
+    for i, cout in enumerate(plan.widths):                    # algorithmic FLOPs: real widths, no padding
         flops[f"conv{i + 1}"] = conv_flops_per_image(cin, cout, 7 if i == 0 else 3, side)
         side //= 2
-    flops["fc1"] = 2 * plan.feat * plan.n1
+        cin = cout
+    flops["fc1"] = 2 * (plan.widths[-1] * side * side) * plan.n1
     for nm, fl in flops.items():
         tf = fl * batch / total[nm] / 1e12
         out[nm] = {"ms": total[nm] * 1e3, "bound": "tensor", "achieved": tf, "unit": "TFLOP/s",
@@ -300,6 +299,7 @@ def run_ours(args):
     rank, world, local = D.init_from_env()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = D.bind_to_gpu_numa_node(local) if world > 1 else {"numa_node": None, "cpus": 0}
     wl = WORKLOADS[args.workload]
     batch, steps, warmup = (args.batch or wl["batch"]), args.steps, args.warmup
     peaks = measured_peaks()
@@ -400,7 +400,8 @@ def run_ours(args):
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": wl["text"], "global_batch": batch * world, "batch_per_gpu": batch,
                    "parallelism": f"dp{world}", "l2": f"inputs larger than L2: ring of {n_slots} distinct "
-                   f"{batch * SRC_H * SRC_W * 3 / 1e6:.0f} MB batches per GPU", "cuda_graph": True},
+                   f"{batch * SRC_H * SRC_W * 3 / 1e6:.0f} MB batches per GPU", "cuda_graph": True,
+                   "host_numa_node_rank0": numa["numa_node"]},
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * dt_e2e / e2e_steps},

@@ -117,18 +117,30 @@ int sia_pack_conv3x3(const float* w_oihw, int cin, int cout, void* packed, void*
 size_t sia_pack_conv3x3_bytes(int cin, int cout);
 /* fc1 [n, c*h*w] (CHW-flattened columns) -> bf16 [n, h*w*c] (HWC-flattened columns). */
 int sia_pack_linear_chw_to_hwc(const float* w, int n, int c, int hw, void* packed_bf16, void* stream);
+/* Same with zero padding to [n_pad, h*w*c_pad]: channel-padded activations, n_pad % 128 == 0 for sia_linear_splitk. */
+int sia_pack_linear_chw_to_hwc_padded(const float* w, int n, int c, int hw, int n_pad, int c_pad, void* packed_bf16,
+                                      void* stream);
+/* conv [cout,cin,3,3] zero-padded to the buffer widths cin_pad (32 or a multiple of 64) x cout_pad (multiple of 8):
+ * what the arbitrary layer widths of tone_bias_optuna.define_isic_model (src/tone_bias_optuna.py:123-173) need. */
+int sia_pack_conv3x3_padded(const float* w_oihw, int cin, int cout, int cin_pad, int cout_pad, void* packed,
+                            void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K4  convolution blocks: conv + bias + ReLU + 2x2/2 max-pool, bf16 in / fp32 accumulate / bf16 out.
  *   in  : padded NHWC4 bf16 [B,h,w+8,4] (conv7x7_c3)  or NHWC bf16 [B,h,w,cin] (conv3x3)
  *   out : NHWC bf16 [B,h/2,w/2,cout]
  * h and w must be even; conv7x7_c3 needs w%16==0 (conv3x3 tiles past the right / bottom edge are masked).
- * Supported (cin,cout): (32,64), (64,128), (128,256).
+ * (cin,cout) = channel counts of the buffers: (32,64), (64,128) use resident-weight kernels; any other pair with
+ * cin % 64 == 0, cin <= 256 and cout in {64,128,192,256} uses the streamed-weight kernel.
  * ------------------------------------------------------------------------------------------ */
 int sia_conv7x7_c3_relu_pool2(const void* in_nhwc4, int batch, int h, int w, const void* w_packed,
                               const float* bias, void* out_nhwc, void* stream);
 int sia_conv3x3_relu_pool2(const void* in_nhwc, int batch, int h, int w, int cin, int cout, const void* w_packed,
                            const float* bias, void* out_nhwc, void* stream);
+/* conv7x7_c3 writing its 32 output channels at channel offset c_offset of an NHWC buffer with c_stride channels per
+ * pixel: first layers wider than 32 channels run as several launches over 32-channel slices of the weights. */
+int sia_conv7x7_c3_relu_pool2_strided(const void* in_nhwc4, int batch, int h, int w, const void* w_packed,
+                                      const float* bias, void* out_nhwc, int c_stride, int c_offset, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K5  split-K linear:  partial[s][m][n] = sum_{k in slice s} a[m][k] * w[n][k]   (fp32)
@@ -149,6 +161,15 @@ int sia_head_tail(const float* partial, int splits, int m, int n1, int n2, const
                   const float* b2, const float* w3, const float* b3, float* logp, uint8_t* pred,
                   const uint8_t* label, const uint8_t* groups, int groups_stride, int n_attr, int n_groups,
                   long long* counts, void* stream);
+
+/* The same tail for a chain of n_layers Linear layers after fc1 (tone_bias_optuna.define_isic_model builds 2-5
+ * hidden layers): wt_host / b_host / n_out_host are HOST arrays of n_layers device pointers / widths, weights
+ * transposed to [n_in][n_out]; ReLU after every layer but the last, whose width must be 2.  partial is
+ * [splits][m][n1_stride] (n1 <= n1_stride: the split-K GEMM pads N to a multiple of 128). */
+int sia_head_tail_chain(const float* partial, int splits, int m, int n1, int n1_stride, const float* b1, int n_layers,
+                        const float* const* wt_host, const float* const* b_host, const int* n_out_host, float* logp,
+                        uint8_t* pred, const uint8_t* label, const uint8_t* groups, int groups_stride, int n_attr,
+                        int n_groups, long long* counts, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K7  counts[a][g][label][pred] += 1 for every instance i and attribute a with

@@ -115,6 +115,28 @@ def forward(kind: str, state: dict[str, torch.Tensor], x: torch.Tensor,
     return out
 
 
+@torch.no_grad()
+def forward_sequential(state: dict[str, torch.Tensor], x: torch.Tensor) -> torch.Tensor:
+    """fp32 forward of the ``nn.Sequential`` built by ``define_isic_model`` (tone_bias_optuna.py:123-173) from its
+    state_dict (keys ``<index>.weight`` / ``<index>.bias`` in layer order): every 4-D weight is a
+    Conv2d(stride 1, padding='same') + ReLU + MaxPool2d(2,2) block, then Flatten, every 2-D weight a Linear with
+    ReLU (+ Dropout = identity in eval) except the last, then LogSoftmax(dim=1)."""
+    names = sorted({k.rsplit(".", 1)[0] for k in state}, key=lambda n: int(n))
+    h = x.to(torch.float32)
+    linears = [n for n in names if state[n + ".weight"].dim() == 2]
+    for n in names:
+        w, b = state[n + ".weight"].float(), state[n + ".bias"].float()
+        if w.dim() == 4:
+            h = F.max_pool2d(F.relu(F.conv2d(h, w, b, stride=1, padding="same")), kernel_size=(2, 2))
+        else:
+            if h.dim() > 2:
+                h = torch.flatten(h, 1)
+            h = F.linear(h, w, b)
+            if n != linears[-1]:
+                h = F.relu(h)
+    return F.log_softmax(h, dim=1)
+
+
 def logits_from_logprobs_margin(logp: torch.Tensor) -> torch.Tensor:
     """l1 - l0 (the decision margin is invariant under log-softmax)."""
     return logp[:, 1] - logp[:, 0]

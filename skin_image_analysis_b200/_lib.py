@@ -36,6 +36,11 @@ SIGNATURES = {
     "sia_pack_conv3x3": (c_int, [_P, c_int, c_int, _P, _P]),
     "sia_pack_conv3x3_bytes": (c_size_t, [c_int, c_int]),
     "sia_pack_linear_chw_to_hwc": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
+    "sia_pack_linear_chw_to_hwc_padded": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "sia_pack_conv3x3_padded": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P]),
+    "sia_conv7x7_c3_relu_pool2_strided": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, c_int, c_int, _P]),
+    "sia_head_tail_chain": (c_int, [_P, c_int, c_int, c_int, c_int, _P, c_int, ctypes.POINTER(_P), ctypes.POINTER(_P),
+                                    ctypes.POINTER(c_int), _P, _P, _P, _P, c_int, c_int, c_int, _P, _P]),
     "sia_conv7x7_c3_relu_pool2": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, _P]),
     "sia_conv3x3_relu_pool2": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P]),
     "sia_linear_splitk": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P]),

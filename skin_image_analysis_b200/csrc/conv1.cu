@@ -84,7 +84,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 __global__ void __launch_bounds__(C1_THREADS, 1)
 conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restrict__ w_packed,
              const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int H, int W, int tiles_y, int tiles_x,
-             int total_tiles) {
+             int total_tiles, int c_stride) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_b = smem;                                   // 65536
@@ -227,7 +227,7 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
       const int py = t.ty * (C1_TILE_Y / 2) + yp;
       const int px = t.tx * (C1_TILE_X / 2) + xp;
       const bool in_range = py < Ho && px < Wo;
-      uint4* opix = reinterpret_cast<uint4*>(out + (((size_t)t.n * Ho + py) * Wo + px) * 32);
+      uint4* opix = reinterpret_cast<uint4*>(out + (((size_t)t.n * Ho + py) * Wo + px) * c_stride);
       wait_full.begin();
       mbar_wait(&tfull_bar[acc], acc_phase, 34);
       wait_full.end();
@@ -319,11 +319,13 @@ extern "C" int sia_pack_conv7x7_c3(const float* w_oihw, void* packed, void* stre
   return launch_status();
 }
 
-extern "C" int sia_conv7x7_c3_relu_pool2(const void* in_nhwc4, int batch, int h, int w, const void* w_packed,
-                                         const float* bias, void* out_nhwc, void* stream) {
+extern "C" int sia_conv7x7_c3_relu_pool2_strided(const void* in_nhwc4, int batch, int h, int w, const void* w_packed,
+                                                 const float* bias, void* out_nhwc, int c_stride, int c_offset,
+                                                 void* stream) {
   using namespace sia;
   SIA_REQUIRE(in_nhwc4 && w_packed && bias && out_nhwc && batch >= 1 && h >= 2 && w >= 16);
   SIA_REQUIRE(aligned(in_nhwc4, 16) && aligned(w_packed, 16) && aligned(out_nhwc, 16));
+  SIA_REQUIRE(c_stride >= 32 && c_stride % 8 == 0 && c_offset >= 0 && c_offset % 8 == 0 && c_offset + 32 <= c_stride);
   if (h % 2 != 0 || w % C1_TILE_X != 0) return SIA_E_UNSUPPORTED;
   if (int wrc = ensure_watchdog()) return wrc;
   CUtensorMap tmap;
@@ -342,7 +344,12 @@ extern "C" int sia_conv7x7_c3_relu_pool2(const void* in_nhwc4, int batch, int h,
   if (int rc2 = ensure_dynamic_smem(conv1_kernel, smem, &configured)) return rc2;
   const int grid = total < sm_count() ? total : sm_count();
   conv1_kernel<<<grid, C1_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
-      tmap, static_cast<const uint8_t*>(w_packed), bias, static_cast<__nv_bfloat16*>(out_nhwc), h, w, tiles_y,
-      tiles_x, total);
+      tmap, static_cast<const uint8_t*>(w_packed), bias, static_cast<__nv_bfloat16*>(out_nhwc) + c_offset, h, w, tiles_y,
+      tiles_x, total, c_stride);
   return launch_status();
+}
+
+extern "C" int sia_conv7x7_c3_relu_pool2(const void* in_nhwc4, int batch, int h, int w, const void* w_packed,
+                                         const float* bias, void* out_nhwc, void* stream) {
+  return sia_conv7x7_c3_relu_pool2_strided(in_nhwc4, batch, h, w, w_packed, bias, out_nhwc, 32, 0, stream);
 }

@@ -330,39 +330,47 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
 
 
 // ------------------------------- streamed-weight variant --------------------------------------
-// Conv2d(128, 256, 3): 9 * 128 * 256 bf16 weights = 576 KB do not fit in shared memory, so they stream from L2
-// through a ring of (tap, 64-channel chunk) blocks of 32 KB while TWO tiles stay resident: both halo buffers in
-// shared memory, both 128 x 256 fp32 accumulators in TMEM (all 512 columns).  Every weight block is used by both
+// Any 64-channel-chunked input (cin_pad = 64 * nchunk, nchunk <= 4) and COUT in {64, 128, 192, 256}: the weights
+// (up to 9 * 256 * 256 bf16 = 1.1 MB) do not have to fit in shared memory, they stream from L2 through a ring of
+// (tap, 64-channel chunk) blocks of COUT x 128 bytes while TILES output tiles stay resident (halo buffers in
+// shared memory, 128 x COUT fp32 accumulators in TMEM).  With TILES = 2 every weight block is used by both
 // tiles, which halves the L2 traffic per FLOP.  Epilogue group t (four warps) drains accumulator t; the MMA warp
-// starts the next pair once both are drained.
+// starts the next pass once all are drained.  Used for Conv2d(128, 256) of SkinCancerModel and, with zero-padded
+// channels, for the arbitrary widths of tone_bias_optuna.define_isic_model.
 constexpr int CS_NB = 3;            // weight-block ring
+constexpr int CS_CHUNK_BYTES = CV_HALO_ROWS * 128;                         // one 64-channel halo chunk (23040)
+constexpr int CS_CHUNK_STRIDE = (CS_CHUNK_BYTES + 1023) / 1024 * 1024;
 
-template <int CIN, int COUT>
+template <int COUT, int TILES>
 __global__ void __launch_bounds__(CV_THREADS, 1)
 conv3x3_stream_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restrict__ w_packed,
                       const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int H, int W, int tiles_y,
-                      int tiles_x, int total_tiles) {
-  using C = ConvCfg<CIN, COUT>;
-  static_assert(2 * COUT <= 512, "two accumulators must fit TMEM");
-  constexpr int NBLK = 9 * C::NCHUNK;                  // weight blocks per tile pair
+                      int tiles_x, int total_tiles, int nchunk) {
+  static_assert(TILES * COUT <= 512, "the accumulators must fit TMEM");
+  static_assert(COUT % 64 == 0 && COUT <= 256 && (TILES == 1 || TILES == 2), "unsupported shape");
+  constexpr int B_BLOCK = COUT * 128;                  // one (tap, chunk) weight block
+  constexpr int BIAS_BYTES = COUT * 32;
+  constexpr uint32_t TMEM_COLS = TILES * COUT <= 64 ? 64 : TILES * COUT <= 128 ? 128 : TILES * COUT <= 256 ? 256 : 512;
+  const int nblk = 9 * nchunk;                         // weight blocks per pass
+  const int stage_stride = nchunk * CS_CHUNK_STRIDE;   // one halo buffer (all chunks)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* smem_b = smem;                               // CS_NB * B_TAP_BYTES
-  uint8_t* smem_a = smem + CS_NB * C::B_TAP_BYTES;      // 2 * STAGE_STRIDE
-  uint8_t* smem_ones = smem_a + 2 * C::STAGE_STRIDE;
+  uint8_t* smem_b = smem;                               // CS_NB * B_BLOCK
+  uint8_t* smem_a = smem + CS_NB * B_BLOCK;             // TILES * stage_stride
+  uint8_t* smem_ones = smem_a + TILES * stage_stride;
   uint8_t* smem_biasop = smem_ones + ONES_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_biasop + C::BIAS_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_biasop + BIAS_BYTES);
   uint64_t* b_full = bars;                 // [CS_NB]
   uint64_t* b_empty = bars + CS_NB;        // [CS_NB]
-  uint64_t* a_full = bars + 2 * CS_NB;     // both halos landed
-  uint64_t* a_empty = a_full + 1;          // MMAs of the pair have read them
+  uint64_t* a_full = bars + 2 * CS_NB;     // the halos of the pass landed
+  uint64_t* a_empty = a_full + 1;          // the MMAs of the pass have read them
   uint64_t* tfull_bar = a_full + 2;        // accumulators complete
   uint64_t* tempty_bar = a_full + 3;       // [2] drained by epilogue group t
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 5);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n_pairs = (total_tiles + 1) / 2;
+  const int n_pass = (total_tiles + TILES - 1) / TILES;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < CS_NB; ++i) {
@@ -377,7 +385,7 @@ conv3x3_stream_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t
     fence_mbar_init();
     tma_prefetch_desc(&tmap_in);
   }
-  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
   fill_ones_operand(smem_ones, threadIdx.x, blockDim.x);
   fill_bias_operand(smem_biasop, bias, COUT, COUT, threadIdx.x, blockDim.x);
   fence_proxy_async_smem();
@@ -392,29 +400,27 @@ conv3x3_stream_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t
     if (lane == 0) {
       int bs = 0;
       uint32_t bphase = 0, pphase = 0;
-      for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      for (int pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
         mbar_wait(a_empty, pphase ^ 1, 25);
-        const int n_tiles = (2 * pair + 1 < total_tiles) ? 2 : 1;
-        mbar_arrive_expect_tx(a_full, n_tiles * C::STAGE_TX_BYTES);
+        const int n_tiles = (TILES * pass + TILES <= total_tiles) ? TILES : total_tiles - TILES * pass;
+        mbar_arrive_expect_tx(a_full, n_tiles * nchunk * CS_CHUNK_BYTES);
         for (int t = 0; t < n_tiles; ++t) {
-          const int tile = 2 * pair + t;
+          const int tile = TILES * pass + t;
           const int n = tile / tiles_per_img, rem = tile % tiles_per_img;
           const int ty = rem / tiles_x, tx = rem % tiles_x;
-#pragma unroll
-          for (int kc = 0; kc < C::NCHUNK; ++kc) {
-            tma_load_4d(smem_a + t * C::STAGE_STRIDE + kc * C::CHUNK_STRIDE, &tmap_in, a_full, kc * C::CK,
+          for (int kc = 0; kc < nchunk; ++kc) {
+            tma_load_4d(smem_a + t * stage_stride + kc * CS_CHUNK_STRIDE, &tmap_in, a_full, kc * 64,
                         tx * CV_TILE_X - 1, ty * CV_TILE_Y - 1, n);
           }
         }
         pphase ^= 1;
-        for (int blk = 0; blk < NBLK; ++blk) {
+        for (int blk = 0; blk < nblk; ++blk) {
           mbar_wait(&b_empty[bs], bphase ^ 1, 26);
-          mbar_arrive_expect_tx(&b_full[bs], C::B_TAP_BYTES);
-          constexpr int PIECE = 16384;
+          mbar_arrive_expect_tx(&b_full[bs], B_BLOCK);
+          constexpr int PIECE = 8192;
 #pragma unroll
-          for (int off = 0; off < C::B_TAP_BYTES; off += PIECE) {
-            bulk_load_1d(smem_b + bs * C::B_TAP_BYTES + off, w_packed + (size_t)blk * C::B_TAP_BYTES + off, PIECE,
-                         &b_full[bs]);
+          for (int off = 0; off < B_BLOCK; off += PIECE) {
+            bulk_load_1d(smem_b + bs * B_BLOCK + off, w_packed + (size_t)blk * B_BLOCK + off, PIECE, &b_full[bs]);
           }
           if (++bs == CS_NB) { bs = 0; bphase ^= 1; }
         }
@@ -423,8 +429,8 @@ conv3x3_stream_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t
   } else if (warp == 1) {
     // ================================ MMA issuer ============================================
     constexpr uint32_t idesc = make_idesc_bf16(128, COUT);
-    constexpr uint32_t a_hi = desc_hi(C::GROUP_STRIDE, C::SWZ);
-    constexpr uint32_t b_hi = desc_hi(8 * C::ROWB, C::SWZ);
+    constexpr uint32_t a_hi = desc_hi(CV_HALO_X * 128, SW_128B);
+    constexpr uint32_t b_hi = desc_hi(8 * 128, SW_128B);
     constexpr uint32_t c_hi = desc_hi(256, SW_NONE);
     const uint32_t a_lo0 = desc_lo(smem_u32(smem_a), 0);
     const uint32_t b_lo0 = desc_lo(smem_u32(smem_b), 0);
@@ -432,8 +438,8 @@ conv3x3_stream_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t
     const uint32_t bias_lo = desc_lo(smem_u32(smem_biasop), 128);
     int bs = 0;
     uint32_t bphase = 0, pphase = 0;
-    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-      const int n_tiles = (2 * pair + 1 < total_tiles) ? 2 : 1;
+    for (int pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
+      const int n_tiles = (TILES * pass + TILES <= total_tiles) ? TILES : total_tiles - TILES * pass;
       mbar_wait(&tempty_bar[0], pphase ^ 1, 27);
       mbar_wait(&tempty_bar[1], pphase ^ 1, 27);
       mbar_wait(a_full, pphase, 28);
@@ -443,35 +449,35 @@ conv3x3_stream_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t
           umma_bf16_ss_w(tmem_base + t * COUT, ones_lo, c_hi, bias_lo, c_hi, idesc, 0u);     // D = bias
       }
       __syncwarp();
-      for (int blk = 0; blk < NBLK; ++blk) {
-        // block order of the packed weights: (tap, chunk) with the chunk fastest
-        const int tap = blk / C::NCHUNK, kc = blk % C::NCHUNK;
+      int tap = 0, kc = 0;                 // block order of the packed weights: (tap, chunk), chunk fastest
+      for (int blk = 0; blk < nblk; ++blk) {
         const int r = tap / 3, s = tap % 3;
         mbar_wait(&b_full[bs], bphase, 29);
         tc_fence_after_sync();
         if (elect_one()) {
-          const uint32_t b_lo = b_lo0 + bs * (C::B_TAP_BYTES >> 4);
+          const uint32_t b_lo = b_lo0 + bs * (B_BLOCK >> 4);
           for (int t = 0; t < n_tiles; ++t) {
-            const uint32_t a_lo = a_lo0 + ((t * C::STAGE_STRIDE + kc * C::CHUNK_STRIDE + (r * CV_HALO_X + s) * C::ROWB) >> 4);
+            const uint32_t a_lo = a_lo0 + ((t * stage_stride + kc * CS_CHUNK_STRIDE + (r * CV_HALO_X + s) * 128) >> 4);
 #pragma unroll
-            for (int kk = 0; kk < C::CK / 16; ++kk) {
+            for (int kk = 0; kk < 4; ++kk) {
               umma_bf16_ss_w(tmem_base + t * COUT, a_lo + kk * 2, a_hi, b_lo + kk * 2, b_hi, idesc, 1u);
             }
           }
           umma_commit(&b_empty[bs]);
-          if (blk == NBLK - 1) {
+          if (blk == nblk - 1) {
             umma_commit(a_empty);
             umma_commit(tfull_bar);
           }
         }
         __syncwarp();
         if (++bs == CS_NB) { bs = 0; bphase ^= 1; }
+        if (++kc == nchunk) { kc = 0; ++tap; }
       }
       pphase ^= 1;
     }
   } else if (warp >= 4) {
     // ================================ epilogue ==============================================
-    const int group = (warp - 4) >> 2;        // tile of the pair
+    const int group = (warp - 4) >> 2;        // tile of the pass
     const int e = (warp - 4) & 3;             // TMEM lanes 32e .. 32e+31
     const int Ho = H >> 1, Wo = W >> 1;
     const int ly = lane >> 3;
@@ -479,9 +485,9 @@ conv3x3_stream_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t
     const bool odd_x = lane & 1;
     const bool odd_y = (lane >> 3) & 1;
     uint32_t pphase = 0;
-    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-      const int tile = 2 * pair + group;
-      const bool have = tile < total_tiles;
+    for (int pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
+      const int tile = TILES * pass + group;
+      const bool have = group < TILES && tile < total_tiles;
       const int n = tile / tiles_per_img, rem = tile % tiles_per_img;
       const int ty = rem / tiles_x, tx = rem % tiles_x;
       const int py = ((ty * CV_TILE_Y + 4 * e + ly) >> 1);
@@ -491,7 +497,7 @@ conv3x3_stream_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t
       mbar_wait(tfull_bar, pphase, 24);
       pphase ^= 1;
       tc_fence_after_sync();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(32 * e) << 16) + group * COUT;
+      const uint32_t t_addr = tmem_base + ((uint32_t)(32 * e) << 16) + (group < TILES ? group : 0) * COUT;
 
       auto finish_chunk = [&](const uint32_t (&v)[32], int cb) {
         uint32_t pk[16];
@@ -538,7 +544,7 @@ conv3x3_stream_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 2) tmem_free(tmem_base, 512);
+  if (warp == 2) tmem_free(tmem_base, TMEM_COLS);
 }
 
 // ------------------------------- pixel-pair variant (cin = 32) --------------------------------
@@ -728,14 +734,15 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* 
 
 // [64][32][3][3] fp32 -> B[n = dx*64 + co][k = r*128 + xw*32 + c] = W[co][c][r][xw - dx] (0 outside 0..2), bf16, as six
 // 128-row x 128-byte blocks (64 k each) with the 16-byte units of every row XOR-swizzled by the row index.
-__global__ void pack_conv3x3_pair_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst) {
+__global__ void pack_conv3x3_pair_kernel(const float* __restrict__ w, int cin, int cout,
+                                         __nv_bfloat16* __restrict__ dst) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < CP_N * CP_K; i += gridDim.x * blockDim.x) {
     const int n = i / CP_K, k = i % CP_K;
     const int dx = n / 64, co = n % 64;
     const int r = k / 128, xw = (k % 128) / 32, c = k % 32;
     const int s = xw - dx;
     float v = 0.f;
-    if (s >= 0 && s < 3) v = w[((co * 32 + c) * 3 + r) * 3 + s];
+    if (s >= 0 && s < 3 && co < cout && c < cin) v = w[((co * cin + c) * 3 + r) * 3 + s];
     const int chunk = k / 64, kq = k % 64;
     const int unit = (kq / 8) ^ (n & 7);
     dst[(size_t)chunk * (CP_B_CHUNK / 2) + n * 64 + unit * 8 + (kq & 7)] = __float2bfloat16_rn(v);
@@ -769,21 +776,23 @@ static int launch_conv3x3_pair(const void* in, int batch, int h, int w, const vo
 // [cout][cin][3][3] fp32 -> for tap (r,s), chunk kc: [cout rows][CK channels] bf16, K-major, with the
 // 16-byte units of each row XOR-swizzled by the row index exactly as TMA / UMMA swizzle modes do
 // (128B rows: unit ^= row%8 ; 64B rows: unit ^= (row/2)%4).
-__global__ void pack_conv3x3_kernel(const float* __restrict__ w, int cin, int cout, __nv_bfloat16* __restrict__ dst) {
-  const int ck = cin < 64 ? cin : 64;
-  const int nchunk = cin / ck;
-  const int total = 9 * cin * cout;
+// cin_pad / cout_pad: channel counts of the (zero-padded) activation buffers; weights outside [cout][cin] are zero.
+__global__ void pack_conv3x3_kernel(const float* __restrict__ w, int cin, int cout, int cin_pad, int cout_pad,
+                                    __nv_bfloat16* __restrict__ dst) {
+  const int ck = cin_pad < 64 ? cin_pad : 64;
+  const int nchunk = cin_pad / ck;
+  const int total = 9 * cin_pad * cout_pad;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int c_in_chunk = i % ck;
-    const int row = (i / ck) % cout;
-    const int kc = (i / (ck * cout)) % nchunk;
-    const int tap = i / (ck * cout * nchunk);
+    const int row = (i / ck) % cout_pad;
+    const int kc = (i / (ck * cout_pad)) % nchunk;
+    const int tap = i / (ck * cout_pad * nchunk);
     const int r = tap / 3, s = tap % 3;
     const int c = kc * ck + c_in_chunk;
-    const float v = w[(((size_t)row * cin + c) * 3 + r) * 3 + s];
+    const float v = (row < cout && c < cin) ? w[(((size_t)row * cin + c) * 3 + r) * 3 + s] : 0.f;
     const int unit = c_in_chunk / 8;
     const int swz = ck == 64 ? (unit ^ (row & 7)) : (unit ^ ((row >> 1) & 3));
-    const size_t block = ((size_t)tap * nchunk + kc) * cout * ck;
+    const size_t block = ((size_t)tap * nchunk + kc) * cout_pad * ck;
     dst[block + (size_t)row * ck + swz * 8 + (c_in_chunk & 7)] = __float2bfloat16_rn(v);
   }
 }
@@ -815,29 +824,54 @@ static int launch_conv3x3(const void* in, int batch, int h, int w, const void* w
 }
 
 
-template <int CIN, int COUT>
-static int launch_conv3x3_stream(const void* in, int batch, int h, int w, const void* w_packed, const float* bias,
-                                 void* out, cudaStream_t st) {
-  using C = ConvCfg<CIN, COUT>;
-  if (int wrc = ensure_watchdog()) return wrc;
-  CUtensorMap tmap;
-  const uint64_t dims[4] = {(uint64_t)CIN, (uint64_t)w, (uint64_t)h, (uint64_t)batch};
-  const uint64_t strides[3] = {(uint64_t)CIN * 2, (uint64_t)w * CIN * 2, (uint64_t)h * w * CIN * 2};
-  const uint32_t box[4] = {(uint32_t)C::CK, CV_HALO_X, CV_HALO_Y, 1};
-  int rc = encode_tmap_bf16(&tmap, in, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
-  if (rc != 0) return rc;
+template <int COUT, int TILES>
+static int launch_conv3x3_stream_t(const CUtensorMap& tmap, int nchunk, int batch, int h, int w, const void* w_packed,
+                                   const float* bias, void* out, cudaStream_t st) {
   const int tiles_y = (h + CV_TILE_Y - 1) / CV_TILE_Y;
   const int tiles_x = (w + CV_TILE_X - 1) / CV_TILE_X;
   const int total = tiles_y * tiles_x * batch;
-  const int pairs = (total + 1) / 2;
-  const int smem = 1024 + CS_NB * C::B_TAP_BYTES + 2 * C::STAGE_STRIDE + ONES_BYTES + C::BIAS_BYTES + (2 * CS_NB + 6) * 8;
-  auto kern = conv3x3_stream_kernel<CIN, COUT>;
+  const int passes = (total + TILES - 1) / TILES;
+  const int smem = 1024 + CS_NB * COUT * 128 + TILES * nchunk * CS_CHUNK_STRIDE + ONES_BYTES + COUT * 32 +
+                   (2 * CS_NB + 6) * 8;
+  auto kern = conv3x3_stream_kernel<COUT, TILES>;
   static int configured = 0;
   if (int rc2 = ensure_dynamic_smem(kern, smem, &configured)) return rc2;
-  const int grid = pairs < sm_count() ? pairs : sm_count();
+  const int grid = passes < sm_count() ? passes : sm_count();
   kern<<<grid, CV_THREADS, smem, st>>>(tmap, static_cast<const uint8_t*>(w_packed), bias,
-                                       static_cast<__nv_bfloat16*>(out), h, w, tiles_y, tiles_x, total);
+                                       static_cast<__nv_bfloat16*>(out), h, w, tiles_y, tiles_x, total, nchunk);
   return launch_status();
+}
+
+// cin_pad: channels of the NHWC input buffer (multiple of 64, <= 256); cout_pad in {64, 128, 192, 256}
+static int launch_conv3x3_stream(const void* in, int batch, int h, int w, int cin_pad, int cout_pad,
+                                 const void* w_packed, const float* bias, void* out, cudaStream_t st) {
+  if (cin_pad % 64 != 0 || cin_pad < 64 || cin_pad > 256 || cout_pad % 64 != 0 || cout_pad < 64 || cout_pad > 256)
+    return SIA_E_UNSUPPORTED;
+  if (int wrc = ensure_watchdog()) return wrc;
+  const int nchunk = cin_pad / 64;
+  CUtensorMap tmap;
+  const uint64_t dims[4] = {(uint64_t)cin_pad, (uint64_t)w, (uint64_t)h, (uint64_t)batch};
+  const uint64_t strides[3] = {(uint64_t)cin_pad * 2, (uint64_t)w * cin_pad * 2, (uint64_t)h * w * cin_pad * 2};
+  const uint32_t box[4] = {64, CV_HALO_X, CV_HALO_Y, 1};
+  int rc = encode_tmap_bf16(&tmap, in, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc != 0) return rc;
+  // two resident tiles whenever both halo sets and the weight ring fit in 227 KB of shared memory
+  const bool two = 1024 + CS_NB * cout_pad * 128 + 2 * nchunk * CS_CHUNK_STRIDE + ONES_BYTES + cout_pad * 32 + 128 <=
+                   227 * 1024;
+  switch (cout_pad) {
+    case 64:
+      return two ? launch_conv3x3_stream_t<64, 2>(tmap, nchunk, batch, h, w, w_packed, bias, out, st)
+                 : launch_conv3x3_stream_t<64, 1>(tmap, nchunk, batch, h, w, w_packed, bias, out, st);
+    case 128:
+      return two ? launch_conv3x3_stream_t<128, 2>(tmap, nchunk, batch, h, w, w_packed, bias, out, st)
+                 : launch_conv3x3_stream_t<128, 1>(tmap, nchunk, batch, h, w, w_packed, bias, out, st);
+    case 192:
+      return two ? launch_conv3x3_stream_t<192, 2>(tmap, nchunk, batch, h, w, w_packed, bias, out, st)
+                 : launch_conv3x3_stream_t<192, 1>(tmap, nchunk, batch, h, w, w_packed, bias, out, st);
+    default:
+      return two ? launch_conv3x3_stream_t<256, 2>(tmap, nchunk, batch, h, w, w_packed, bias, out, st)
+                 : launch_conv3x3_stream_t<256, 1>(tmap, nchunk, batch, h, w, w_packed, bias, out, st);
+  }
 }
 
 }  // namespace sia
@@ -857,19 +891,24 @@ extern "C" size_t sia_pack_conv3x3_bytes(int cin, int cout) {
   return use_pair_variant(cin, cout) ? (size_t)sia::CP_B_BYTES : (size_t)9 * cin * cout * 2;
 }
 
-extern "C" int sia_pack_conv3x3(const float* w_oihw, int cin, int cout, void* packed, void* stream) {
+extern "C" int sia_pack_conv3x3_padded(const float* w_oihw, int cin, int cout, int cin_pad, int cout_pad, void* packed,
+                                       void* stream) {
   using namespace sia;
-  SIA_REQUIRE(w_oihw && packed && cin >= 32 && cout >= 8);
-  if (!((cin == 32) || (cin % 64 == 0))) return SIA_E_UNSUPPORTED;
-  if (use_pair_variant(cin, cout)) {
+  SIA_REQUIRE(w_oihw && packed && cin >= 1 && cout >= 1 && cin_pad >= cin && cout_pad >= cout);
+  if (!((cin_pad == 32) || (cin_pad % 64 == 0)) || cout_pad % 8 != 0) return SIA_E_UNSUPPORTED;
+  if (use_pair_variant(cin_pad, cout_pad)) {
     pack_conv3x3_pair_kernel<<<(CP_N * CP_K + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        w_oihw, static_cast<__nv_bfloat16*>(packed));
+        w_oihw, cin, cout, static_cast<__nv_bfloat16*>(packed));
     return launch_status();
   }
-  const int total = 9 * cin * cout;
+  const int total = 9 * cin_pad * cout_pad;
   pack_conv3x3_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      w_oihw, cin, cout, static_cast<__nv_bfloat16*>(packed));
+      w_oihw, cin, cout, cin_pad, cout_pad, static_cast<__nv_bfloat16*>(packed));
   return launch_status();
+}
+
+extern "C" int sia_pack_conv3x3(const float* w_oihw, int cin, int cout, void* packed, void* stream) {
+  return sia_pack_conv3x3_padded(w_oihw, cin, cout, cin, cout, packed, stream);
 }
 
 extern "C" int sia_conv3x3_relu_pool2(const void* in_nhwc, int batch, int h, int w, int cin, int cout,
@@ -882,6 +921,6 @@ extern "C" int sia_conv3x3_relu_pool2(const void* in_nhwc, int batch, int h, int
   if (use_pair_variant(cin, cout)) return launch_conv3x3_pair(in_nhwc, batch, h, w, w_packed, bias, out_nhwc, st);
   if (cin == 32 && cout == 64) return launch_conv3x3<32, 64, 6>(in_nhwc, batch, h, w, w_packed, bias, out_nhwc, st);
   if (cin == 64 && cout == 128) return launch_conv3x3<64, 128, 3>(in_nhwc, batch, h, w, w_packed, bias, out_nhwc, st);
-  if (cin == 128 && cout == 256) return launch_conv3x3_stream<128, 256>(in_nhwc, batch, h, w, w_packed, bias, out_nhwc, st);
-  return SIA_E_UNSUPPORTED;
+  // everything else with 64-channel-chunked buffers: the streamed-weight kernel (cin, cout = buffer widths)
+  return launch_conv3x3_stream(in_nhwc, batch, h, w, cin, cout, w_packed, bias, out_nhwc, st);
 }

@@ -256,6 +256,32 @@ __global__ void pack_linear_kernel(const float* __restrict__ w, int n, int c, in
 
 }  // namespace sia
 
+namespace sia {
+// fc1 weight [n][c*hw] -> bf16 [n_pad][hw*c_pad] (column = p*c_pad + ch), zero outside [n][c]: the activations are
+// NHWC with c_pad (zero-padded) channels and the split-K GEMM wants n_pad % 128 == 0
+__global__ void pack_linear_padded_kernel(const float* __restrict__ w, int n, int c, int hw, int n_pad, int c_pad,
+                                          __nv_bfloat16* __restrict__ dst) {
+  const size_t total = (size_t)n_pad * c_pad * hw;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % c_pad);
+    const size_t rest = i / c_pad;
+    const int p = (int)(rest % hw);
+    const size_t row = rest / hw;
+    const float v = (row < (size_t)n && ch < c) ? w[(row * c + ch) * hw + p] : 0.f;
+    dst[i] = __float2bfloat16_rn(v);
+  }
+}
+}  // namespace sia
+
+extern "C" int sia_pack_linear_chw_to_hwc_padded(const float* w, int n, int c, int hw, int n_pad, int c_pad,
+                                                 void* packed_bf16, void* stream) {
+  using namespace sia;
+  SIA_REQUIRE(w && packed_bf16 && n >= 1 && c >= 1 && hw >= 1 && n_pad >= n && c_pad >= c);
+  pack_linear_padded_kernel<<<sm_count() * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, n, c, hw, n_pad, c_pad, static_cast<__nv_bfloat16*>(packed_bf16));
+  return launch_status();
+}
+
 extern "C" int sia_pack_linear_chw_to_hwc(const float* w, int n, int c, int hw, void* packed_bf16, void* stream) {
   using namespace sia;
   SIA_REQUIRE(w && packed_bf16 && n >= 1 && c >= 1 && hw >= 1);
@@ -307,6 +333,108 @@ extern "C" int sia_head_tail(const float* partial, int splits, int m, int n1, in
   }
   head_tail_kernel<<<(m + TAIL_IMGS - 1) / TAIL_IMGS, TAIL_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
       partial, splits, m, n1, n2, b1, w2t, b2, w3, b3, logp, pred, label, groups, groups_stride, n_attr, n_groups,
+      reinterpret_cast<unsigned long long*>(counts));
+  return launch_status();
+}
+
+// ------------------------------------- tail, any depth -----------------------------------------
+// tone_bias_optuna.define_isic_model (:123-173) builds 2-5 hidden Linear layers of 16-256 units: the same tail as
+// head_tail_kernel for a chain  h1 = relu(sum_s partial + b1);  h_{l+1} = relu(W_l h_l + b_l) ...;  z = W_L h_L + b_L
+// (2 classes); log-softmax; argmax; optional confusion counts.  fp32 throughout; four images per CTA.
+namespace sia {
+constexpr int CHAIN_MAX_LAYERS = 6;
+struct ChainParams {
+  const float* wt[CHAIN_MAX_LAYERS];   // [n_in][n_out] (transposed Linear weights)
+  const float* b[CHAIN_MAX_LAYERS];
+  int n_in[CHAIN_MAX_LAYERS], n_out[CHAIN_MAX_LAYERS];
+  int n_layers;                        // layers after fc1; the last one has n_out == 2
+};
+
+__global__ void __launch_bounds__(256)
+tail_chain_kernel(const float* __restrict__ partial, int splits, int M, int n1, int n1_stride,
+                  const float* __restrict__ b1, const __grid_constant__ ChainParams cp, float* __restrict__ logp,
+                  uint8_t* __restrict__ pred, const uint8_t* __restrict__ label, const uint8_t* __restrict__ groups,
+                  int groups_stride, int n_attr, int n_groups, unsigned long long* __restrict__ counts) {
+  __shared__ float h[2][TAIL_IMGS][TAIL_MAX_N1];
+  const int m0 = blockIdx.x * TAIL_IMGS;
+  for (int i = threadIdx.x; i < TAIL_IMGS * n1; i += blockDim.x) {
+    const int img = i / n1, k = i % n1;
+    float s = 0.f;
+    if (m0 + img < M) {
+      const float* src = partial + (size_t)(m0 + img) * n1_stride + k;
+      const size_t step = (size_t)M * n1_stride;
+      for (int sp = 0; sp < splits; ++sp) s += __ldg(src + (size_t)sp * step);      // split order: deterministic
+      s = fmaxf(s + b1[k], 0.f);
+    }
+    h[0][img][k] = s;
+  }
+  __syncthreads();
+  int cur = 0;
+  for (int l = 0; l < cp.n_layers; ++l) {
+    const int n_in = cp.n_in[l], n_out = cp.n_out[l];
+    const bool last = l == cp.n_layers - 1;
+    for (int j = threadIdx.x; j < n_out; j += blockDim.x) {
+      float a[TAIL_IMGS];
+#pragma unroll
+      for (int img = 0; img < TAIL_IMGS; ++img) a[img] = 0.f;
+      for (int k = 0; k < n_in; ++k) {
+        const float w = __ldg(cp.wt[l] + (size_t)k * n_out + j);
+#pragma unroll
+        for (int img = 0; img < TAIL_IMGS; ++img) a[img] = fmaf(w, h[cur][img][k], a[img]);
+      }
+      const float bj = cp.b[l][j];
+#pragma unroll
+      for (int img = 0; img < TAIL_IMGS; ++img) h[cur ^ 1][img][j] = last ? a[img] + bj : fmaxf(a[img] + bj, 0.f);
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+  if (threadIdx.x < TAIL_IMGS && m0 + threadIdx.x < M) {
+    const int img = threadIdx.x, m = m0 + img;
+    const float z0 = h[cur][img][0], z1 = h[cur][img][1];
+    const float mx = fmaxf(z0, z1);
+    const float lse = mx + logf(expf(z0 - mx) + expf(z1 - mx));
+    logp[2 * m] = z0 - lse;
+    logp[2 * m + 1] = z1 - lse;
+    const int pr = (z1 > z0) ? 1 : 0;   // torch.max: first maximal index on ties
+    pred[m] = (uint8_t)pr;
+    if (counts != nullptr) {
+      const int cell = ((label[m] != 0) ? 2 : 0) | pr;
+      for (int a = 0; a < n_attr; ++a) {
+        const int g = groups[(size_t)a * groups_stride + m];
+        if (g < n_groups) atomicAdd(&counts[(a * n_groups + g) * 4 + cell], 1ull);
+      }
+    }
+  }
+}
+}  // namespace sia
+
+extern "C" int sia_head_tail_chain(const float* partial, int splits, int m, int n1, int n1_stride, const float* b1,
+                                   int n_layers, const float* const* wt_host, const float* const* b_host,
+                                   const int* n_out_host, float* logp, uint8_t* pred, const uint8_t* label,
+                                   const uint8_t* groups, int groups_stride, int n_attr, int n_groups,
+                                   long long* counts, void* stream) {
+  using namespace sia;
+  SIA_REQUIRE(partial && b1 && wt_host && b_host && n_out_host && logp && pred && splits >= 1 && m >= 1);
+  if (n1 < 1 || n1 > TAIL_MAX_N1 || n1_stride < n1 || n_layers < 1 || n_layers > CHAIN_MAX_LAYERS) return SIA_E_UNSUPPORTED;
+  if (counts != nullptr) {
+    SIA_REQUIRE(label && groups && n_attr >= 1 && n_groups >= 1 && groups_stride >= m);
+  }
+  ChainParams cp;
+  int n_in = n1;
+  for (int l = 0; l < n_layers; ++l) {
+    SIA_REQUIRE(wt_host[l] && b_host[l]);
+    if (n_out_host[l] < 1 || n_out_host[l] > TAIL_MAX_N1) return SIA_E_UNSUPPORTED;
+    cp.wt[l] = wt_host[l];
+    cp.b[l] = b_host[l];
+    cp.n_in[l] = n_in;
+    cp.n_out[l] = n_out_host[l];
+    n_in = n_out_host[l];
+  }
+  if (n_in != 2) return SIA_E_UNSUPPORTED;            // the fused tail handles exactly two classes
+  cp.n_layers = n_layers;
+  tail_chain_kernel<<<(m + TAIL_IMGS - 1) / TAIL_IMGS, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      partial, splits, m, n1, n1_stride, b1, cp, logp, pred, label, groups, groups_stride, n_attr, n_groups,
       reinterpret_cast<unsigned long long*>(counts));
   return launch_status();
 }

@@ -57,3 +57,29 @@ def max_over_ranks(value: float, device=None) -> float:
     t = torch.tensor([value], dtype=torch.float64, device=device or ("cuda" if dist.get_backend() == "nccl" else "cpu"))
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def bind_to_gpu_numa_node(local_rank: int) -> dict:
+    """Pins this process (and therefore the pinned host buffers it allocates afterwards, by first touch) to the
+    CPUs of the NUMA node the GPU hangs off, so that host->device copies of N ranks do not cross sockets.
+    Best effort: returns {"numa_node": n or None, "cpus": count}; never raises."""
+    info = {"numa_node": None, "cpus": 0}
+    try:
+        props = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return info
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info = {"numa_node": node, "cpus": len(allowed)}
+    except Exception:
+        pass
+    return info

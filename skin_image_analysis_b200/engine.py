@@ -23,7 +23,6 @@ from .tone_bias_model import CnnPlan
 
 N_ATTR = 3        # Fitzpatrick type, sex, control   
 N_GROUPS = 6
-KERNELS_PER_BATCH = 6
 
 
 def plan_from_state_dict(state: dict, device) -> CnnPlan:
@@ -67,7 +66,8 @@ class EvalEngine:
             self.slot_ready = [torch.cuda.Event() for _ in range(n_slots)]     # H2D into the slot finished
             self.slot_free = [torch.cuda.Event() for _ in range(n_slots)]      # kernels reading the slot finished
             self.graphs = [None] * n_slots
-            self.launches_per_batch = KERNELS_PER_BATCH - 3 + len(self.plan.convs)
+            # preprocess + first block (one launch per 32 output channels) + 3x3 blocks + fc1 + tail
+            self.launches_per_batch = 1 + len(self.plan.convs[0][0]) + (len(self.plan.convs) - 1) + 2
             if use_graph:
                 self._capture()
 

@@ -18,7 +18,7 @@ from ._lib import (LAYOUT_NCHW_BF16, LAYOUT_NCHW_F32, LAYOUT_NHWC4_BF16, NHWC4_P
 
 __all__ = [
     "preprocess_u8hwc", "nchw_f32_to_nhwc4", "pack_conv7x7_c3", "pack_conv3x3", "pack_linear_chw_to_hwc",
-    "conv7x7_c3_relu_pool2", "conv3x3_relu_pool2", "linear_splitk", "head_tail", "confusion_counts",
+    "conv7x7_c3_relu_pool2", "conv3x3_relu_pool2", "linear_splitk", "head_tail", "head_tail_chain", "confusion_counts",
     "umma_probe", "tma_probe", "LAYOUT_NCHW_F32", "LAYOUT_NCHW_BF16", "LAYOUT_NHWC4_BF16", "NHWC4_PAD",
 ]
 
@@ -150,24 +150,31 @@ def pack_conv7x7_c3(w: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def pack_conv3x3(w: torch.Tensor) -> torch.Tensor:
+def pack_conv3x3(w: torch.Tensor, cin_pad: int | None = None, cout_pad: int | None = None) -> torch.Tensor:
+    """[cout,cin,3,3] fp32 -> the packed bf16 operand for buffers of cin_pad x cout_pad channels (zero padded)."""
     _need(w, torch.float32, "w")
     cout, cin, kh, kw = w.shape
     if (kh, kw) != (3, 3):
         raise ValueError("expected a 3x3 kernel")
+    cin_pad, cout_pad = cin_pad or cin, cout_pad or cout
     lib = _lib.load()
-    out = torch.empty(lib.sia_pack_conv3x3_bytes(cin, cout), dtype=torch.uint8, device=w.device)
-    check(lib.sia_pack_conv3x3(ptr(w), cin, cout, ptr(out), stream_ptr()), "sia_pack_conv3x3")
+    out = torch.empty(lib.sia_pack_conv3x3_bytes(cin_pad, cout_pad), dtype=torch.uint8, device=w.device)
+    check(lib.sia_pack_conv3x3_padded(ptr(w), cin, cout, cin_pad, cout_pad, ptr(out), stream_ptr()),
+          "sia_pack_conv3x3_padded")
     return out
 
 
-def pack_linear_chw_to_hwc(w: torch.Tensor, c: int, hw: int) -> torch.Tensor:
+def pack_linear_chw_to_hwc(w: torch.Tensor, c: int, hw: int, n_pad: int | None = None,
+                           c_pad: int | None = None) -> torch.Tensor:
+    """[n, c*hw] fp32 (CHW-flattened columns) -> bf16 [n_pad, hw*c_pad] (HWC-flattened, zero padded)."""
     _need(w, torch.float32, "w")
     n, k = w.shape
     if k != c * hw:
         raise ValueError("in_features != c*hw")
-    out = torch.empty((n, k), dtype=torch.bfloat16, device=w.device)
-    check(_lib.load().sia_pack_linear_chw_to_hwc(ptr(w), n, c, hw, ptr(out), stream_ptr()), "sia_pack_linear_chw_to_hwc")
+    n_pad, c_pad = n_pad or n, c_pad or c
+    out = torch.empty((n_pad, hw * c_pad), dtype=torch.bfloat16, device=w.device)
+    check(_lib.load().sia_pack_linear_chw_to_hwc_padded(ptr(w), n, c, hw, n_pad, c_pad, ptr(out), stream_ptr()),
+          "sia_pack_linear_chw_to_hwc_padded")
     return out
 
 
@@ -175,7 +182,8 @@ def pack_linear_chw_to_hwc(w: torch.Tensor, c: int, hw: int) -> torch.Tensor:
 # K4 conv blocks
 # -------------------------------------------------------------------------------------------------
 def conv7x7_c3_relu_pool2(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor,
-                          out: torch.Tensor | None = None) -> torch.Tensor:
+                          out: torch.Tensor | None = None, c_offset: int = 0) -> torch.Tensor:
+    """One 32-output-channel slice of the first block, written at channel ``c_offset`` of ``out`` [B,H/2,W/2,C]."""
     _need(x, torch.bfloat16, "x")
     _need(w_packed, torch.uint8, "w_packed")
     _need(bias, torch.float32, "bias")
@@ -185,8 +193,9 @@ def conv7x7_c3_relu_pool2(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.T
         raise ValueError("expected padded NHWC4 input [B,H,W+8,4]")
     if out is None:
         out = torch.empty((b, h // 2, w // 2, 32), dtype=torch.bfloat16, device=x.device)
-    check(_lib.load().sia_conv7x7_c3_relu_pool2(ptr(x), b, h, w, ptr(w_packed), ptr(bias), ptr(out), stream_ptr()),
-          "sia_conv7x7_c3_relu_pool2")
+    check(_lib.load().sia_conv7x7_c3_relu_pool2_strided(ptr(x), b, h, w, ptr(w_packed), ptr(bias), ptr(out),
+                                                        out.shape[3], int(c_offset), stream_ptr()),
+          "sia_conv7x7_c3_relu_pool2_strided")
     return out
 
 
@@ -242,6 +251,36 @@ def head_tail(partial, b1, w2t, b2, w3, b3, label=None, groups=None, n_groups: i
     check(_lib.load().sia_head_tail(ptr(partial), splits, m, n1, n2, ptr(b1), ptr(w2t), ptr(b2), ptr(w3), ptr(b3),
                                     ptr(logp), ptr(pred), ptr(label), ptr(groups), stride, n_attr, n_groups,
                                     ptr(counts), stream_ptr()), "sia_head_tail")
+    return logp, pred
+
+
+def head_tail_chain(partial, n1: int, b1, layers, label=None, groups=None, n_groups: int = 0, counts=None,
+                    logp=None, pred=None):
+    """Tail for any number of Linear layers after fc1: ``layers`` = [(w_t [n_in, n_out] f32, b [n_out] f32), ...],
+    ReLU after all but the last (2 classes).  ``partial`` is [splits, M, n1_stride] with n1 <= n1_stride."""
+    _need(partial, torch.float32, "partial")
+    splits, m, n1_stride = partial.shape
+    _need(b1, torch.float32, "b1")
+    for wt, b in layers:
+        _need(wt, torch.float32, "w_t")
+        _need(b, torch.float32, "b")
+    if logp is None:
+        logp = torch.empty((m, 2), dtype=torch.float32, device=partial.device)
+    if pred is None:
+        pred = torch.empty((m,), dtype=torch.uint8, device=partial.device)
+    n_attr, stride = 0, 0
+    if counts is not None:
+        _need(counts, torch.int64, "counts")
+        _need(label, torch.uint8, "label")
+        _need(groups, torch.uint8, "groups")
+        n_attr, stride = groups.shape
+    k = len(layers)
+    wt_arr = (ctypes.c_void_p * k)(*[wt.data_ptr() for wt, _ in layers])
+    b_arr = (ctypes.c_void_p * k)(*[b.data_ptr() for _, b in layers])
+    n_arr = (ctypes.c_int * k)(*[int(wt.shape[1]) for wt, _ in layers])
+    check(_lib.load().sia_head_tail_chain(ptr(partial), splits, m, int(n1), n1_stride, ptr(b1), k, wt_arr, b_arr, n_arr,
+                                          ptr(logp), ptr(pred), ptr(label), ptr(groups), stride, n_attr, n_groups,
+                                          ptr(counts), stream_ptr()), "sia_head_tail_chain")
     return logp, pred
 
 

@@ -21,10 +21,21 @@ __all__ = ["SkinCancerListModel", "SkinCancerModel", "create_loss_function", "sa
            "load_model", "CnnPlan"]
 
 
+LEGACY_WIDTHS = ([32, 64, 128], [32, 64, 128, 256])     # SkinCancerListModel / SkinCancerModel: no channel padding
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
 class CnnPlan:
     """Packed bf16 weights + the launch sequence for one architecture on one device.
 
-    conv_params: [(weight[O,I,k,k], bias[O])...]; fc_params: [(weight, bias)] * 3 (reference layout).
+    conv_params: [(weight[O,I,k,k], bias[O])...] -- a 7x7 block on 3 channels, then 3x3 blocks;
+    fc_params: [(weight, bias), ...] -- two or more Linear layers, the last one with 2 outputs (reference layout).
+    The two fixed architectures of tone_bias_model.py use their exact widths; any other widths (16..256,
+    tone_bias_optuna.define_isic_model) run through the same kernels on channel buffers zero-padded to multiples
+    of 64 (padded weights and biases are zero, so padded activations are exactly zero).
     """
 
     def __init__(self, conv_params, fc_params, image_size: int | None = None):
@@ -32,48 +43,72 @@ class CnnPlan:
         if dev.type != "cuda":
             raise SiaError("CnnPlan needs CUDA parameters (there is no CPU fallback)")
         self.device = dev
+        widths = [int(w.shape[0]) for w, _ in conv_params]
         if image_size is None:
             # the reference hard-codes 224 (tone_bias_model.py:69-70); other sizes follow from the first Linear:
             # in_features = c_last * (image_size / 2^n_conv)^2
-            c_last = conv_params[-1][0].shape[0]
-            side = int(round((fc_params[0][0].shape[1] / c_last) ** 0.5))
+            side = int(round((fc_params[0][0].shape[1] / widths[-1]) ** 0.5))
             image_size = side << len(conv_params)
         self.image_size = image_size
-        self.convs = []
+        if len(fc_params) < 2 or fc_params[-1][0].shape[0] != 2:
+            raise SiaError("the fused tail handles exactly two classes (benign / malignant) after >= 1 hidden Linear")
+        legacy = widths in LEGACY_WIDTHS
+        pads = widths if legacy else [_round_up(c, 64) for c in widths]
+        if max(pads) > 256:
+            raise SiaError("conv widths above 256 channels are not supported")
+        self.pads = pads
+        self.widths = widths
+        self.convs = []          # (packed | [packed chunks], bias | [bias chunks], cin_pad, cout_pad)
         side = image_size
         for i, (w, b) in enumerate(conv_params):
             w = w.detach().float().contiguous()
+            b = b.detach().float().contiguous()
             cout, cin, k, _ = w.shape
             if i == 0:
-                if (cout, cin, k) != (32, 3, 7):
-                    raise SiaError(f"first block must be Conv2d(3,32,7); got ({cin},{cout},{k})")
-                packed = ops.pack_conv7x7_c3(w)
+                if (cin, k) != (3, 7):
+                    raise SiaError(f"first block must be Conv2d(3, n, 7); got ({cin},{cout},{k})")
+                chunks, biases = [], []
+                for c0 in range(0, cout, 32):      # the kernel computes 32 output channels per launch
+                    wc = torch.zeros((32, 3, 7, 7), dtype=torch.float32, device=dev)
+                    bc = torch.zeros((32,), dtype=torch.float32, device=dev)
+                    n = min(32, cout - c0)
+                    wc[:n], bc[:n] = w[c0:c0 + n], b[c0:c0 + n]
+                    chunks.append(ops.pack_conv7x7_c3(wc))
+                    biases.append(bc)
+                self.convs.append((chunks, biases, 3, pads[0]))
             else:
-                if k != 3:
-                    raise SiaError("only 3x3 kernels after the first block")
-                packed = ops.pack_conv3x3(w)
-            self.convs.append((packed, b.detach().float().contiguous(), cin, cout))
+                if k != 3 or cin != widths[i - 1]:
+                    raise SiaError("only chained 3x3 kernels after the first block")
+                bp = torch.zeros((pads[i],), dtype=torch.float32, device=dev)
+                bp[:cout] = b
+                self.convs.append((ops.pack_conv3x3(w, pads[i - 1], pads[i]), bp, pads[i - 1], pads[i]))
             side //= 2
-        c_last = self.convs[-1][3]
-        (w1, b1), (w2, b2), (w3, b3) = fc_params
+        c_last, c_last_pad = widths[-1], pads[-1]
+        (w1, b1) = fc_params[0]
         if w1.shape[1] != c_last * side * side:
             raise SiaError("first Linear does not match the flattened conv output")
         # nn.Flatten on NCHW orders features (C,H,W); activations here are NHWC -> permute columns once
-        self.w1 = ops.pack_linear_chw_to_hwc(w1.detach().float().contiguous(), c_last, side * side)
+        self.n1 = int(w1.shape[0])
+        self.n1_pad = _round_up(self.n1, 128)
+        self.w1 = ops.pack_linear_chw_to_hwc(w1.detach().float().contiguous(), c_last, side * side, self.n1_pad, c_last_pad)
         self.b1 = b1.detach().float().contiguous()
-        self.w2t = w2.detach().float().t().contiguous()
-        self.b2 = b2.detach().float().contiguous()
-        self.w3 = w3.detach().float().contiguous()
-        self.b3 = b3.detach().float().contiguous()
-        if self.w3.shape[0] != 2:
-            raise SiaError("the fused tail handles exactly two classes (benign / malignant)")
-        self.n1, self.n2 = self.w1.shape[0], self.w2t.shape[1]
         self.feat = self.w1.shape[1]
+        rest = [(w.detach().float(), b.detach().float().contiguous()) for w, b in fc_params[1:]]
+        self.fused_tail = (len(rest) == 2 and self.n1 == self.n1_pad and self.n1 <= 512 and rest[0][0].shape[0] <= 256)
+        if self.fused_tail:
+            (w2, self.b2), (w3, self.b3) = rest
+            self.w2t = w2.t().contiguous()
+            self.w3 = w3.contiguous()
+            self.n2 = self.w2t.shape[1]
+        else:
+            if self.n1 > 512 or any(w.shape[0] > 512 for w, _ in rest):
+                raise SiaError("Linear layers wider than 512 are not supported by the tail kernel")
+            self.chain = [(w.t().contiguous(), b) for w, b in rest]
         self._ws = {}
         torch.cuda.current_stream(dev).synchronize()
 
     def splits_for(self, batch: int) -> int:
-        tiles = ((batch + 127) // 128) * (self.n1 // 128)
+        tiles = ((batch + 127) // 128) * (self.n1_pad // 128)
         sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         return max(1, min(self.feat // 64, sms // tiles))
 
@@ -82,31 +117,43 @@ class CnnPlan:
         if ws is None:
             s = self.image_size
             acts = []
-            for (_p, _b, _cin, cout) in self.convs:
+            for (_p, _b, _cin, cout_pad) in self.convs:
                 s //= 2
-                acts.append(torch.empty((batch, s, s, cout), dtype=torch.bfloat16, device=self.device))
+                # zero-initialised: padded channels are never written by the first block and must read as zero
+                acts.append(torch.zeros((batch, s, s, cout_pad), dtype=torch.bfloat16, device=self.device))
             splits = self.splits_for(batch)
             ws = dict(acts=acts, splits=splits,
-                      partial=torch.empty((splits, batch, self.n1), dtype=torch.float32, device=self.device),
+                      partial=torch.empty((splits, batch, self.n1_pad), dtype=torch.float32, device=self.device),
                       logp=torch.empty((batch, 2), dtype=torch.float32, device=self.device),
                       pred=torch.empty((batch,), dtype=torch.uint8, device=self.device))
             self._ws[batch] = ws
         return ws
+
+    def conv_block(self, i: int, x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        packed, bias, _cin_pad, cout_pad = self.convs[i]
+        if i == 0:
+            for j, (pk, bs) in enumerate(zip(packed, bias)):
+                ops.conv7x7_c3_relu_pool2(x, pk, bs, out=out, c_offset=32 * j)
+            return out
+        return ops.conv3x3_relu_pool2(x, packed, bias, cout_pad, out=out)
+
+    def tail(self, part, label=None, groups=None, n_groups: int = 0, counts=None, logp=None, pred=None):
+        if self.fused_tail:
+            return ops.head_tail(part, self.b1, self.w2t, self.b2, self.w3, self.b3, label=label, groups=groups,
+                                 n_groups=n_groups, counts=counts, logp=logp, pred=pred)
+        return ops.head_tail_chain(part, self.n1, self.b1, self.chain, label=label, groups=groups, n_groups=n_groups,
+                                   counts=counts, logp=logp, pred=pred)
 
     def forward_nhwc4(self, x4: torch.Tensor, label=None, groups=None, n_groups: int = 0, counts=None):
         """x4: padded NHWC4 [B,S,S+8,4] bf16 -> (logp [B,2] f32, pred [B] u8).  Buffers are reused per batch size."""
         batch = x4.shape[0]
         ws = self.workspace(batch)
         h = x4
-        for i, (packed, bias, _cin, cout) in enumerate(self.convs):
-            if i == 0:
-                h = ops.conv7x7_c3_relu_pool2(h, packed, bias, out=ws["acts"][i])
-            else:
-                h = ops.conv3x3_relu_pool2(h, packed, bias, cout, out=ws["acts"][i])
-        a = h.view(batch, -1)
-        part = ops.linear_splitk(a, self.w1, ws["splits"], out=ws["partial"])
-        return ops.head_tail(part, self.b1, self.w2t, self.b2, self.w3, self.b3, label=label, groups=groups,
-                             n_groups=n_groups, counts=counts, logp=ws["logp"], pred=ws["pred"])
+        for i in range(len(self.convs)):
+            h = self.conv_block(i, h, ws["acts"][i])
+        part = ops.linear_splitk(h.view(batch, -1), self.w1, ws["splits"], out=ws["partial"])
+        return self.tail(part, label=label, groups=groups, n_groups=n_groups, counts=counts, logp=ws["logp"],
+                         pred=ws["pred"])
 
 
 class _B200Eval(nn.Module):

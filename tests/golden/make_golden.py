@@ -209,9 +209,31 @@ def gen_experiments(ref):
         json.dump(out, f, indent=1, sort_keys=True)
 
 
+def gen_optuna_best(ref):
+    """model_optuna_best.npz: the reference's own ``tone_bias_optuna.create_best_model()`` (:116-120; conv 192 / 172 /
+    22 / 86, linear 227 / 80 / 86) built under torch.manual_seed(123) -- the drop-in builder creates the same layers
+    in the same order, so the same seed reproduces the weights -- and its log-probabilities for a seeded batch."""
+    import importlib
+    ro = importlib.import_module("tone_bias_optuna")
+    torch.manual_seed(123)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = ro.create_best_model().eval()
+    x = helpers.synthetic_batch_f32(3, 224, seed=33)
+    with torch.no_grad():
+        logp = model(x)
+    state = model.state_dict()
+    checks = {k.replace(".", "_") + "_sum": float(v.double().sum()) for k, v in state.items()}
+    np.savez(os.path.join(HERE, "model_optuna_best.npz"), logp=logp.numpy(), pred=logp.argmax(1).numpy(),
+             keys=np.array(list(state.keys())), **{k: np.float64(v) for k, v in checks.items()})
+    # the oracle restatement must agree with the reference class on the same weights
+    got = omodel.forward_sequential(state, x)
+    assert float((got - logp).abs().max()) < 1e-6
+
+
 def main():
     ref = ref_import.load()
     gen_notebook()
+    gen_optuna_best(ref)
     gen_experiments(ref)
     gen_analysis(ref)
     gen_transform(ref)

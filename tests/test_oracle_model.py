@@ -40,3 +40,36 @@ def test_logsoftmax_rows_normalised():
     x = helpers.synthetic_batch_f32(2, 224, seed=2)
     logp = om.forward(om.LIST_MODEL, state, x)
     assert torch.allclose(logp.exp().sum(1), torch.ones(2), atol=1e-6)
+
+
+def test_optuna_best_model_builder_reproduces_reference_weights_and_oracle(golden_dir):
+    """tone_bias_optuna drop-in: same layers in the same order as the reference builder, so the same torch seed
+    gives the same parameters (checked by per-tensor sums recorded from the reference), and the oracle's
+    sequential forward of those weights reproduces the reference's log-probabilities."""
+    import contextlib
+    import io
+    import os
+
+    import numpy as np
+    import torch
+
+    from oracle import model as om
+    from skin_image_analysis_b200 import tone_bias_optuna as to
+    from tests import helpers
+    g = np.load(os.path.join(golden_dir, "model_optuna_best.npz"))
+    torch.manual_seed(123)
+    with contextlib.redirect_stdout(io.StringIO()) as out:
+        model = to.create_best_model()
+    assert "DEBUGGING 16856 = 86 * (14*14)" in out.getvalue()
+    state = model.state_dict()
+    assert list(state.keys()) == list(g["keys"])
+    for k, v in state.items():
+        assert float(v.double().sum()) == float(g[k.replace(".", "_") + "_sum"]), k
+    x = helpers.synthetic_batch_f32(3, 224, seed=33)
+    logp = om.forward_sequential(state, x).numpy()
+    assert np.abs(logp - g["logp"]).max() < 1e-5
+    trial = to.TrialDummy({"a": 3, "b": 0.5})
+    assert trial.suggest_int("a", 1, 6) == 3 and trial.suggest_float("b", 0.2, 0.5) == 0.5
+    with pytest.raises(ValueError):
+        trial.suggest_int("a", 4, 6)                      # below the minimum
+    assert trial.suggest_int("a", 1, 2) == 3              # above the maximum: not enforced by the reference either
