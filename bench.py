@@ -43,6 +43,9 @@ WORKLOADS = {
     "fourconv224": dict(kind="SkinCancerModel", out=224, batch=512,
                         text="configs[3]: SkinCancerModel (= jgi_hiba_2022_model) eval, batch 512 per GPU, bf16, fused "
                              "resize+normalise from synthetic 600x450 uint8 images, per-group confusion counts"),
+    "optuna224": dict(kind="optuna_best", out=224, batch=128,
+                      text="tone_bias_optuna.create_best_model (conv 192/172/22/86, linear 227/80/86; 10.5 GFLOP per "
+                           "image) eval, batch 128 per GPU, bf16, zero-padded channel buffers"),
     "list512": dict(kind="SkinCancerListModel", out=512, batch=128,
                     text="configs[4]: SkinCancerListModel eval at 512x512 (first Linear 524288->512), batch 128 per "
                          "GPU, bf16, fused resize+normalise from synthetic 600x450 uint8 images"),

@@ -29,6 +29,10 @@ def plan_from_state_dict(state: dict, device) -> CnnPlan:
     """Reference ``state_dict`` (either architecture) -> packed weights on ``device``."""
     if any(k.startswith("layers.") for k in state):
         conv_keys, fc_keys = ["layers.0", "layers.3", "layers.6"], ["layers.10", "layers.13", "layers.16"]
+    elif all(k.split(".")[0].isdigit() for k in state):          # an nn.Sequential (define_isic_model)
+        names = sorted({k.rsplit(".", 1)[0] for k in state}, key=int)
+        conv_keys = [n for n in names if state[n + ".weight"].dim() == 4]
+        fc_keys = [n for n in names if state[n + ".weight"].dim() == 2]
     else:
         conv_keys = [k for k in ("conv1", "conv2", "conv3", "conv4") if k + ".weight" in state]
         fc_keys = ["fc4", "fc5", "fc6"]

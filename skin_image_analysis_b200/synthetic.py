@@ -40,6 +40,9 @@ ARCHS = {   # reference state_dict prefixes (tone_bias_model.py:56-152 and :155-
     "SkinCancerModel": dict(convs=[("conv1", 32, 3, 7), ("conv2", 64, 32, 3), ("conv3", 128, 64, 3),
                                    ("conv4", 256, 128, 3)],
                             linears=[("fc4", 512), ("fc5", 256), ("fc6", 2)]),
+    # tone_bias_optuna.create_best_model (:96-120): nn.Sequential indices of the Conv2d / Linear children
+    "optuna_best": dict(convs=[("0", 192, 3, 7), ("3", 172, 192, 3), ("6", 22, 172, 3), ("9", 86, 22, 3)],
+                        linears=[("13", 227), ("16", 80), ("19", 86), ("22", 2)]),
 }
 
 
