@@ -198,6 +198,10 @@ int sia_debug_umma_probe_ex(const void* smem_image, int image_bytes, const uint6
                             const uint64_t* b_desc_host, int n_mma, int n, int kind, uint32_t idesc,
                             void* out_128xn_raw, int repeat, long long* cycles_host, void* stream);
 
+/* Debug (timing only): the following probes move to the other of two accumulators every switch_every MMAs
+ * (0 = off), optionally with a tcgen05.commit at every switch: the cost of short accumulation chains. */
+int sia_debug_umma_probe_switch(int switch_every, int commit_each);
+
 /* Debug / bring-up: one TMA tiled load of a bf16 tensor (rank 2..4; dims / box in elements, innermost
  * first; strides in bytes for dims 1..rank-1; swizzle_bytes in {0,32,64,128}) at the given coordinates;
  * `out` receives the box bytes exactly as they landed in shared memory.  repeat > 1 issues that many

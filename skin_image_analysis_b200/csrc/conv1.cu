@@ -130,6 +130,56 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
   const uint32_t tmem_base = bcast0(*tmem_slot);
   const float* smem_bias = reinterpret_cast<const float*>(smem_biasop);
 
+#ifdef SIA_C1_RAW_ISSUE
+  // timing experiment: only the MMA warp runs, issuing every tile's UMMAs back to back without any barrier traffic
+  if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_bf16(128, C1_N);
+    constexpr uint32_t a_hi = desc_hi(2 * C1_ROWB, SW_NONE);
+    constexpr uint32_t b_hi = desc_hi(C1_B_SBO, SW_NONE);
+    const uint32_t a_lo0 = desc_lo(smem_u32(smem_a), 16);
+    const uint32_t b_lo0 = desc_lo(smem_u32(smem_b), 128);
+    int stage = 0, acc = 0;
+    uint32_t sphase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+#if SIA_C1_RAW_ISSUE == 3 || SIA_C1_RAW_ISSUE == 4 || SIA_C1_RAW_ISSUE == 6
+      // a barrier that is always already complete: the cost of the wait (+ fence) themselves
+      if (lane < 4) mbar_arrive(&tempty_bar[0]);
+      mbar_wait(&tempty_bar[0], sphase, 38);
+#if SIA_C1_RAW_ISSUE == 4
+      if (lane == 0) mbar_arrive(&full_bar[0]);
+      mbar_wait(&full_bar[0], sphase, 38);
+#endif
+      sphase ^= 1;
+#endif
+#if SIA_C1_RAW_ISSUE == 3 || SIA_C1_RAW_ISSUE == 4 || SIA_C1_RAW_ISSUE == 5
+      tc_fence_after_sync();
+#endif
+      if (elect_one()) {
+        const uint32_t d_tmem = tmem_base + acc * C1_N;
+        const uint32_t a_lo = a_lo0 + stage * (C1_STAGE_STRIDE >> 4);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            umma_bf16_ss_w(d_tmem, a_lo + r * (C1_ROWB >> 4) + kk * 2, a_hi, b_lo0 + (r * 4 + kk * 2) * 8, b_hi, idesc,
+                           (r | kk) ? 1u : 0u);
+          }
+        }
+#if SIA_C1_RAW_ISSUE >= 2
+        umma_commit(&empty_bar[stage]);
+        umma_commit(&tfull_bar[acc]);
+#endif
+      }
+      __syncwarp();
+      if (++stage == C1_NSTAGE) stage = 0;
+      if (++acc == C1_NACC) acc = 0;
+    }
+    if (elect_one()) umma_commit(wload_bar);
+    __syncwarp();
+    mbar_wait(wload_bar, 0, 39);
+  }
+  if (warp < 64) goto c1_done;
+#endif
   if (warp == 0) {
     if (lane == 0) {
       mbar_arrive_expect_tx(wload_bar, C1_B_BYTES);
@@ -144,11 +194,15 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
         mbar_wait(&empty_bar[stage], phase ^ 1, 30);
         wait_stage.end();
         trace(lt, 0);
+#ifdef SIA_C1_NO_TMA
+        mbar_arrive(&full_bar[stage]);                    // timing experiment: operands are whatever is in smem
+#else
         mbar_arrive_expect_tx(&full_bar[stage], C1_STAGE_BYTES);
         // innermost coordinate is in bf16 elements (4 per pixel) and must be 16-byte aligned for TMA:
         // image pixel x sits in column x+1 of the padded row, so the window start x0-3 is column x0-2
         tma_load_3d(smem_a + stage * C1_STAGE_STRIDE, &tmap_in, &full_bar[stage], (t.tx * C1_TILE_X - 2) * 4,
                     t.ty * C1_TILE_Y - 3, t.n);
+#endif
         trace(lt, 1);
         if (++stage == C1_NSTAGE) { stage = 0; phase ^= 1; }
       }
@@ -188,8 +242,11 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
         const uint32_t d_tmem = tmem_base + acc * C1_N;
         const uint32_t a_lo = a_lo0 + stage * (C1_STAGE_STRIDE >> 4);
         if (C1_BIAS_UMMA) umma_bf16_ss_w(d_tmem, ones_lo, c_hi, bias_lo, c_hi, idesc, 0u);     // D = bias
+#ifndef SIA_C1_ROWS
+#define SIA_C1_ROWS 8
+#endif
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
+        for (int r = 0; r < SIA_C1_ROWS; ++r) {       // (timing experiments may issue fewer window rows)
 #pragma unroll
           for (int kk = 0; kk < 2; ++kk) {
             umma_bf16_ss_w(d_tmem, a_lo + r * (C1_ROWB >> 4) + kk * 2, a_hi, b_lo0 + (r * 4 + kk * 2) * 8, b_hi, idesc,
@@ -259,6 +316,12 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
         }
       };
 
+#ifdef SIA_C1_NO_EPI
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);     // timing experiment: the accumulator is not read
+      continue;
+#endif
       uint32_t a0[16], a1[16], a2[16], a3[16], b0[16], b1[16], b2[16], b3[16];
       tmem_ld16(t_addr + 0, a0);
       tmem_ld16(t_addr + 32, a1);
@@ -286,6 +349,9 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
     }
   }
 
+#ifdef SIA_C1_RAW_ISSUE
+c1_done:
+#endif
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 2) tmem_free(tmem_base, C1_NACC * C1_N);

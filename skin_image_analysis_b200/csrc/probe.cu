@@ -17,6 +17,8 @@ struct ProbeParams {
   int image_bytes;
   int repeat;
   int kind;          // 0 = kind::f16 (bf16 inputs, fp32 accumulate), 1 = kind::i8 (s32 accumulate)
+  int switch_every;  // > 0 (timing only): after this many MMAs move to the next of two accumulators, restarting it
+  int commit_each;   // != 0 (timing only): tcgen05.commit to a scratch barrier at every accumulator switch
   uint32_t idesc;    // 0 = the default bf16 K-major descriptor for (128, n)
 };
 
@@ -25,6 +27,7 @@ umma_probe_kernel(const uint8_t* __restrict__ image, const __grid_constant__ Pro
                   long long* __restrict__ cycles) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ uint64_t done_bar;
+  __shared__ uint64_t scratch_bar;
   __shared__ uint32_t tmem_slot;
 
   // 1024-byte aligned image base so that relative alignment == absolute alignment
@@ -36,12 +39,13 @@ umma_probe_kernel(const uint8_t* __restrict__ image, const __grid_constant__ Pro
   }
   fence_proxy_async_smem();
 
-  const uint32_t ncols = p.n <= 32 ? 32 : p.n <= 64 ? 64 : p.n <= 128 ? 128 : 256;
+  const uint32_t ncols = p.switch_every > 0 ? 512 : p.n <= 32 ? 32 : p.n <= 64 ? 64 : p.n <= 128 ? 128 : 256;
   if (threadIdx.x < 32) {
     tmem_alloc(&tmem_slot, ncols);
   }
   if (threadIdx.x == 32) {
     mbar_init(&done_bar, 1);
+    mbar_init(&scratch_bar, 1 << 20);
     fence_mbar_init();
   }
   tc_fence_before_sync();
@@ -56,6 +60,19 @@ umma_probe_kernel(const uint8_t* __restrict__ image, const __grid_constant__ Pro
     long long t0 = 0;
     if (elect_one()) {
       t0 = clock64();
+      if (p.switch_every > 0) {              // timing experiment: rotate over two accumulators every k MMAs
+        // n_mma is a multiple of switch_every; chains alternate between the two accumulators
+        uint32_t acc = 0;
+        for (int rep = 0; rep < p.repeat; ++rep) {
+          for (int i0 = 0; i0 < p.n_mma; i0 += p.switch_every) {
+            for (int i = i0; i < i0 + p.switch_every; ++i) {
+              umma_bf16_ss(tmem + acc, p.a_desc[i] + base16, p.b_desc[i] + base16, idesc, i > i0 ? 1u : 0u);
+            }
+            if (p.commit_each) umma_commit(&scratch_bar);
+            acc ^= 256u;
+          }
+        }
+      } else
       for (int rep = 0; rep < p.repeat; ++rep) {
         for (int i = 0; i < p.n_mma; ++i) {
           // start-address field is relative to the image base (no carry: the image is < 256 KB)
@@ -94,6 +111,13 @@ umma_probe_kernel(const uint8_t* __restrict__ image, const __grid_constant__ Pro
 
 }  // namespace sia
 
+static int g_probe_switch_every = 0, g_probe_commit_each = 0;
+extern "C" int sia_debug_umma_probe_switch(int switch_every, int commit_each) {
+  g_probe_switch_every = switch_every;
+  g_probe_commit_each = commit_each;
+  return 0;
+}
+
 extern "C" int sia_debug_umma_probe(const void* smem_image, int image_bytes, const uint64_t* a_desc_host,
                                     const uint64_t* b_desc_host, int n_mma, int n, float* out_128xn, int repeat,
                                     long long* cycles_host, void* stream) {
@@ -123,6 +147,8 @@ extern "C" int sia_debug_umma_probe_ex(const void* smem_image, int image_bytes, 
   p.repeat = repeat;
   p.kind = kind;
   p.idesc = idesc;
+  p.switch_every = g_probe_switch_every;
+  p.commit_each = g_probe_commit_each;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   long long* d_cycles = nullptr;
   if (cycles_host) SIA_CUDA_OK(cudaMalloc(&d_cycles, sizeof(long long)));
