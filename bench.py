@@ -338,6 +338,10 @@ def run_ours(args):
     # ------------------------------------ value: inputs resident in HBM ------------------------------
     for s in range(warmup):
         resident_step(s)
+    with torch.cuda.stream(eng.stream):
+        # warm-up of the collective too: NCCL loads its int64-sum kernel and sets the stream up lazily on the first
+        # call (about a millisecond -- 10 % of a 20-step timed region)
+        D.allreduce_counts(torch.zeros_like(eng.counts))
     eng.synchronize()
     eng.reset_counts()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -210,6 +210,9 @@ preprocess_tc_kernel(const __grid_constant__ CUtensorMap tmap_src, const __grid_
             mbar_wait(&raw_full[rs], rphase, 46);
             if (warp == 0 && lane == 0 && q == 0) trace(it0 / TC_NQ, 2);
             uint2 v[16];
+#ifdef SIA_TC_NOCONV
+            if (it0 < 0)                             // timing experiment: barriers only, operands are whatever is in smem
+#endif
             {
               const uint32_t src = smem_u32(smem_raw_ring) + rs * TC_RAW_BYTES + ld_lane + mis;
 #pragma unroll
@@ -220,6 +223,9 @@ preprocess_tc_kernel(const __grid_constant__ CUtensorMap tmap_src, const __grid_
               }
             }
             mbar_wait(&empty_bar[stage], phase ^ 1, 40);
+#ifdef SIA_TC_NOCONV
+            if (it0 < 0)
+#endif
             {
               const uint32_t base = smem_u32(smem_b) + stage * TC_STAGE_BYTES + st_lane;
 #pragma unroll
