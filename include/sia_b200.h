@@ -101,6 +101,23 @@ int sia_preprocess_tc_u8hwc(const uint8_t* src, int batch, int src_h, int src_w,
                             const void* items, int n_items, int n_blocks, int last_block_cols, int pads_in_schedule,
                             int out_h, int out_w, const float* out_scale_host, const float* out_bias_host, void* dst_nhwc4, void* stream);
 
+/* SURVEY 8(f) row 2 -- the ToneClassifier test transform (notebooks/ToneClassifier/CNNTrialDataset.py:71-76:
+ * v2.Resize((224,224)) on uint8 [bilinear, antialias] -> v2.ToDtype(float32, scale=True) -> v2.Normalize(mean, std))
+ * for a batch of u8 HWC decode buffers.  torchvision's uint8 resize is ATen's fixed-point separable resampler
+ * (aten/src/ATen/native/cpu/UpSampleKernel.cpp): horizontal pass -> uint8 -> vertical pass -> uint8, so the
+ * kernel is bit-exact.  Tables (resize_weights.build_tv_tables), all device pointers:
+ *   x_min[out_w], x_w_tapmajor[x_taps][out_w] (int16, scaled by 2^x_prec)     horizontal taps
+ *   y_min[out_h], y_w[out_h][y_taps]          (int16, scaled by 2^y_prec)     vertical taps
+ *   lut_3x256                                 float32 value of byte b in channel c after ToDtype + Normalize
+ * x_min[j] + x_taps <= src_w and y_min[i] + y_taps <= src_h for every j, i (the builder shifts windows that
+ * would run off the edge and zero-pads their weights).  One CTA produces tile_rows output rows of one image from
+ * at most max_window_rows source rows staged in shared memory (SIA_E_UNSUPPORTED if that exceeds 227 KB).
+ * layout: SIA_LAYOUT_* as for sia_preprocess_u8hwc. */
+int sia_preprocess_tv_u8hwc(const uint8_t* src, int batch, int src_h, int src_w, const int32_t* x_min,
+                            const int16_t* x_w_tapmajor, int x_taps, int x_prec, const int32_t* y_min,
+                            const int16_t* y_w, int y_taps, int y_prec, const float* lut_3x256, int out_h, int out_w,
+                            int tile_rows, int max_window_rows, int layout, void* dst, void* stream);
+
 /* Model boundary: NCHW fp32 [B,3,h,w] (the tensor the reference DataLoader feeds to model(images),
  * src/tone_bias_test.py:190-196) -> padded NHWC4 bf16 [B,h,w+8,4] (SIA_LAYOUT_NHWC4_BF16). */
 int sia_nchw_f32_to_nhwc4_bf16(const float* src, int batch, int h, int w, void* dst, void* stream);

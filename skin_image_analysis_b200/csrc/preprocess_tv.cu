@@ -1,0 +1,192 @@
+// the ToneClassifier test transform (notebooks/ToneClassifier/CNNTrialDataset.py:71-76)
+//
+//     v2.Resize((224, 224))                      uint8, bilinear, antialias=True
+//     v2.ToDtype(torch.float32, scale=True)      u8 * (1/255)
+//     v2.Normalize(mean, std)                    (x - mean[c]) / std[c]
+//
+// for a whole batch of decoded u8 HWC images resident in HBM.  torchvision's uint8 resize is ATen's
+// Pillow-style FIXED-POINT separable resampler (int16 taps, horizontal pass -> uint8 -> vertical pass ->
+// uint8), so this is integer work and the kernel is bit-exact, not "within a tolerance":
+//
+//     h[r][j][c]   = clamp_u8((sum_t xw[j][t] * src[r][xmin[j] + t][c] + 2^(xp-1)) >> xp)
+//     out[i][j][c] = lut[c][ clamp_u8((sum_t yw[i][t] * h[ymin[i] + t][j][c] + 2^(yp-1)) >> yp) ]
+//
+// The taps come from the host (resize_weights.build_tv_tables, same formulas as ATen's
+// _compute_index_ranges_int16_weights); lut[c][b] is the float32 value ToDtype + Normalize give to byte b,
+// computed on the host with the same float32 operations, so the float tensor is bit-identical too.
+//
+// One CTA = (image, tile of tile_rows output rows): the source rows the tile needs are copied once into shared
+// memory with 16-byte loads (HBM reads every source byte once per tile, halo rows twice), the horizontal pass
+// writes its uint8 rows into a second shared buffer, the vertical pass reads them and stores the output layout
+// with coalesced stores.  HBM-bound by design: src_h*src_w*3 bytes in, out_h*out_w*3*sizeof(out) bytes out.
+#include <cuda_bf16.h>
+
+#include "sia_host.cuh"
+#include "sia_ptx.cuh"
+
+namespace sia {
+
+constexpr int TV_THREADS = 512;
+
+struct TvParams {
+  const uint8_t* src;
+  const int32_t* x_min;   // [out_w]
+  const int16_t* x_w;     // [x_taps][out_w]  (tap-major: lanes of a warp read consecutive shorts)
+  const int32_t* y_min;   // [out_h]
+  const int16_t* y_w;     // [out_h][y_taps]
+  const float* lut;       // [3][256]
+  void* dst;
+  int batch, src_h, src_w, out_h, out_w;
+  int x_taps, y_taps, x_prec, y_prec;
+  int tile_rows, max_rows;          // output rows per CTA; capacity (source rows) of the shared window
+};
+
+__device__ __forceinline__ int clamp_u8(int v) { return min(max(v, 0), 255); }
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(TV_THREADS)
+preprocess_tv_kernel(const __grid_constant__ TvParams p) {
+  extern __shared__ __align__(128) uint8_t smem_tv[];
+  const int row_bytes = p.src_w * 3;
+  const int hrow = p.out_w * 3;
+  const int hpitch = (hrow + 3) & ~3;
+  uint8_t* s_rows = smem_tv;                                                  // max_rows * row_bytes + 32
+  uint8_t* s_h = s_rows + (((size_t)p.max_rows * row_bytes + 32 + 15) & ~(size_t)15);   // max_rows * hpitch
+  float* s_lut = reinterpret_cast<float*>(s_h + (((size_t)p.max_rows * hpitch + 15) & ~(size_t)15));
+  int32_t* s_xmin = reinterpret_cast<int32_t*>(s_lut + 768);
+  int16_t* s_xw = reinterpret_cast<int16_t*>(s_xmin + p.out_w);
+
+  const int n = blockIdx.y;
+  const int i0 = blockIdx.x * p.tile_rows;
+  const int i1 = min(i0 + p.tile_rows, p.out_h);
+  const int r0 = p.y_min[i0];
+  const int rows = min(p.y_min[i1 - 1] + p.y_taps - r0, p.max_rows);
+
+  // ---- stage the source window: [r0, r0 + rows) is one contiguous span of the decode buffer ---------------
+  const uint8_t* g = p.src + ((size_t)n * p.src_h + r0) * row_bytes;
+  const uint32_t len = (uint32_t)rows * row_bytes;
+  const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 15u);
+  uint8_t* s = s_rows + mis;                       // same misalignment: aligned global 16 bytes <-> aligned shared 16 bytes
+  const uint32_t head = min(len, (16u - mis) & 15u);
+  const uint32_t nvec = (len - head) >> 4;
+  const uint32_t tail0 = head + (nvec << 4);
+  for (uint32_t b = threadIdx.x; b < head; b += TV_THREADS) s[b] = g[b];
+  {
+    const uint4* gv = reinterpret_cast<const uint4*>(g + head);
+    uint4* sv = reinterpret_cast<uint4*>(s + head);
+    for (uint32_t v = threadIdx.x; v < nvec; v += TV_THREADS) sv[v] = __ldg(gv + v);
+  }
+  for (uint32_t b = tail0 + threadIdx.x; b < len; b += TV_THREADS) s[b] = g[b];
+  for (int k = threadIdx.x; k < 768; k += TV_THREADS) s_lut[k] = p.lut[k];
+  for (int k = threadIdx.x; k < p.out_w; k += TV_THREADS) s_xmin[k] = p.x_min[k];
+  for (int k = threadIdx.x; k < p.out_w * p.x_taps; k += TV_THREADS) s_xw[k] = p.x_w[k];
+  __syncthreads();
+
+  // ---- horizontal pass: every staged source row -> out_w uint8 pixels -------------------------------------
+  {
+    const int half = 1 << (p.x_prec - 1);
+    const int total = rows * p.out_w;
+    for (int idx = threadIdx.x; idx < total; idx += TV_THREADS) {
+      const int r = idx / p.out_w, j = idx - r * p.out_w;
+      const uint8_t* px = s + (size_t)r * row_bytes + 3 * s_xmin[j];
+      int a0 = half, a1 = half, a2 = half;
+      for (int t = 0; t < p.x_taps; ++t) {
+        const int w = s_xw[t * p.out_w + j];
+        a0 += w * px[3 * t];
+        a1 += w * px[3 * t + 1];
+        a2 += w * px[3 * t + 2];
+      }
+      uint8_t* h = s_h + (size_t)r * hpitch + 3 * j;
+      h[0] = (uint8_t)clamp_u8(a0 >> p.x_prec);
+      h[1] = (uint8_t)clamp_u8(a1 >> p.x_prec);
+      h[2] = (uint8_t)clamp_u8(a2 >> p.x_prec);
+    }
+  }
+  __syncthreads();
+
+  // ---- vertical pass + ToDtype/Normalize (table) + output layout -------------------------------------------
+  {
+    const int half = 1 << (p.y_prec - 1);
+    const int total = (i1 - i0) * p.out_w;
+    for (int idx = threadIdx.x; idx < total; idx += TV_THREADS) {
+      const int di = idx / p.out_w, j = idx - di * p.out_w;
+      const int i = i0 + di;
+      const uint8_t* h = s_h + (size_t)(p.y_min[i] - r0) * hpitch + 3 * j;
+      const int16_t* yw = p.y_w + (size_t)i * p.y_taps;
+      int a0 = half, a1 = half, a2 = half;
+      for (int t = 0; t < p.y_taps; ++t) {
+        const int w = __ldg(yw + t);
+        a0 += w * h[(size_t)t * hpitch];
+        a1 += w * h[(size_t)t * hpitch + 1];
+        a2 += w * h[(size_t)t * hpitch + 2];
+      }
+      const float f0 = s_lut[clamp_u8(a0 >> p.y_prec)];
+      const float f1 = s_lut[256 + clamp_u8(a1 >> p.y_prec)];
+      const float f2 = s_lut[512 + clamp_u8(a2 >> p.y_prec)];
+      if constexpr (LAYOUT == SIA_LAYOUT_NCHW_F32) {
+        float* d = static_cast<float*>(p.dst) + (((size_t)n * 3) * p.out_h + i) * p.out_w + j;
+        const size_t plane = (size_t)p.out_h * p.out_w;
+        d[0] = f0;
+        d[plane] = f1;
+        d[2 * plane] = f2;
+      } else if constexpr (LAYOUT == SIA_LAYOUT_NCHW_BF16) {
+        __nv_bfloat16* d = static_cast<__nv_bfloat16*>(p.dst) + (((size_t)n * 3) * p.out_h + i) * p.out_w + j;
+        const size_t plane = (size_t)p.out_h * p.out_w;
+        d[0] = __float2bfloat16_rn(f0);
+        d[plane] = __float2bfloat16_rn(f1);
+        d[2 * plane] = __float2bfloat16_rn(f2);
+      } else {
+        const int pitch = p.out_w + SIA_NHWC4_PAD;
+        uint2* d = static_cast<uint2*>(p.dst) + ((size_t)n * p.out_h + i) * pitch;
+        d[j + 1] = make_uint2(pack_bf16x2(f0, f1), pack_bf16x2(f2, 0.f));
+        if (j == 0) d[0] = make_uint2(0u, 0u);
+        if (j == p.out_w - 1) {
+#pragma unroll
+          for (int c = 1; c < SIA_NHWC4_PAD; ++c) d[p.out_w + c] = make_uint2(0u, 0u);
+        }
+      }
+    }
+  }
+}
+
+}  // namespace sia
+
+extern "C" int sia_preprocess_tv_u8hwc(const uint8_t* src, int batch, int src_h, int src_w, const int32_t* x_min,
+                                       const int16_t* x_w_tapmajor, int x_taps, int x_prec, const int32_t* y_min,
+                                       const int16_t* y_w, int y_taps, int y_prec, const float* lut_3x256, int out_h,
+                                       int out_w, int tile_rows, int max_window_rows, int layout, void* dst,
+                                       void* stream) {
+  using namespace sia;
+  SIA_REQUIRE(src && x_min && x_w_tapmajor && y_min && y_w && lut_3x256 && dst);
+  SIA_REQUIRE(batch >= 1 && src_h >= 1 && src_w >= 1 && out_h >= 1 && out_w >= 1);
+  SIA_REQUIRE(x_taps >= 1 && y_taps >= 1 && x_prec >= 1 && x_prec < 23 && y_prec >= 1 && y_prec < 23);
+  SIA_REQUIRE(tile_rows >= 1 && max_window_rows >= y_taps && max_window_rows <= src_h);
+  SIA_REQUIRE(layout == SIA_LAYOUT_NCHW_F32 || layout == SIA_LAYOUT_NCHW_BF16 || layout == SIA_LAYOUT_NHWC4_BF16);
+  if (batch > 65535) return SIA_E_UNSUPPORTED;
+  const size_t row_bytes = (size_t)src_w * 3;
+  const size_t hpitch = ((size_t)out_w * 3 + 3) & ~(size_t)3;
+  const size_t smem = (((size_t)max_window_rows * row_bytes + 32 + 15) & ~(size_t)15) +
+                      (((size_t)max_window_rows * hpitch + 15) & ~(size_t)15) + 768 * 4 + (size_t)out_w * 4 +
+                      (size_t)out_w * x_taps * 2 + 16;
+  if (smem > 227 * 1024) return SIA_E_UNSUPPORTED;
+
+  TvParams p;
+  p.src = src; p.x_min = x_min; p.x_w = x_w_tapmajor; p.y_min = y_min; p.y_w = y_w; p.lut = lut_3x256; p.dst = dst;
+  p.batch = batch; p.src_h = src_h; p.src_w = src_w; p.out_h = out_h; p.out_w = out_w;
+  p.x_taps = x_taps; p.y_taps = y_taps; p.x_prec = x_prec; p.y_prec = y_prec;
+  p.tile_rows = tile_rows; p.max_rows = max_window_rows;
+  const dim3 grid((out_h + tile_rows - 1) / tile_rows, batch);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static int configured[3] = {0, 0, 0};
+  if (layout == SIA_LAYOUT_NCHW_F32) {
+    if (int rc = ensure_dynamic_smem(preprocess_tv_kernel<SIA_LAYOUT_NCHW_F32>, (int)smem, &configured[0])) return rc;
+    preprocess_tv_kernel<SIA_LAYOUT_NCHW_F32><<<grid, TV_THREADS, smem, st>>>(p);
+  } else if (layout == SIA_LAYOUT_NCHW_BF16) {
+    if (int rc = ensure_dynamic_smem(preprocess_tv_kernel<SIA_LAYOUT_NCHW_BF16>, (int)smem, &configured[1])) return rc;
+    preprocess_tv_kernel<SIA_LAYOUT_NCHW_BF16><<<grid, TV_THREADS, smem, st>>>(p);
+  } else {
+    if (int rc = ensure_dynamic_smem(preprocess_tv_kernel<SIA_LAYOUT_NHWC4_BF16>, (int)smem, &configured[2])) return rc;
+    preprocess_tv_kernel<SIA_LAYOUT_NHWC4_BF16><<<grid, TV_THREADS, smem, st>>>(p);
+  }
+  return launch_status();
+}

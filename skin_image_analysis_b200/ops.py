@@ -126,6 +126,53 @@ def preprocess_u8hwc(src: torch.Tensor, size, layout: int = LAYOUT_NCHW_F32, mea
     return out
 
 
+class _DeviceTvTables:
+    def __init__(self, src_h, src_w, out_h, out_w, mean, std, device):
+        self.x = _rw.tv_axis(src_w, out_w)
+        self.y = _rw.tv_axis(src_h, out_h)
+        self.tile_rows, self.max_rows = _rw.tv_tile_plan(self.y, src_w * 3, out_w, self.x.taps)
+        self.x_min = torch.from_numpy(self.x.xmin).to(device)
+        self.x_w = torch.from_numpy(np.ascontiguousarray(self.x.w.T)).to(device)      # tap-major
+        self.y_min = torch.from_numpy(self.y.xmin).to(device)
+        self.y_w = torch.from_numpy(self.y.w).to(device)
+        self.lut = torch.from_numpy(_rw.tv_normalise_lut(mean, std)).to(device)
+
+
+@lru_cache(maxsize=64)
+def _tv_tables(device_index: int, src_h: int, src_w: int, out_h: int, out_w: int, mean: tuple, std: tuple):
+    return _DeviceTvTables(src_h, src_w, out_h, out_w, mean, std, torch.device("cuda", device_index))
+
+
+IMAGENET_MEAN = (0.485, 0.456, 0.406)      # notebooks/ToneClassifier/CNNTrialDataset.py:73
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def preprocess_tv_u8hwc(src: torch.Tensor, size=(224, 224), layout: int = LAYOUT_NCHW_F32, mean=IMAGENET_MEAN,
+                        std=IMAGENET_STD, out: torch.Tensor | None = None) -> torch.Tensor:
+    """[B,H,W,3] uint8 decode buffers -> the ToneClassifier test transform (CNNTrialDataset.py:71-76):
+    ``v2.Resize(size)`` on uint8 (bilinear, antialias: ATen's fixed-point resampler, uint8 after each axis) ->
+    ``v2.ToDtype(float32, scale=True)`` -> ``v2.Normalize(mean, std)``.  Bit-exact with torchvision for the float32
+    layout (integer taps + a 3 x 256 table of the float32 normalisation); the bf16 layouts round that value once."""
+    _need(src, torch.uint8, "src")
+    if src.dim() != 4 or src.shape[3] != 3:
+        raise ValueError("src must be [B,H,W,3] uint8")
+    b, sh, sw, _ = src.shape
+    oh, ow = int(size[0]), int(size[1])
+    tab = _tv_tables(src.device.index, sh, sw, oh, ow, tuple(float(m) for m in mean), tuple(float(v) for v in std))
+    shape = (b, oh, ow + NHWC4_PAD, 4) if layout == LAYOUT_NHWC4_BF16 else (b, 3, oh, ow)
+    if out is None:
+        out = torch.empty(shape, dtype=_LAYOUT_DTYPE[layout], device=src.device)
+    else:
+        _need(out, _LAYOUT_DTYPE[layout], "out")
+        if tuple(out.shape) != shape:
+            raise ValueError(f"out must have shape {shape}")
+    check(_lib.load().sia_preprocess_tv_u8hwc(
+        ptr(src), b, sh, sw, ptr(tab.x_min), ptr(tab.x_w), tab.x.taps, tab.x.precision, ptr(tab.y_min), ptr(tab.y_w),
+        tab.y.taps, tab.y.precision, ptr(tab.lut), oh, ow, tab.tile_rows, tab.max_rows, layout, ptr(out),
+        stream_ptr()), "sia_preprocess_tv_u8hwc")
+    return out
+
+
 def nchw_f32_to_nhwc4(x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
     _need(x, torch.float32, "x")
     b, c, h, w = x.shape

@@ -13,6 +13,8 @@ from __future__ import annotations
 
 from dataclasses import dataclass
 
+import math
+
 import numpy as np
 
 N_SLOTS = 4          # accumulator slots of the kernel's vertical pass (PRE_SLOTS)
@@ -354,3 +356,93 @@ def tc_emulate(u8: np.ndarray, t: TcTables, out_h: int, out_w: int, scale: float
                 out[tile * t.tile_rows: tile * t.tile_rows + lanes, emit] = o
             acc[:, i % N_SLOTS] = 0
     return out
+
+
+# -------------------------------------------------------------------------------------------------
+# Tables of the torchvision-variant kernel (csrc/preprocess_tv.cu): ATen's fixed-point antialias resampler
+# -------------------------------------------------------------------------------------------------
+@dataclass
+class TvAxis:
+    xmin: np.ndarray        # int32 [n_out]: first source index of every output sample's window
+    w: np.ndarray           # int16 [n_out, taps]: taps scaled by 2^precision (zero padded)
+    taps: int
+    precision: int
+
+
+def tv_axis(n_in: int, n_out: int) -> TvAxis:
+    """One axis of ``torch.nn.functional.interpolate(mode="bilinear", antialias=True)`` on uint8 -- the
+    resampler behind ``v2.Resize`` (notebooks/ToneClassifier/CNNTrialDataset.py:71).  Formulas of ATen's
+    ``_compute_indices_min_size_weights_aa`` / ``_compute_index_ranges_int16_weights``
+    (aten/src/ATen/native/cpu/UpSampleKernel.cpp): triangle filter of half width max(scale, 1) centred on
+    scale * (i + 0.5), weights normalised in float64, then rounded half away from zero to int16 at the largest
+    precision that keeps the biggest weight below 2^15.  An axis that keeps its size is the identity (ATen skips
+    the pass).  Windows that would run past the last sample are shifted left and zero padded in front so that
+    xmin + taps <= n_in always holds (the kernel then needs no bounds checks)."""
+    if n_in < 1 or n_out < 1:
+        raise ValueError("sizes must be positive")
+    if n_in == n_out:
+        return TvAxis(np.arange(n_out, dtype=np.int32), np.full((n_out, 1), 1 << 14, np.int16), 1, 14)
+    scale = n_in / n_out
+    support = scale if scale >= 1.0 else 1.0
+    taps = int(math.ceil(support)) * 2 + 1
+    invscale = 1.0 / scale if scale >= 1.0 else 1.0
+    xmin = np.zeros(n_out, np.int32)
+    w = np.zeros((n_out, taps), np.float64)
+    sizes = np.zeros(n_out, np.int64)
+    wt_max = 0.0
+    for i in range(n_out):
+        centre = scale * (i + 0.5)
+        lo = max(int(centre - support + 0.5), 0)
+        size = min(max(min(int(centre + support + 0.5), n_in) - lo, 0), taps)
+        vals = [max(0.0, 1.0 - abs((j + lo - centre + 0.5) * invscale)) for j in range(size)]
+        total = 0.0
+        for v in vals:
+            total += v
+        if total != 0.0:
+            for j in range(size):
+                w[i, j] = vals[j] / total
+            wt_max = max(wt_max, max(w[i, :size]))
+        xmin[i], sizes[i] = lo, size
+    prec = 0
+    while prec < 22 and int(0.5 + wt_max * (1 << (prec + 1))) < (1 << 15):
+        prec += 1
+    v = w * float(1 << prec)
+    wi = np.where(v < 0, np.trunc(v - 0.5), np.trunc(v + 0.5)).astype(np.int16)
+    if taps > n_in:                                   # tiny sources: the window is the whole axis
+        wi = wi[:, :n_in].copy()
+        taps = n_in
+    for i in range(n_out):
+        over = int(xmin[i]) + taps - n_in
+        if over > 0:
+            if np.any(wi[i, taps - over:] != 0):
+                raise ValueError("internal: non-zero taps past the edge")
+            wi[i] = np.concatenate([np.zeros(over, np.int16), wi[i, :taps - over]])
+            xmin[i] -= over
+    return TvAxis(xmin, np.ascontiguousarray(wi), taps, prec)
+
+
+def tv_normalise_lut(mean, std) -> np.ndarray:
+    """float32 [3, 256]: ``v2.ToDtype(float32, scale=True)`` then ``v2.Normalize(mean, std)`` of byte b in channel
+    c, with the same float32 operations (CNNTrialDataset.py:72-73), so a table lookup is bit-identical."""
+    b = np.arange(256, dtype=np.float32) * np.float32(1.0 / 255.0)
+    m = np.asarray(mean, np.float32).reshape(3, 1)
+    s = np.asarray(std, np.float32).reshape(3, 1)
+    return ((b[None, :] - m) / s).astype(np.float32)
+
+
+def tv_tile_plan(y: TvAxis, row_bytes: int, out_w: int, x_taps: int, budget: int = 100 * 1024) -> tuple[int, int]:
+    """(tile_rows, max_window_rows) of the kernel launch: the largest tile of 32/16/8/4/2/1 output rows whose
+    source window (plus the horizontal-pass buffer and tables) fits ``budget`` bytes of shared memory, so that
+    two CTAs share an SM; falls back to the 227 KB limit before giving up."""
+    n_out = y.xmin.shape[0]
+    hpitch = (out_w * 3 + 3) & ~3
+    for limit in (budget, 227 * 1024):
+        for tile in (32, 16, 8, 4, 2, 1):
+            rows = 0
+            for i0 in range(0, n_out, tile):
+                i1 = min(i0 + tile, n_out)
+                rows = max(rows, int(y.xmin[i1 - 1]) + y.taps - int(y.xmin[i0]))
+            smem = ((rows * row_bytes + 32 + 15) & ~15) + ((rows * hpitch + 15) & ~15) + 768 * 4 + out_w * 4 + out_w * x_taps * 2 + 16
+            if smem <= limit:
+                return tile, rows
+    raise ValueError("source rows too long for the shared-memory window of the torchvision-variant kernel")

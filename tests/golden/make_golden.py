@@ -17,6 +17,10 @@ What is pinned
                           (scikit-image itself is not installable here -- see oracle/__init__.py).
   * analysis_experiments.json : synthetic per-epoch result files + the reference's ``tone_bias_analysis``
                           outputs for them (read_experiment(s), transpose_dict, compute_ci; :12-39, :281-510).
+  * transform_tv.npz    : the ToneClassifier test transform -- the ``transforms`` Compose built by the reference's
+                          own ``ISIC(image_path, "Test")`` dataset (notebooks/ToneClassifier/CNNTrialDataset.py:71-76:
+                          v2.Resize((224,224)) -> v2.ToDtype(float32, scale=True) -> v2.Normalize(ImageNet)) applied
+                          to seeded u8 CHW tensors, run on the torch / torchvision of this image.
   * notebook_di.json    : hand-transcribed from the reference's saved notebook outputs
                           (notebooks/jgi_hiba_2022_torch.ipynb raw 3591-3617, 3643-3669, 3318-3322,
                           3433-3434, 3178); written by this script so the provenance is in one place.
@@ -125,6 +129,31 @@ def gen_transform(ref):
             arrays[name + "_sub"] = t[:, ::7, ::5].copy()
     del tf_tuple
     np.savez_compressed(os.path.join(HERE, "transform.npz"), **arrays)
+
+
+TV_CASES = [("noise_450x600", 450, 600, 41, "noise"), ("smooth_450x600", 450, 600, 42, "smooth"),
+            ("extremes_450x600", 450, 600, 43, "extremes"), ("noise_97x131", 97, 131, 44, "noise"),
+            ("noise_600x450", 600, 450, 45, "noise"), ("noise_160x200_up", 160, 200, 46, "noise")]
+
+
+def gen_transform_tv():
+    """The reference's own Compose, obtained by constructing its Dataset on a stub directory."""
+    import tempfile
+    sys.path.insert(0, "/root/reference/notebooks/ToneClassifier")
+    import CNNTrialDataset as ref_ds                                   # the reference module, unmodified
+    with tempfile.TemporaryDirectory() as d:
+        with open(os.path.join(d, "testmeta.csv"), "w") as f:
+            f.write("isic_id,fitzpatrick_skin_type\nISIC_0000000,II\n")
+        open(os.path.join(d, "ISIC_0000000.JPG"), "wb").close()
+        ds = ref_ds.ISIC(d, "Test")
+    arrays = {}
+    for name, h, w, seed, kind in TV_CASES:
+        u8 = helpers.synthetic_u8_image(h, w, seed, kind)
+        t = ds.transforms(torch.from_numpy(u8).permute(2, 0, 1).contiguous()).contiguous().numpy()
+        assert t.shape == (3, 224, 224) and t.dtype == np.float32
+        arrays[name + "_sum"] = np.array([t.astype(np.float64).sum()])
+        arrays[name + "_sub"] = t[:, ::5, ::3].copy()
+    np.savez_compressed(os.path.join(HERE, "transform_tv.npz"), **arrays)
 
 
 def gen_notebook():
@@ -237,6 +266,7 @@ def main():
     gen_experiments(ref)
     gen_analysis(ref)
     gen_transform(ref)
+    gen_transform_tv()
     gen_model(ref)
     print("golden fixtures written to", HERE)
 
