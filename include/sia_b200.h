@@ -112,11 +112,12 @@ int sia_preprocess_tc_u8hwc(const uint8_t* src, int batch, int src_h, int src_w,
  * x_min[j] + x_taps <= src_w and y_min[i] + y_taps <= src_h for every j, i (the builder shifts windows that
  * would run off the edge and zero-pads their weights).  One CTA produces tile_rows output rows of one image from
  * at most max_window_rows source rows staged in shared memory (SIA_E_UNSUPPORTED if that exceeds 227 KB).
- * layout: SIA_LAYOUT_* as for sia_preprocess_u8hwc. */
+ * layout: SIA_LAYOUT_* as for sia_preprocess_u8hwc.  planar_chw != 0: src is [B,3,H,W] uint8 (what
+ * torchvision.io.read_image / decode_jpeg produce, CNNTrialDataset.py:93) instead of [B,H,W,3]. */
 int sia_preprocess_tv_u8hwc(const uint8_t* src, int batch, int src_h, int src_w, const int32_t* x_min,
                             const int16_t* x_w_tapmajor, int x_taps, int x_prec, const int32_t* y_min,
                             const int16_t* y_w, int y_taps, int y_prec, const float* lut_3x256, int out_h, int out_w,
-                            int tile_rows, int max_window_rows, int layout, void* dst, void* stream);
+                            int tile_rows, int max_window_rows, int layout, int planar_chw, void* dst, void* stream);
 
 /* Model boundary: NCHW fp32 [B,3,h,w] (the tensor the reference DataLoader feeds to model(images),
  * src/tone_bias_test.py:190-196) -> padded NHWC4 bf16 [B,h,w+8,4] (SIA_LAYOUT_NHWC4_BF16). */

@@ -130,7 +130,9 @@ head_tail_kernel(const float* __restrict__ partial, int splits, int M, int n1, i
                  const float* __restrict__ b3, float* __restrict__ logp, uint8_t* __restrict__ pred,
                  const uint8_t* __restrict__ label, const uint8_t* __restrict__ groups, int groups_stride, int n_attr,
                  int n_groups, unsigned long long* __restrict__ counts) {
-  __shared__ float h1[TAIL_IMGS][TAIL_MAX_N1];
+  static_assert(TAIL_IMGS == 4, "h1 is stored as one float4 per k (x, y, z, w = the CTA's four images)");
+  __shared__ float4 h1v[TAIL_MAX_N1];                // [k] -> the four images: one LDS.128 per weight in fc2
+  float* h1 = reinterpret_cast<float*>(h1v);         // h1[k * 4 + img]
   __shared__ float h2p[2][TAIL_IMGS][TAIL_MAX_N2];   // the two K-halves of fc2
   __shared__ float z[TAIL_IMGS][2];
   const int m0 = blockIdx.x * TAIL_IMGS;
@@ -160,7 +162,7 @@ head_tail_kernel(const float* __restrict__ partial, int splits, int M, int n1, i
       for (; sp < splits; ++sp) s += __ldg(src + (size_t)sp * step);
       s = fmaxf(s + b1[k], 0.f);
     }
-    h1[img][k] = s;
+    h1[k * TAIL_IMGS + img] = s;
   }
   __syncthreads();
 
@@ -181,8 +183,11 @@ head_tail_kernel(const float* __restrict__ partial, int splits, int M, int n1, i
         for (int u = 0; u < 32; ++u) w[u] = __ldg(w2t + (size_t)(k + u) * n2 + j);
 #pragma unroll
         for (int u = 0; u < 32; ++u) {
-#pragma unroll
-          for (int img = 0; img < TAIL_IMGS; ++img) a[img] = fmaf(w[u], h1[img][k + u], a[img]);
+          const float4 hv = h1v[k + u];
+          a[0] = fmaf(w[u], hv.x, a[0]);
+          a[1] = fmaf(w[u], hv.y, a[1]);
+          a[2] = fmaf(w[u], hv.z, a[2]);
+          a[3] = fmaf(w[u], hv.w, a[3]);
         }
       }
       for (; k + 8 <= k_hi; k += 8) {
@@ -191,14 +196,17 @@ head_tail_kernel(const float* __restrict__ partial, int splits, int M, int n1, i
         for (int u = 0; u < 8; ++u) w[u] = w2t[(size_t)(k + u) * n2 + j];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-#pragma unroll
-          for (int img = 0; img < TAIL_IMGS; ++img) a[img] = fmaf(w[u], h1[img][k + u], a[img]);
+          const float4 hv = h1v[k + u];
+          a[0] = fmaf(w[u], hv.x, a[0]);
+          a[1] = fmaf(w[u], hv.y, a[1]);
+          a[2] = fmaf(w[u], hv.z, a[2]);
+          a[3] = fmaf(w[u], hv.w, a[3]);
         }
       }
       for (; k < k_hi; ++k) {
         const float w = w2t[(size_t)k * n2 + j];
 #pragma unroll
-        for (int img = 0; img < TAIL_IMGS; ++img) a[img] = fmaf(w, h1[img][k], a[img]);
+        for (int img = 0; img < TAIL_IMGS; ++img) a[img] = fmaf(w, h1[k * TAIL_IMGS + img], a[img]);
       }
 #pragma unroll
       for (int img = 0; img < TAIL_IMGS; ++img) h2p[half][img][j] = a[img];

@@ -39,9 +39,30 @@ struct TvParams {
   int batch, src_h, src_w, out_h, out_w;
   int x_taps, y_taps, x_prec, y_prec;
   int tile_rows, max_rows;          // output rows per CTA; capacity (source rows) of the shared window
+  int planar;                       // 0: src is [B,H,W,3] (HWC); 1: src is [B,3,H,W] (planar CHW)
 };
 
+__host__ __device__ inline size_t tv_rows_bytes(int max_rows, int src_w, int planar) {
+  return planar ? 3 * (((size_t)max_rows * src_w + 31) & ~(size_t)15) : (((size_t)max_rows * src_w * 3 + 32 + 15) & ~(size_t)15);
+}
+
 __device__ __forceinline__ int clamp_u8(int v) { return min(max(v, 0), 255); }
+
+// Copies len bytes from global g into shared memory at dst16 (16-byte aligned) + (g & 15): the same misalignment
+// on both sides, so the body moves as aligned 16-byte vectors; returns where byte 0 landed.  All threads call it.
+__device__ __forceinline__ const uint8_t* stage_span(uint8_t* dst16, const uint8_t* g, uint32_t len) {
+  const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 15u);
+  uint8_t* s = dst16 + mis;
+  const uint32_t head = min(len, (16u - mis) & 15u);
+  const uint32_t nvec = (len - head) >> 4;
+  const uint32_t tail0 = head + (nvec << 4);
+  for (uint32_t b = threadIdx.x; b < head; b += TV_THREADS) s[b] = g[b];
+  const uint4* gv = reinterpret_cast<const uint4*>(g + head);
+  uint4* sv = reinterpret_cast<uint4*>(s + head);
+  for (uint32_t v = threadIdx.x; v < nvec; v += TV_THREADS) sv[v] = __ldg(gv + v);
+  for (uint32_t b = tail0 + threadIdx.x; b < len; b += TV_THREADS) s[b] = g[b];
+  return s;
+}
 
 template <int LAYOUT>
 __global__ void __launch_bounds__(TV_THREADS)
@@ -51,7 +72,7 @@ preprocess_tv_kernel(const __grid_constant__ TvParams p) {
   const int hrow = p.out_w * 3;
   const int hpitch = (hrow + 3) & ~3;
   uint8_t* s_rows = smem_tv;                                                  // max_rows * row_bytes + 32
-  uint8_t* s_h = s_rows + (((size_t)p.max_rows * row_bytes + 32 + 15) & ~(size_t)15);   // max_rows * hpitch
+  uint8_t* s_h = s_rows + tv_rows_bytes(p.max_rows, p.src_w, p.planar);                   // max_rows * hpitch
   float* s_lut = reinterpret_cast<float*>(s_h + (((size_t)p.max_rows * hpitch + 15) & ~(size_t)15));
   int32_t* s_xmin = reinterpret_cast<int32_t*>(s_lut + 768);
   int16_t* s_xw = reinterpret_cast<int16_t*>(s_xmin + p.out_w);
@@ -61,22 +82,22 @@ preprocess_tv_kernel(const __grid_constant__ TvParams p) {
   const int i1 = min(i0 + p.tile_rows, p.out_h);
   const int r0 = p.y_min[i0];
   const int rows = min(p.y_min[i1 - 1] + p.y_taps - r0, p.max_rows);
+  const uint8_t* s_plane[3];
 
-  // ---- stage the source window: [r0, r0 + rows) is one contiguous span of the decode buffer ---------------
-  const uint8_t* g = p.src + ((size_t)n * p.src_h + r0) * row_bytes;
-  const uint32_t len = (uint32_t)rows * row_bytes;
-  const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 15u);
-  uint8_t* s = s_rows + mis;                       // same misalignment: aligned global 16 bytes <-> aligned shared 16 bytes
-  const uint32_t head = min(len, (16u - mis) & 15u);
-  const uint32_t nvec = (len - head) >> 4;
-  const uint32_t tail0 = head + (nvec << 4);
-  for (uint32_t b = threadIdx.x; b < head; b += TV_THREADS) s[b] = g[b];
-  {
-    const uint4* gv = reinterpret_cast<const uint4*>(g + head);
-    uint4* sv = reinterpret_cast<uint4*>(s + head);
-    for (uint32_t v = threadIdx.x; v < nvec; v += TV_THREADS) sv[v] = __ldg(gv + v);
+  // ---- stage the source window: rows [r0, r0 + rows) are one contiguous span of the decode buffer (HWC) or one
+  //      span per colour plane (planar CHW input, what torchvision.io.read_image / decode_jpeg produce) ---------
+  int row_stride, px_stride;           // s_plane[c] + r * row_stride + x * px_stride = channel c of pixel (r0 + r, x)
+  if (p.planar) {
+    const uint32_t cap = ((uint32_t)p.max_rows * p.src_w + 31u) & ~15u;
+    for (int c = 0; c < 3; ++c)          // each plane keeps its own misalignment
+      s_plane[c] = stage_span(s_rows + c * cap, p.src + (((size_t)n * 3 + c) * p.src_h + r0) * p.src_w,
+                              (uint32_t)rows * p.src_w);
+    row_stride = p.src_w; px_stride = 1;
+  } else {
+    const uint8_t* s0 = stage_span(s_rows, p.src + ((size_t)n * p.src_h + r0) * row_bytes, (uint32_t)rows * row_bytes);
+    s_plane[0] = s0; s_plane[1] = s0 + 1; s_plane[2] = s0 + 2;
+    row_stride = row_bytes; px_stride = 3;
   }
-  for (uint32_t b = tail0 + threadIdx.x; b < len; b += TV_THREADS) s[b] = g[b];
   for (int k = threadIdx.x; k < 768; k += TV_THREADS) s_lut[k] = p.lut[k];
   for (int k = threadIdx.x; k < p.out_w; k += TV_THREADS) s_xmin[k] = p.x_min[k];
   for (int k = threadIdx.x; k < p.out_w * p.x_taps; k += TV_THREADS) s_xw[k] = p.x_w[k];
@@ -88,13 +109,14 @@ preprocess_tv_kernel(const __grid_constant__ TvParams p) {
     const int total = rows * p.out_w;
     for (int idx = threadIdx.x; idx < total; idx += TV_THREADS) {
       const int r = idx / p.out_w, j = idx - r * p.out_w;
-      const uint8_t* px = s + (size_t)r * row_bytes + 3 * s_xmin[j];
+      const size_t off = (size_t)r * row_stride + (size_t)px_stride * s_xmin[j];
+      const uint8_t *p0 = s_plane[0] + off, *p1 = s_plane[1] + off, *p2 = s_plane[2] + off;
       int a0 = half, a1 = half, a2 = half;
       for (int t = 0; t < p.x_taps; ++t) {
         const int w = s_xw[t * p.out_w + j];
-        a0 += w * px[3 * t];
-        a1 += w * px[3 * t + 1];
-        a2 += w * px[3 * t + 2];
+        a0 += w * p0[px_stride * t];
+        a1 += w * p1[px_stride * t];
+        a2 += w * p2[px_stride * t];
       }
       uint8_t* h = s_h + (size_t)r * hpitch + 3 * j;
       h[0] = (uint8_t)clamp_u8(a0 >> p.x_prec);
@@ -154,8 +176,8 @@ preprocess_tv_kernel(const __grid_constant__ TvParams p) {
 extern "C" int sia_preprocess_tv_u8hwc(const uint8_t* src, int batch, int src_h, int src_w, const int32_t* x_min,
                                        const int16_t* x_w_tapmajor, int x_taps, int x_prec, const int32_t* y_min,
                                        const int16_t* y_w, int y_taps, int y_prec, const float* lut_3x256, int out_h,
-                                       int out_w, int tile_rows, int max_window_rows, int layout, void* dst,
-                                       void* stream) {
+                                       int out_w, int tile_rows, int max_window_rows, int layout, int planar_chw,
+                                       void* dst, void* stream) {
   using namespace sia;
   SIA_REQUIRE(src && x_min && x_w_tapmajor && y_min && y_w && lut_3x256 && dst);
   SIA_REQUIRE(batch >= 1 && src_h >= 1 && src_w >= 1 && out_h >= 1 && out_w >= 1);
@@ -163,9 +185,8 @@ extern "C" int sia_preprocess_tv_u8hwc(const uint8_t* src, int batch, int src_h,
   SIA_REQUIRE(tile_rows >= 1 && max_window_rows >= y_taps && max_window_rows <= src_h);
   SIA_REQUIRE(layout == SIA_LAYOUT_NCHW_F32 || layout == SIA_LAYOUT_NCHW_BF16 || layout == SIA_LAYOUT_NHWC4_BF16);
   if (batch > 65535) return SIA_E_UNSUPPORTED;
-  const size_t row_bytes = (size_t)src_w * 3;
   const size_t hpitch = ((size_t)out_w * 3 + 3) & ~(size_t)3;
-  const size_t smem = (((size_t)max_window_rows * row_bytes + 32 + 15) & ~(size_t)15) +
+  const size_t smem = tv_rows_bytes(max_window_rows, src_w, planar_chw) +
                       (((size_t)max_window_rows * hpitch + 15) & ~(size_t)15) + 768 * 4 + (size_t)out_w * 4 +
                       (size_t)out_w * x_taps * 2 + 16;
   if (smem > 227 * 1024) return SIA_E_UNSUPPORTED;
@@ -174,7 +195,7 @@ extern "C" int sia_preprocess_tv_u8hwc(const uint8_t* src, int batch, int src_h,
   p.src = src; p.x_min = x_min; p.x_w = x_w_tapmajor; p.y_min = y_min; p.y_w = y_w; p.lut = lut_3x256; p.dst = dst;
   p.batch = batch; p.src_h = src_h; p.src_w = src_w; p.out_h = out_h; p.out_w = out_w;
   p.x_taps = x_taps; p.y_taps = y_taps; p.x_prec = x_prec; p.y_prec = y_prec;
-  p.tile_rows = tile_rows; p.max_rows = max_window_rows;
+  p.tile_rows = tile_rows; p.max_rows = max_window_rows; p.planar = planar_chw ? 1 : 0;
   const dim3 grid((out_h + tile_rows - 1) / tile_rows, batch);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   static int configured[3] = {0, 0, 0};

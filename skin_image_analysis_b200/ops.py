@@ -148,15 +148,16 @@ IMAGENET_STD = (0.229, 0.224, 0.225)
 
 
 def preprocess_tv_u8hwc(src: torch.Tensor, size=(224, 224), layout: int = LAYOUT_NCHW_F32, mean=IMAGENET_MEAN,
-                        std=IMAGENET_STD, out: torch.Tensor | None = None) -> torch.Tensor:
-    """[B,H,W,3] uint8 decode buffers -> the ToneClassifier test transform (CNNTrialDataset.py:71-76):
+                        std=IMAGENET_STD, out: torch.Tensor | None = None, planar: bool = False) -> torch.Tensor:
+    """[B,H,W,3] uint8 decode buffers (``planar=True``: [B,3,H,W], what ``torchvision.io.read_image`` returns,
+    CNNTrialDataset.py:93) -> the ToneClassifier test transform (CNNTrialDataset.py:71-76):
     ``v2.Resize(size)`` on uint8 (bilinear, antialias: ATen's fixed-point resampler, uint8 after each axis) ->
     ``v2.ToDtype(float32, scale=True)`` -> ``v2.Normalize(mean, std)``.  Bit-exact with torchvision for the float32
     layout (integer taps + a 3 x 256 table of the float32 normalisation); the bf16 layouts round that value once."""
     _need(src, torch.uint8, "src")
-    if src.dim() != 4 or src.shape[3] != 3:
-        raise ValueError("src must be [B,H,W,3] uint8")
-    b, sh, sw, _ = src.shape
+    if src.dim() != 4 or src.shape[1 if planar else 3] != 3:
+        raise ValueError("src must be [B,H,W,3] uint8 ([B,3,H,W] with planar=True)")
+    b, sh, sw = (src.shape[0], src.shape[2], src.shape[3]) if planar else src.shape[:3]
     oh, ow = int(size[0]), int(size[1])
     tab = _tv_tables(src.device.index, sh, sw, oh, ow, tuple(float(m) for m in mean), tuple(float(v) for v in std))
     shape = (b, oh, ow + NHWC4_PAD, 4) if layout == LAYOUT_NHWC4_BF16 else (b, 3, oh, ow)
@@ -168,8 +169,8 @@ def preprocess_tv_u8hwc(src: torch.Tensor, size=(224, 224), layout: int = LAYOUT
             raise ValueError(f"out must have shape {shape}")
     check(_lib.load().sia_preprocess_tv_u8hwc(
         ptr(src), b, sh, sw, ptr(tab.x_min), ptr(tab.x_w), tab.x.taps, tab.x.precision, ptr(tab.y_min), ptr(tab.y_w),
-        tab.y.taps, tab.y.precision, ptr(tab.lut), oh, ow, tab.tile_rows, tab.max_rows, layout, ptr(out),
-        stream_ptr()), "sia_preprocess_tv_u8hwc")
+        tab.y.taps, tab.y.precision, ptr(tab.lut), oh, ow, tab.tile_rows, tab.max_rows, layout, int(bool(planar)),
+        ptr(out), stream_ptr()), "sia_preprocess_tv_u8hwc")
     return out
 
 

@@ -88,3 +88,21 @@ def test_model_consumes_the_tv_layout():
     logp, pred = plan.forward_nhwc4(x4)
     torch.cuda.synchronize()
     assert logp.shape == (4, 2) and torch.isfinite(logp).all()
+
+
+@pytest.mark.parametrize("shape", [(450, 600), (97, 131), (33, 47)])
+def test_planar_chw_input_like_read_image(shape):
+    """The drop-in surface: uint8 CHW tensors (torchvision.io.read_image, CNNTrialDataset.py:93-95)."""
+    from skin_image_analysis_b200.cnn_trial_dataset import TestTransforms
+    rng = np.random.default_rng(21)
+    u8 = rng.integers(0, 256, (3,) + shape + (3,), dtype=np.uint8)
+    chw = torch.from_numpy(u8).permute(0, 3, 1, 2).contiguous().cuda()
+    tf = TestTransforms()
+    got = tf(chw).cpu().numpy()
+    for n in range(3):
+        assert np.array_equal(got[n], R.transform_u8_chw(u8[n])), n
+    one = tf(chw[2]).cpu().numpy()                                   # a single [3,H,W] image, misaligned base
+    assert one.shape == (3, 224, 224) and np.array_equal(one, got[2])
+    assert np.array_equal(tf.hwc(torch.from_numpy(u8).cuda()).cpu().numpy(), got)
+    with pytest.raises(TypeError):
+        tf(chw.float())

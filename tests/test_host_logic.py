@@ -187,3 +187,19 @@ def test_tensor_core_tables_reject_unsupported_geometry():
     for shape in ((97, 131, 64, 86), (1024, 1024, 224, 224), (64, 64, 128, 128), (450, 601, 224, 224)):
         with pytest.raises(ValueError):
             rw.build_tc_tables(*shape)
+
+
+def test_tone_classifier_surface_on_cpu():
+    """cnn_trial_dataset mirrors notebooks/ToneClassifier/CNNTrialDataset.py: the label converter (:11-25) and a
+    transform that refuses CPU tensors instead of falling back."""
+    import torch
+    from skin_image_analysis_b200 import _lib
+    from skin_image_analysis_b200.cnn_trial_dataset import TestTransforms, fitzpatrick_converter
+    assert [fitzpatrick_converter(t) for t in ("I", "II", "III", "IV", "V", "VI")] == [0, 0, 1, 1, 1, 1]
+    assert fitzpatrick_converter("VII") == "Error" and fitzpatrick_converter(float("nan")) == "Error"
+    tf = TestTransforms()
+    with pytest.raises(TypeError):
+        tf(torch.zeros(3, 8, 8))
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.SiaError):
+            tf(torch.zeros(3, 8, 8, dtype=torch.uint8))
