@@ -64,7 +64,8 @@ __device__ __forceinline__ const uint8_t* stage_span(uint8_t* dst16, const uint8
   return s;
 }
 
-template <int LAYOUT>
+// XT / YT: compile-time tap counts (fully unrolled passes, horizontal taps held in registers) or 0 = run-time loops.
+template <int LAYOUT, int XT, int YT>
 __global__ void __launch_bounds__(TV_THREADS)
 preprocess_tv_kernel(const __grid_constant__ TvParams p) {
   extern __shared__ __align__(128) uint8_t smem_tv[];
@@ -104,7 +105,32 @@ preprocess_tv_kernel(const __grid_constant__ TvParams p) {
   __syncthreads();
 
   // ---- horizontal pass: every staged source row -> out_w uint8 pixels -------------------------------------
-  {
+  if constexpr (XT > 0) {
+    // thread = (output column, row group): the column's taps and window offset stay in registers for all rows
+    constexpr int COLS = 256, GROUPS = TV_THREADS / COLS;
+    const int half = 1 << (p.x_prec - 1);
+    const int grp = threadIdx.x / COLS;
+    for (int j = threadIdx.x % COLS; j < p.out_w; j += COLS) {
+      int w[XT];
+#pragma unroll
+      for (int t = 0; t < XT; ++t) w[t] = s_xw[t * p.out_w + j];
+      const size_t off0 = (size_t)px_stride * s_xmin[j];
+      for (int r = grp; r < rows; r += GROUPS) {
+        const size_t off = (size_t)r * row_stride + off0;
+        const uint8_t *p0 = s_plane[0] + off, *p1 = s_plane[1] + off, *p2 = s_plane[2] + off;
+        int v0[XT], v1[XT], v2[XT];
+#pragma unroll
+        for (int t = 0; t < XT; ++t) { v0[t] = p0[px_stride * t]; v1[t] = p1[px_stride * t]; v2[t] = p2[px_stride * t]; }
+        int a0 = half, a1 = half, a2 = half;
+#pragma unroll
+        for (int t = 0; t < XT; ++t) { a0 += w[t] * v0[t]; a1 += w[t] * v1[t]; a2 += w[t] * v2[t]; }
+        uint8_t* h = s_h + (size_t)r * hpitch + 3 * j;
+        h[0] = (uint8_t)clamp_u8(a0 >> p.x_prec);
+        h[1] = (uint8_t)clamp_u8(a1 >> p.x_prec);
+        h[2] = (uint8_t)clamp_u8(a2 >> p.x_prec);
+      }
+    }
+  } else {
     const int half = 1 << (p.x_prec - 1);
     const int total = rows * p.out_w;
     for (int idx = threadIdx.x; idx < total; idx += TV_THREADS) {
@@ -136,11 +162,22 @@ preprocess_tv_kernel(const __grid_constant__ TvParams p) {
       const uint8_t* h = s_h + (size_t)(p.y_min[i] - r0) * hpitch + 3 * j;
       const int16_t* yw = p.y_w + (size_t)i * p.y_taps;
       int a0 = half, a1 = half, a2 = half;
-      for (int t = 0; t < p.y_taps; ++t) {
-        const int w = __ldg(yw + t);
-        a0 += w * h[(size_t)t * hpitch];
-        a1 += w * h[(size_t)t * hpitch + 1];
-        a2 += w * h[(size_t)t * hpitch + 2];
+      if constexpr (YT > 0) {
+        int w[YT], v0[YT], v1[YT], v2[YT];
+#pragma unroll
+        for (int t = 0; t < YT; ++t) {
+          w[t] = __ldg(yw + t);
+          v0[t] = h[(size_t)t * hpitch]; v1[t] = h[(size_t)t * hpitch + 1]; v2[t] = h[(size_t)t * hpitch + 2];
+        }
+#pragma unroll
+        for (int t = 0; t < YT; ++t) { a0 += w[t] * v0[t]; a1 += w[t] * v1[t]; a2 += w[t] * v2[t]; }
+      } else {
+        for (int t = 0; t < p.y_taps; ++t) {
+          const int w = __ldg(yw + t);
+          a0 += w * h[(size_t)t * hpitch];
+          a1 += w * h[(size_t)t * hpitch + 1];
+          a2 += w * h[(size_t)t * hpitch + 2];
+        }
       }
       const float f0 = s_lut[clamp_u8(a0 >> p.y_prec)];
       const float f1 = s_lut[256 + clamp_u8(a1 >> p.y_prec)];
@@ -198,16 +235,21 @@ extern "C" int sia_preprocess_tv_u8hwc(const uint8_t* src, int batch, int src_h,
   p.tile_rows = tile_rows; p.max_rows = max_window_rows; p.planar = planar_chw ? 1 : 0;
   const dim3 grid((out_h + tile_rows - 1) / tile_rows, batch);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  static int configured[3] = {0, 0, 0};
+  // 7 x 7 taps = down-sampling by 2..3 on both axes (600x450 -> 224x224, the case the transform is used for)
+  const bool unrolled = x_taps == 7 && y_taps == 7;
+  static int configured[6] = {0, 0, 0, 0, 0, 0};
+#define SIA_TV_LAUNCH(LAYOUT, XT, YT, SLOT)                                                                  \
+  do {                                                                                                       \
+    if (int rc = ensure_dynamic_smem(preprocess_tv_kernel<LAYOUT, XT, YT>, (int)smem, &configured[SLOT])) return rc; \
+    preprocess_tv_kernel<LAYOUT, XT, YT><<<grid, TV_THREADS, smem, st>>>(p);                                  \
+  } while (0)
   if (layout == SIA_LAYOUT_NCHW_F32) {
-    if (int rc = ensure_dynamic_smem(preprocess_tv_kernel<SIA_LAYOUT_NCHW_F32>, (int)smem, &configured[0])) return rc;
-    preprocess_tv_kernel<SIA_LAYOUT_NCHW_F32><<<grid, TV_THREADS, smem, st>>>(p);
+    if (unrolled) SIA_TV_LAUNCH(SIA_LAYOUT_NCHW_F32, 7, 7, 0); else SIA_TV_LAUNCH(SIA_LAYOUT_NCHW_F32, 0, 0, 1);
   } else if (layout == SIA_LAYOUT_NCHW_BF16) {
-    if (int rc = ensure_dynamic_smem(preprocess_tv_kernel<SIA_LAYOUT_NCHW_BF16>, (int)smem, &configured[1])) return rc;
-    preprocess_tv_kernel<SIA_LAYOUT_NCHW_BF16><<<grid, TV_THREADS, smem, st>>>(p);
+    if (unrolled) SIA_TV_LAUNCH(SIA_LAYOUT_NCHW_BF16, 7, 7, 2); else SIA_TV_LAUNCH(SIA_LAYOUT_NCHW_BF16, 0, 0, 3);
   } else {
-    if (int rc = ensure_dynamic_smem(preprocess_tv_kernel<SIA_LAYOUT_NHWC4_BF16>, (int)smem, &configured[2])) return rc;
-    preprocess_tv_kernel<SIA_LAYOUT_NHWC4_BF16><<<grid, TV_THREADS, smem, st>>>(p);
+    if (unrolled) SIA_TV_LAUNCH(SIA_LAYOUT_NHWC4_BF16, 7, 7, 4); else SIA_TV_LAUNCH(SIA_LAYOUT_NHWC4_BF16, 0, 0, 5);
   }
+#undef SIA_TV_LAUNCH
   return launch_status();
 }
