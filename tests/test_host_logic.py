@@ -34,6 +34,26 @@ def test_library_exports_every_declared_symbol():
     assert lib.sia_pack_conv3x3_bytes(64, 128) == 9 * 64 * 128 * 2
 
 
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Every prototype of include/sia_b200.h against _lib.SIGNATURES: same number of parameters, pointers bound
+    as pointers and integers as integers (a missing argument shifts the stream handle and crashes on the GPU box)."""
+    import ctypes
+    from skin_image_analysis_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "sia_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    protos = re.findall(r"\b(sia_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S)
+    assert len(protos) == len(_lib.SIGNATURES)
+    for name, params in protos:
+        params = " ".join(params.split())
+        plist = [] if params in ("", "void") else [q.strip() for q in params.split(",")]
+        _res, args = _lib.SIGNATURES[name]
+        assert len(plist) == len(args), f"{name}: header has {len(plist)} parameters, _lib binds {len(args)}"
+        for q, a in zip(plist, args):
+            is_ptr = "*" in q
+            bound_ptr = a is ctypes.c_void_p or a is ctypes.c_char_p or isinstance(a, type(ctypes.POINTER(ctypes.c_int)))
+            assert is_ptr == bound_ptr, f"{name}: parameter '{q}' bound as {a}"
+
+
 @pytest.mark.parametrize("shape", [(450, 600, 224, 224), (450, 600, 512, 512), (97, 131, 64, 86), (600, 450, 298, 224)])
 def test_resize_tables_equal_oracle_operator(shape):
     from skin_image_analysis_b200 import resize_weights as rw
