@@ -119,6 +119,10 @@ int sia_preprocess_tv_u8hwc(const uint8_t* src, int batch, int src_h, int src_w,
                             const int16_t* y_w, int y_taps, int y_prec, const float* lut_3x256, int out_h, int out_w,
                             int tile_rows, int max_window_rows, int layout, int planar_chw, void* dst, void* stream);
 
+/* Debug / A-B: on != 0 makes sia_preprocess_tv_u8hwc use its byte-wise kernel even where the IDP.2A instance
+ * applies (the two must agree bit for bit; tests compare them). */
+int sia_debug_tv_force_generic(int on);
+
 /* Model boundary: NCHW fp32 [B,3,h,w] (the tensor the reference DataLoader feeds to model(images),
  * src/tone_bias_test.py:190-196) -> padded NHWC4 bf16 [B,h,w+8,4] (SIA_LAYOUT_NHWC4_BF16). */
 int sia_nchw_f32_to_nhwc4_bf16(const float* src, int batch, int h, int w, void* dst, void* stream);

@@ -112,7 +112,11 @@ class EvalEngine:
                 self._launch_all(slot)
 
     def load_slot(self, slot: int, u8, label, groups):
-        """Asynchronous copy (host pinned or device source) into an input slot on the copy stream."""
+        """Asynchronous copy (host pinned or device source) into an input slot on the copy stream.  Device sources
+        may still be being written by work queued on the caller's current stream: the copy is ordered after it."""
+        with torch.cuda.device(self.device):
+            if any(isinstance(t, torch.Tensor) and t.is_cuda for t in (u8, label, groups)):
+                self.copy_stream.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.device(self.device), torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self.slot_free[slot])
             self.u8[slot].copy_(u8, non_blocking=True)

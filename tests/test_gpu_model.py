@@ -319,3 +319,63 @@ def test_optuna_best_model_matches_reference_fixture_and_oracle(golden_dir):
     safe = (ref[:, 1] - ref[:, 0]).abs() > 2 * tol
     assert torch.equal(got.argmax(1)[safe], ref.argmax(1)[safe])
     assert 0 < int(ref.argmax(1).sum()) < 16
+
+
+def test_full_size_bench_config_properties():
+    """BASELINE configs[1] at FULL size (batch 256 of 600x450 uint8 images, SkinCancerListModel, bf16): the oracle
+    takes minutes there, so parity is checked through size-independent properties --
+      * sub-batch consistency: the same images evaluated as 8 batches of 32 (a size the oracle tests cover) give
+        the same log-probabilities (<= 1e-3: only the split-K summation order of fc1 changes) and the same labels
+        outside that band;
+      * permutation equivariance: reversing the batch reverses the outputs BIT FOR BIT (no cross-image coupling);
+      * the count tensor is the exact histogram of (label, prediction, group) recomputed on the host, its total
+        is the batch size, and accumulating two passes doubles it."""
+    from skin_image_analysis_b200.engine import EvalEngine
+    from skin_image_analysis_b200.synthetic import random_state_dict
+    batch = 256
+    state = random_state_dict(om.LIST_MODEL, 224, seed=0)
+    g = torch.Generator(device="cuda").manual_seed(17)
+    coarse = torch.rand((batch, 3, 15, 20), device="cuda", generator=g)
+    u8 = (torch.nn.functional.interpolate(coarse, size=(450, 600), mode="bilinear") * 255).round().clamp(0, 255)
+    u8 = (u8 + torch.randint(-8, 9, u8.shape, device="cuda", generator=g)).clamp(0, 255).to(torch.uint8)
+    u8 = u8.permute(0, 2, 3, 1).contiguous()                                  # image-like test data (setup only)
+    label, ftype, sex, control = helpers.counter_metadata(np.arange(batch), seed=4)
+    lab = torch.from_numpy(label).cuda()
+    grp = torch.from_numpy(np.stack([ftype, sex, control])).cuda()
+
+    big = EvalEngine(state, batch, n_slots=1)
+    big.step(u8, lab, grp)
+    big.synchronize()
+    logp, pred = big.logp.clone(), big.pred.clone()
+    shift = float((logp[:, 1] - logp[:, 0]).median())                        # centre the head: both classes occur
+    state[[k for k in state if k.endswith(".bias")][-1]][1] -= shift
+    big = EvalEngine(state, batch, n_slots=1)
+    big.step(u8, lab, grp)
+    big.synchronize()
+    logp, pred, counts = big.logp.clone(), big.pred.clone(), big.read_counts().clone()
+    assert 0 < int(pred.sum()) < batch
+
+    small = EvalEngine(state, 32, n_slots=1)
+    for k in range(batch // 32):
+        sl = slice(32 * k, 32 * k + 32)
+        small.step(u8[sl], lab[sl], grp[:, sl].contiguous())
+        small.synchronize()
+        d = (small.logp - logp[sl]).abs().max().item()
+        assert d <= 1e-3, (k, d)
+        safe = (logp[sl, 1] - logp[sl, 0]).abs() > 2e-3
+        assert torch.equal(small.pred[safe], pred[sl][safe])
+    assert int(small.read_counts()[0].sum()) == batch
+
+    big.reset_counts()
+    big.step(u8.flip(0).contiguous(), lab.flip(0).contiguous(), grp.flip(1).contiguous())
+    big.synchronize()
+    assert torch.equal(big.logp.flip(0), logp) and torch.equal(big.pred.flip(0), pred)
+    assert torch.equal(big.read_counts(), counts)
+
+    p, want = pred.cpu().numpy(), np.zeros((3, 6, 2, 2), np.int64)
+    for a, ids in enumerate((ftype, sex, control)):
+        np.add.at(want[a], (ids, label, p), 1)
+    assert np.array_equal(counts.cpu().numpy(), want) and int(counts[0].sum()) == batch
+    big.step(u8.flip(0).contiguous(), lab.flip(0).contiguous(), grp.flip(1).contiguous())
+    big.synchronize()
+    assert np.array_equal(big.read_counts().cpu().numpy(), 2 * want)

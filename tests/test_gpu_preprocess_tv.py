@@ -106,3 +106,31 @@ def test_planar_chw_input_like_read_image(shape):
     assert np.array_equal(tf.hwc(torch.from_numpy(u8).cuda()).cpu().numpy(), got)
     with pytest.raises(TypeError):
         tf(chw.float())
+
+
+def test_idp2a_instance_equals_bytewise_kernel():
+    """The IDP.2A instance (interleaved source, rows % 4 == 0, 7 x 7 taps) and the byte-wise kernel are the same
+    integer arithmetic: bit-identical outputs in every layout, on a batch with extreme bytes."""
+    from skin_image_analysis_b200 import _lib, ops
+    rng = np.random.default_rng(31)
+    u8 = rng.integers(0, 256, (5, 450, 600, 3), dtype=np.uint8)
+    u8[3] = helpers.synthetic_u8_image(450, 600, 43, "extremes")
+    u8[4] = 255
+    x = torch.from_numpy(u8).cuda()
+    lib = _lib.load()
+    for layout in (ops.LAYOUT_NCHW_F32, ops.LAYOUT_NCHW_BF16, ops.LAYOUT_NHWC4_BF16):
+        fast = ops.preprocess_tv_u8hwc(x, (224, 224), layout)
+        try:
+            lib.sia_debug_tv_force_generic(1)
+            slow = ops.preprocess_tv_u8hwc(x, (224, 224), layout)
+        finally:
+            lib.sia_debug_tv_force_generic(0)
+        assert torch.equal(fast, slow), layout
+    got = ops.preprocess_tv_u8hwc(x, (224, 224), ops.LAYOUT_NCHW_F32).cpu().numpy()
+    for n in (0, 3, 4):
+        assert np.array_equal(got[n], R.transform_u8_chw(u8[n])), n
+    # another size that takes the IDP.2A path (7 x 7 taps, 4-byte rows), tile boundaries elsewhere
+    v8 = rng.integers(0, 256, (2, 500, 560, 3), dtype=np.uint8)
+    g2 = ops.preprocess_tv_u8hwc(torch.from_numpy(v8).cuda(), (224, 224), ops.LAYOUT_NCHW_F32).cpu().numpy()
+    for n in range(2):
+        assert np.array_equal(g2[n], R.transform_u8_chw(v8[n])), n

@@ -29,7 +29,7 @@ if [[ " $WHAT " == *" tests "* ]]; then
   else
     MODEL_FILES="tests/test_gpu_model.py"
   fi
-  for f in tests/test_gpu_counts.py tests/test_gpu_preprocess.py tests/test_umma_i8_probe.py $MODEL_FILES; do
+  for f in tests/test_gpu_counts.py tests/test_gpu_preprocess.py tests/test_gpu_preprocess_tv.py tests/test_umma_i8_probe.py $MODEL_FILES; do
     timeout 900 python -m pytest "$f" -q -m gpu -p no:cacheprovider > $OUT/$(basename $f .py).log 2>&1
     echo "$? $f" >> $OUT/tests_summary.txt
     tail -60 $OUT/$(basename $f .py).log >> $OUT/tests_failures.txt
