@@ -122,6 +122,9 @@ class EvalEngine:
             self.u8[slot].copy_(u8, non_blocking=True)
             self.label[slot].copy_(label, non_blocking=True)
             self.groups[slot].copy_(groups, non_blocking=True)
+            for t in (u8, label, groups):                      # keep temporaries alive until the copy has read them
+                if isinstance(t, torch.Tensor) and t.is_cuda:
+                    t.record_stream(self.copy_stream)
             self.slot_ready[slot].record(self.copy_stream)
 
     def step_slot(self, slot: int):
