@@ -31,7 +31,10 @@ constexpr int C1_ROWB = C1_WIN_PX * 8;       // 192 bytes
 constexpr int C1_ROWS = C1_TILE_Y + 6;       // 38 input rows
 constexpr int C1_STAGE_BYTES = C1_ROWS * C1_ROWB;        // 7296
 constexpr int C1_STAGE_STRIDE = 7424;                    // 29 * 256
-constexpr int C1_NSTAGE = 4;
+#ifndef SIA_C1_NSTAGE
+#define SIA_C1_NSTAGE 4
+#endif
+constexpr int C1_NSTAGE = SIA_C1_NSTAGE;     // input-patch stages in flight (7.3 KB each)
 constexpr int C1_N = 128;
 constexpr int C1_K = 256;                    // 8 window rows * 32
 constexpr int C1_B_BYTES = C1_N * C1_K * 2;  // 65536
@@ -49,6 +52,10 @@ constexpr int C1_NACC = SIA_C1_NACC;         // TMEM accumulator ring (NACC x 12
 constexpr int C1_EPI_GROUPS = SIA_C1_EPI_GROUPS;
 constexpr int C1_THREADS = 128 + 128 * C1_EPI_GROUPS;  // warps 0-3 TMA / MMA / TMEM alloc / idle, then epilogue groups
 constexpr bool C1_BIAS_UMMA = SIA_C1_BIAS_UMMA != 0;
+#ifndef SIA_C1_MMA_WARPS
+#define SIA_C1_MMA_WARPS 2
+#endif
+constexpr int C1_MMA_WARPS = SIA_C1_MMA_WARPS;  // warps issuing UMMAs (alternate tiles): 1 = warp 1, 2 = warps 1 and 3
 constexpr int C1_BIAS_BYTES = C1_N * 32;
 
 struct TileWalker1 {
@@ -208,7 +215,7 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
       }
       wait_stage.store(0);
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || (C1_MMA_WARPS == 2 && warp == 3)) {
     // whole warp runs the uniform control flow; one elected lane issues UMMAs + commits
     constexpr uint32_t idesc = make_idesc_bf16(128, C1_N);
     // A: rows = pixel pairs 16 B apart, K-adjacent core matrix = next 2 pixels (LBO 16 B), next 8 rows =
@@ -221,14 +228,17 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
     const uint32_t ones_lo = desc_lo(smem_u32(smem_ones), 128);
     const uint32_t bias_lo = desc_lo(smem_u32(smem_biasop), 128);
     mbar_wait(wload_bar, 0, 31);
-    int stage = 0;
-    uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
+    // Two issuing warps (1 and 3) take alternate tiles: a wait on an mbarrier costs the issuing thread ~130 clocks
+    // even when the phase completed long ago (measured), and the tensor pipe's queue is too shallow to hide two of
+    // them per 17-instruction tile; with two issuers one warp's waits overlap the other's instruction stream.
+    // Tiles use disjoint stages / accumulators and every barrier is per tile, so no ordering between the two is
+    // needed (tcgen05.commit tracks the MMAs of the committing thread).
+    const int which = C1_MMA_WARPS == 2 ? (warp == 3 ? 1 : 0) : 0;
     RoleTimer wait_acc, wait_ops, loop;
     loop.begin();
-    int lt = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+    for (int lt = which; blockIdx.x + (long long)lt * gridDim.x < total_tiles; lt += C1_MMA_WARPS) {
+      const int stage = lt % C1_NSTAGE, acc = lt % C1_NACC;
+      const uint32_t phase = (uint32_t)(lt / C1_NSTAGE) & 1u, acc_phase = (uint32_t)(lt / C1_NACC) & 1u;
       wait_acc.begin();
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 32);
       wait_acc.end();
@@ -258,11 +268,9 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
       }
       __syncwarp();
       if (lane == 0) trace(lt, 4);
-      if (++stage == C1_NSTAGE) { stage = 0; phase ^= 1; }
-      if (++acc == C1_NACC) { acc = 0; acc_phase ^= 1; }
     }
     loop.end();
-    if (lane == 0) { wait_acc.store(1); wait_ops.store(2); loop.store(3); }
+    if (lane == 0 && warp == 1) { wait_acc.store(1); wait_ops.store(2); loop.store(3); }
   } else if (warp >= 4) {
     // epilogue: thread = one GEMM row = one pooled output pixel, 32 channels.  Two groups of four warps;
     // group g owns the tiles with local index j = g, g+2, ...
