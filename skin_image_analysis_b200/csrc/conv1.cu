@@ -53,9 +53,9 @@ constexpr int C1_EPI_GROUPS = SIA_C1_EPI_GROUPS;
 constexpr int C1_THREADS = 128 + 128 * C1_EPI_GROUPS;  // warps 0-3 TMA / MMA / TMEM alloc / idle, then epilogue groups
 constexpr bool C1_BIAS_UMMA = SIA_C1_BIAS_UMMA != 0;
 #ifndef SIA_C1_MMA_WARPS
-#define SIA_C1_MMA_WARPS 2
+#define SIA_C1_MMA_WARPS 3
 #endif
-constexpr int C1_MMA_WARPS = SIA_C1_MMA_WARPS;  // warps issuing UMMAs (alternate tiles): 1 = warp 1, 2 = warps 1 and 3
+constexpr int C1_MMA_WARPS = SIA_C1_MMA_WARPS;  // warps issuing UMMAs, tiles dealt round-robin: warps 1 .. C1_MMA_WARPS (<= 3)
 constexpr int C1_BIAS_BYTES = C1_N * 32;
 
 struct TileWalker1 {
@@ -215,7 +215,7 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
       }
       wait_stage.store(0);
     }
-  } else if (warp == 1 || (C1_MMA_WARPS == 2 && warp == 3)) {
+  } else if (warp >= 1 && warp <= C1_MMA_WARPS) {
     // whole warp runs the uniform control flow; one elected lane issues UMMAs + commits
     constexpr uint32_t idesc = make_idesc_bf16(128, C1_N);
     // A: rows = pixel pairs 16 B apart, K-adjacent core matrix = next 2 pixels (LBO 16 B), next 8 rows =
@@ -228,12 +228,12 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
     const uint32_t ones_lo = desc_lo(smem_u32(smem_ones), 128);
     const uint32_t bias_lo = desc_lo(smem_u32(smem_biasop), 128);
     mbar_wait(wload_bar, 0, 31);
-    // Two issuing warps (1 and 3) take alternate tiles: a wait on an mbarrier costs the issuing thread ~130 clocks
+    // Several issuing warps (1 .. C1_MMA_WARPS) take the tiles round-robin: a wait on an mbarrier costs the issuing thread ~130 clocks
     // even when the phase completed long ago (measured), and the tensor pipe's queue is too shallow to hide two of
     // them per 17-instruction tile; with two issuers one warp's waits overlap the other's instruction stream.
     // Tiles use disjoint stages / accumulators and every barrier is per tile, so no ordering between the two is
     // needed (tcgen05.commit tracks the MMAs of the committing thread).
-    const int which = C1_MMA_WARPS == 2 ? (warp == 3 ? 1 : 0) : 0;
+    const int which = warp - 1;
     RoleTimer wait_acc, wait_ops, loop;
     loop.begin();
     for (int lt = which; blockIdx.x + (long long)lt * gridDim.x < total_tiles; lt += C1_MMA_WARPS) {

@@ -34,6 +34,14 @@ constexpr int CV_HALO_Y = CV_TILE_Y + 2;
 constexpr int CV_HALO_X = CV_TILE_X + 2;
 constexpr int CV_HALO_ROWS = CV_HALO_Y * CV_HALO_X;   // 180 pixels
 constexpr int CV_NACC = 4;       // TMEM accumulator ring
+#ifndef SIA_CV_MMA_WARPS
+#define SIA_CV_MMA_WARPS 2
+#endif
+constexpr int CV_MMA_WARPS = SIA_CV_MMA_WARPS;   // warps issuing UMMAs (1 .. 3), tiles dealt round-robin
+#ifndef SIA_CP_MMA_WARPS
+#define SIA_CP_MMA_WARPS 3
+#endif
+constexpr int CP_MMA_WARPS = SIA_CP_MMA_WARPS;   // same for the pixel-pair kernel (measured: 3 beats 2 there, 2 beats 3 above)
 constexpr int CV_THREADS = 384;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle,
                                  // warps 4-7 epilogue group 0 (even tiles), warps 8-11 group 1 (odd tiles)
 constexpr int ONES_BYTES = 4096;                      // [128 rows][16 k] bf16, no-swizzle core matrices
@@ -178,7 +186,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
       }
       wait_stage.store(0);
     }
-  } else if (warp == 1) {
+  } else if (warp >= 1 && warp <= CV_MMA_WARPS) {
     // ================================ MMA issuer ============================================
     // The whole warp runs the (warp-uniform) control flow so descriptors stay in uniform registers;
     // one elected lane issues the UMMAs and their commits.
@@ -191,14 +199,15 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
     const uint32_t ones_lo = desc_lo(smem_u32(smem_ones), 128);
     const uint32_t bias_lo = desc_lo(smem_u32(smem_biasop), 128);
     mbar_wait(wload_bar, 0, 21);
-    int stage = 0;
-    uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
+    // CV_MMA_WARPS issuing warps (1 ..) take the tiles round-robin: an mbarrier wait costs the issuing thread ~130
+    // clocks even when the phase completed long ago, and the tensor pipe's queue does not hide two of them per
+    // tile; one warp's waits now overlap another's instruction stream (see conv1.cu).  Tiles use disjoint stages /
+    // accumulators and every barrier is per tile, so the issuers need no ordering among themselves.
     RoleTimer wait_acc, wait_ops, loop;
     loop.begin();
-    int lt = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+    for (int lt = warp - 1; blockIdx.x + (long long)lt * gridDim.x < total_tiles; lt += CV_MMA_WARPS) {
+      const int stage = lt % NSTAGE, acc = lt % CV_NACC;
+      const uint32_t phase = (uint32_t)(lt / NSTAGE) & 1u, acc_phase = (uint32_t)(lt / CV_NACC) & 1u;
       wait_acc.begin();
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 22);
       wait_acc.end();
@@ -232,11 +241,9 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
       }
       __syncwarp();
       if (lane == 0) trace(lt, 4);
-      if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-      if (++acc == CV_NACC) { acc = 0; acc_phase ^= 1; }
     }
     loop.end();
-    if (lane == 0) { wait_acc.store(1); wait_ops.store(2); loop.store(3); }
+    if (lane == 0 && warp == 1) { wait_acc.store(1); wait_ops.store(2); loop.store(3); }
   } else if (warp >= 4) {
     // ================================ epilogue ==============================================
     // two groups of four warps; group g owns the tiles with local index j = g, g+2, g+4, ...
@@ -629,7 +636,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* 
         if (++stage == CP_NSTAGE) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp >= 1 && warp <= CP_MMA_WARPS) {
     // ================================ MMA issuer ============================================
     constexpr uint32_t idesc = make_idesc_bf16(128, CP_N);
     constexpr uint32_t a_hi = desc_hi(CP_HALO_XP * CP_ROWB, SW_128B);   // 8-row groups = tile rows, one halo row apart
@@ -640,11 +647,10 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* 
     const uint32_t ones_lo = desc_lo(smem_u32(smem_ones), 128);
     const uint32_t bias_lo = desc_lo(smem_u32(smem_biasop), 128);
     mbar_wait(wload_bar, 0, 51);
-    int stage = 0;
-    uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    // CP_MMA_WARPS issuing warps take the tiles round-robin (see conv3x3_kernel)
+    for (int lt = warp - 1; blockIdx.x + (long long)lt * gridDim.x < total_tiles; lt += CP_MMA_WARPS) {
+      const int stage = lt % CP_NSTAGE, acc = lt % CV_NACC;
+      const uint32_t phase = (uint32_t)(lt / CP_NSTAGE) & 1u, acc_phase = (uint32_t)(lt / CV_NACC) & 1u;
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 52);
       mbar_wait(&full_bar[stage], phase, 53);
       tc_fence_after_sync();
@@ -666,8 +672,6 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* 
         umma_commit(&tfull_bar[acc]);
       }
       __syncwarp();
-      if (++stage == CP_NSTAGE) { stage = 0; phase ^= 1; }
-      if (++acc == CV_NACC) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
     // ================================ epilogue ==============================================
