@@ -23,6 +23,10 @@ def main():
     for _ in range(steps):
         eng.step_resident(0)
     eng.synchronize()
+    # the ToneClassifier transform variant on the same decode buffers (one launch)
+    from skin_image_analysis_b200 import ops
+    ops.preprocess_tv_u8hwc(eng.u8[0], (OUT, OUT), ops.LAYOUT_NHWC4_BF16, out=eng.x4)
+    torch.cuda.synchronize()
     print("counted", int(eng.read_counts()[0].sum()))
 
 
