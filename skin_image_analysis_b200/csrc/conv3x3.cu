@@ -382,11 +382,11 @@ conv3x3_stream_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t
   if (threadIdx.x == 0) {
     for (int i = 0; i < CS_NB; ++i) {
       mbar_init(&b_full[i], 1);
-      mbar_init(&b_empty[i], TILES);         // one tcgen05.commit per issuing warp (one issuer per resident tile)
+      mbar_init(&b_empty[i], 1);
     }
     mbar_init(a_full, 1);
-    mbar_init(a_empty, TILES);
-    mbar_init(tfull_bar, TILES);
+    mbar_init(a_empty, 1);
+    mbar_init(tfull_bar, 1);
     mbar_init(&tempty_bar[0], 4);
     mbar_init(&tempty_bar[1], 4);
     fence_mbar_init();
@@ -433,14 +433,8 @@ conv3x3_stream_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t
         }
       }
     }
-  } else if (warp >= 1 && warp <= TILES) {
-    // ================================ MMA issuers ===========================================
-    // One issuing warp per resident tile (warp 1 -> tile 0, warp 2 -> tile 1): every accumulator has a single
-    // issuing thread (deterministic accumulation order), and one warp's mbarrier waits (~130 clocks each for the
-    // issuing thread, see conv3x3_kernel) overlap the other's instruction stream.  Both wait for every weight block
-    // and both commit to its empty barrier (initialised with TILES arrivals); a warp whose tile does not exist in
-    // the last pass still waits and commits, so the arrival counts never change.
-    const int t = warp - 1;
+  } else if (warp == 1) {
+    // ================================ MMA issuer ============================================
     constexpr uint32_t idesc = make_idesc_bf16(128, COUT);
     constexpr uint32_t a_hi = desc_hi(CV_HALO_X * 128, SW_128B);
     constexpr uint32_t b_hi = desc_hi(8 * 128, SW_128B);
@@ -453,11 +447,14 @@ conv3x3_stream_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t
     uint32_t bphase = 0, pphase = 0;
     for (int pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
       const int n_tiles = (TILES * pass + TILES <= total_tiles) ? TILES : total_tiles - TILES * pass;
-      const bool mine = t < n_tiles;
-      mbar_wait(&tempty_bar[t], pphase ^ 1, 27);
+      mbar_wait(&tempty_bar[0], pphase ^ 1, 27);
+      mbar_wait(&tempty_bar[1], pphase ^ 1, 27);
       mbar_wait(a_full, pphase, 28);
       tc_fence_after_sync();
-      if (mine && elect_one()) umma_bf16_ss_w(tmem_base + t * COUT, ones_lo, c_hi, bias_lo, c_hi, idesc, 0u);     // D = bias
+      if (elect_one()) {
+        for (int t = 0; t < n_tiles; ++t)
+          umma_bf16_ss_w(tmem_base + t * COUT, ones_lo, c_hi, bias_lo, c_hi, idesc, 0u);     // D = bias
+      }
       __syncwarp();
       int tap = 0, kc = 0;                 // block order of the packed weights: (tap, chunk), chunk fastest
       for (int blk = 0; blk < nblk; ++blk) {
@@ -465,8 +462,8 @@ conv3x3_stream_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t
         mbar_wait(&b_full[bs], bphase, 29);
         tc_fence_after_sync();
         if (elect_one()) {
-          if (mine) {
-            const uint32_t b_lo = b_lo0 + bs * (B_BLOCK >> 4);
+          const uint32_t b_lo = b_lo0 + bs * (B_BLOCK >> 4);
+          for (int t = 0; t < n_tiles; ++t) {
             const uint32_t a_lo = a_lo0 + ((t * stage_stride + kc * CS_CHUNK_STRIDE + (r * CV_HALO_X + s) * 128) >> 4);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
