@@ -123,6 +123,7 @@ constexpr int TAIL_THREADS = 512;
 constexpr int TAIL_IMGS = 4;     // images per CTA (amortises the W2 read)
 constexpr int TAIL_MAX_N1 = 512;
 constexpr int TAIL_MAX_N2 = 256;
+constexpr int TAIL_KPARTS = 8;   // fc2: K is split over 8 thread groups (64 threads x 4 outputs each)
 
 __global__ void __launch_bounds__(TAIL_THREADS, 1)
 head_tail_kernel(const float* __restrict__ partial, int splits, int M, int n1, int n2, const float* __restrict__ b1,
@@ -133,7 +134,7 @@ head_tail_kernel(const float* __restrict__ partial, int splits, int M, int n1, i
   static_assert(TAIL_IMGS == 4, "h1 is stored as one float4 per k (x, y, z, w = the CTA's four images)");
   __shared__ float4 h1v[TAIL_MAX_N1];                // [k] -> the four images: one LDS.128 per weight in fc2
   float* h1 = reinterpret_cast<float*>(h1v);         // h1[k * 4 + img]
-  __shared__ float h2p[2][TAIL_IMGS][TAIL_MAX_N2];   // the two K-halves of fc2
+  __shared__ __align__(16) float h2p[TAIL_KPARTS][TAIL_IMGS][TAIL_MAX_N2];   // partial sums of fc2 over the K parts
   __shared__ float z[TAIL_IMGS][2];
   const int m0 = blockIdx.x * TAIL_IMGS;
 
@@ -166,9 +167,65 @@ head_tail_kernel(const float* __restrict__ partial, int splits, int M, int n1, i
   }
   __syncthreads();
 
-  // h2 = relu(W2 h1 + b2): thread (j, half) owns output j over half of K for all images; w2t is [n1][n2]
-  // so a warp reads 128 contiguous bytes per k
-  {
+  // h2 = relu(W2 h1 + b2); w2t is [n1][n2].  Fast path (n2 % 4 == 0, n2 <= 256): thread (g, q) owns the four outputs
+  // 4g .. 4g+3 over the q-th eighth of K for all four images -- one 16-byte weight load per k (a warp reads 512
+  // contiguous bytes) and one LDS.128 of h1 per k, all loads of an eighth in flight at once (the loop is L2-latency
+  // bound).  The eight partial sums are added in a fixed order: deterministic.
+  if ((n2 & 3) == 0 && n2 <= 4 * (TAIL_THREADS / TAIL_KPARTS) && (reinterpret_cast<uintptr_t>(w2t) & 15) == 0) {
+    const int q = threadIdx.x / (TAIL_THREADS / TAIL_KPARTS);           // K part
+    const int g = threadIdx.x % (TAIL_THREADS / TAIL_KPARTS);           // output quad
+    const int k_lo = (int)((long long)n1 * q / TAIL_KPARTS), k_hi = (int)((long long)n1 * (q + 1) / TAIL_KPARTS);
+    if (4 * g < n2) {
+      float a[TAIL_IMGS][4];
+#pragma unroll
+      for (int img = 0; img < TAIL_IMGS; ++img) a[img][0] = a[img][1] = a[img][2] = a[img][3] = 0.f;
+      const float4* wq = reinterpret_cast<const float4*>(w2t) + g;
+      const int n2q = n2 >> 2;
+      int k = k_lo;
+      for (; k + 16 <= k_hi; k += 16) {
+        float4 w[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) w[u] = __ldg(wq + (size_t)(k + u) * n2q);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const float4 hv = h1v[k + u];
+          const float hs[TAIL_IMGS] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+          for (int img = 0; img < TAIL_IMGS; ++img) {
+            a[img][0] = fmaf(w[u].x, hs[img], a[img][0]);
+            a[img][1] = fmaf(w[u].y, hs[img], a[img][1]);
+            a[img][2] = fmaf(w[u].z, hs[img], a[img][2]);
+            a[img][3] = fmaf(w[u].w, hs[img], a[img][3]);
+          }
+        }
+      }
+      for (; k < k_hi; ++k) {
+        const float4 w = __ldg(wq + (size_t)k * n2q);
+        const float4 hv = h1v[k];
+        const float hs[TAIL_IMGS] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+        for (int img = 0; img < TAIL_IMGS; ++img) {
+          a[img][0] = fmaf(w.x, hs[img], a[img][0]);
+          a[img][1] = fmaf(w.y, hs[img], a[img][1]);
+          a[img][2] = fmaf(w.z, hs[img], a[img][2]);
+          a[img][3] = fmaf(w.w, hs[img], a[img][3]);
+        }
+      }
+#pragma unroll
+      for (int img = 0; img < TAIL_IMGS; ++img)
+        *reinterpret_cast<float4*>(&h2p[q][img][4 * g]) = make_float4(a[img][0], a[img][1], a[img][2], a[img][3]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < TAIL_IMGS * n2; i += blockDim.x) {
+      const int img = i / n2, j = i % n2;
+      float s2 = h2p[0][img][j];
+#pragma unroll
+      for (int part = 1; part < TAIL_KPARTS; ++part) s2 += h2p[part][img][j];
+      h2p[0][img][j] = fmaxf(s2 + b2[j], 0.f);
+    }
+    __syncthreads();
+  } else {
+    // generic path: thread (j, half) owns output j over half of K for all images
     const int half = threadIdx.x / (TAIL_THREADS / 2);
     const int j0 = threadIdx.x % (TAIL_THREADS / 2);
     const int k_lo = half * (n1 / 2), k_hi = half == 0 ? n1 / 2 : n1;
@@ -176,48 +233,24 @@ head_tail_kernel(const float* __restrict__ partial, int splits, int M, int n1, i
       float a[TAIL_IMGS];
 #pragma unroll
       for (int img = 0; img < TAIL_IMGS; ++img) a[img] = 0.f;
-      int k = k_lo;
-      for (; k + 32 <= k_hi; k += 32) {             // 32 weight loads in flight: the loop is L2-latency bound
-        float w[32];
-#pragma unroll
-        for (int u = 0; u < 32; ++u) w[u] = __ldg(w2t + (size_t)(k + u) * n2 + j);
-#pragma unroll
-        for (int u = 0; u < 32; ++u) {
-          const float4 hv = h1v[k + u];
-          a[0] = fmaf(w[u], hv.x, a[0]);
-          a[1] = fmaf(w[u], hv.y, a[1]);
-          a[2] = fmaf(w[u], hv.z, a[2]);
-          a[3] = fmaf(w[u], hv.w, a[3]);
-        }
-      }
-      for (; k + 8 <= k_hi; k += 8) {
-        float w[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) w[u] = w2t[(size_t)(k + u) * n2 + j];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const float4 hv = h1v[k + u];
-          a[0] = fmaf(w[u], hv.x, a[0]);
-          a[1] = fmaf(w[u], hv.y, a[1]);
-          a[2] = fmaf(w[u], hv.z, a[2]);
-          a[3] = fmaf(w[u], hv.w, a[3]);
-        }
-      }
-      for (; k < k_hi; ++k) {
-        const float w = w2t[(size_t)k * n2 + j];
-#pragma unroll
-        for (int img = 0; img < TAIL_IMGS; ++img) a[img] = fmaf(w, h1[k * TAIL_IMGS + img], a[img]);
+      for (int k = k_lo; k < k_hi; ++k) {
+        const float w = __ldg(w2t + (size_t)k * n2 + j);
+        const float4 hv = h1v[k];
+        a[0] = fmaf(w, hv.x, a[0]);
+        a[1] = fmaf(w, hv.y, a[1]);
+        a[2] = fmaf(w, hv.z, a[2]);
+        a[3] = fmaf(w, hv.w, a[3]);
       }
 #pragma unroll
       for (int img = 0; img < TAIL_IMGS; ++img) h2p[half][img][j] = a[img];
     }
+    __syncthreads();
+    for (int i = threadIdx.x; i < TAIL_IMGS * n2; i += blockDim.x) {
+      const int img = i / n2, j = i % n2;
+      h2p[0][img][j] = fmaxf(h2p[0][img][j] + h2p[1][img][j] + b2[j], 0.f);
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < TAIL_IMGS * n2; i += blockDim.x) {
-    const int img = i / n2, j = i % n2;
-    h2p[0][img][j] = fmaxf(h2p[0][img][j] + h2p[1][img][j] + b2[j], 0.f);
-  }
-  __syncthreads();
 
   // z = W3 h2 + b3: one warp per (image, class)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
