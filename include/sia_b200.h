@@ -224,6 +224,14 @@ int sia_debug_umma_probe_ex(const void* smem_image, int image_bytes, const uint6
  * (0 = off), optionally with a tcgen05.commit at every switch: the cost of short accumulation chains. */
 int sia_debug_umma_probe_switch(int switch_every, int commit_each);
 
+/* Debug / bring-up: tcgen05.mma with the A operand in tensor memory.  a_words [128][a_cols] uint32 (row m = the
+ * 32-bit words thread m stores to TMEM columns 0 .. a_cols-1 of lane m); UMMA i reads A at TMEM column a_col_step * i
+ * and B through b_desc_host[i] (relative to the shared-memory image, as for sia_debug_umma_probe); the 128 x n fp32
+ * accumulator is returned.  idesc 0 = bf16 K-major (128, n). */
+int sia_debug_umma_ts_probe(const void* smem_image, int image_bytes, const void* a_words, int a_cols, int a_col_step,
+                            const uint64_t* b_desc_host, int n_mma, int n, uint32_t idesc, float* out_128xn,
+                            void* stream);
+
 /* Debug / bring-up: one TMA tiled load of a bf16 tensor (rank 2..4; dims / box in elements, innermost
  * first; strides in bytes for dims 1..rank-1; swizzle_bytes in {0,32,64,128}) at the given coordinates;
  * `out` receives the box bytes exactly as they landed in shared memory.  repeat > 1 issues that many

@@ -55,6 +55,8 @@ SIGNATURES = {
     "sia_debug_umma_probe_ex": (c_int, [_P, c_int, ctypes.POINTER(c_uint64), ctypes.POINTER(c_uint64), c_int, c_int,
                                         c_int, ctypes.c_uint32, _P, c_int, ctypes.POINTER(c_longlong), _P]),
     "sia_debug_umma_probe_switch": (c_int, [c_int, c_int]),
+    "sia_debug_umma_ts_probe": (c_int, [_P, c_int, _P, c_int, c_int, ctypes.POINTER(c_uint64), c_int, c_int,
+                                        ctypes.c_uint32, _P, _P]),
     "sia_debug_tma_probe": (c_int, [_P, c_int, ctypes.POINTER(c_uint64), ctypes.POINTER(c_uint64),
                                     ctypes.POINTER(ctypes.c_uint32), c_int, ctypes.POINTER(c_int), _P, c_int, c_int,
                                     c_int, ctypes.POINTER(c_longlong), _P]),

@@ -451,3 +451,113 @@ extern "C" int sia_debug_tmem_ld_rates(double* out_host, int n) {
   cudaFree(sink);
   return rc;
 }
+
+
+// ------------------------------------------------------------------------------------------------------------
+// Bring-up of tcgen05.mma with the A operand in TENSOR MEMORY (the form a second product on an accumulator needs:
+// DESIGN.md section 5, "second tensor-core product").  Thread m writes row m of A -- a_cols 32-bit words, i.e.
+// 2 * a_cols 16-bit elements -- to TMEM columns [0, a_cols) of lane m with tcgen05.st; one thread then issues
+// n_mma UMMAs  D[128 x n] (+)= A[:, 16 i .. 16 i + 15] * B_i^T  with A addressed as TMEM column a_col_step * i and
+// B_i through the caller's shared-memory descriptors; D (fp32, TMEM columns 256 ..) is read back.
+namespace sia {
+
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+struct TsProbeParams {
+  uint64_t b_desc[32];
+  int n_mma, n, a_cols, a_col_step, image_bytes;
+  uint32_t idesc;
+};
+
+__global__ void __launch_bounds__(128, 1)
+umma_ts_probe_kernel(const uint8_t* __restrict__ image, const uint32_t* __restrict__ a_words,
+                     const __grid_constant__ TsProbeParams p, float* __restrict__ out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t done_bar;
+  __shared__ uint32_t tmem_slot;
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  for (int i = threadIdx.x; i < p.image_bytes / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(smem)[i] = reinterpret_cast<const uint32_t*>(image)[i];
+  fence_proxy_async_smem();
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  if (threadIdx.x == 32) {
+    mbar_init(&done_bar, 1);
+    fence_mbar_init();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t lanes = tmem + ((uint32_t)(32 * warp) << 16);
+  // A rows -> TMEM columns [0, a_cols)
+  for (int c = 0; c < p.a_cols; c += 8) {
+    uint32_t v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = a_words[(size_t)threadIdx.x * p.a_cols + c + j];
+    tmem_st8(lanes + c, v);
+  }
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint64_t base16 = (uint64_t)((smem_u32(smem) >> 4) & 0x3FFF);
+      const uint32_t idesc = p.idesc ? p.idesc : make_idesc_bf16(128, p.n);
+      for (int i = 0; i < p.n_mma; ++i)
+        umma_f16_ts(tmem + 256, tmem + (uint32_t)(p.a_col_step * i), p.b_desc[i] + base16, idesc, i > 0 ? 1u : 0u);
+      umma_commit(&done_bar);
+    }
+    __syncwarp();
+  }
+  mbar_wait(&done_bar, 0, 60);
+  tc_fence_after_sync();
+  for (int c = 0; c < p.n; c += 8) {
+    uint32_t v[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(lanes + 256 + c)
+                 : "memory");
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) out[(size_t)threadIdx.x * p.n + c + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_free(tmem, 512);
+}
+
+}  // namespace sia
+
+extern "C" int sia_debug_umma_ts_probe(const void* smem_image, int image_bytes, const void* a_words, int a_cols,
+                                       int a_col_step, const uint64_t* b_desc_host, int n_mma, int n, uint32_t idesc,
+                                       float* out_128xn, void* stream) {
+  using namespace sia;
+  SIA_REQUIRE(smem_image && a_words && b_desc_host && out_128xn);
+  SIA_REQUIRE(image_bytes > 0 && image_bytes % 16 == 0 && image_bytes <= 200 * 1024);
+  SIA_REQUIRE(n_mma >= 1 && n_mma <= 32 && n >= 8 && n <= 256 && n % 8 == 0 && a_cols >= 8 && a_cols <= 256 && a_cols % 8 == 0);
+  if (int wrc = ensure_watchdog()) return wrc;
+  TsProbeParams p;
+  for (int i = 0; i < n_mma; ++i) p.b_desc[i] = b_desc_host[i];
+  p.n_mma = n_mma; p.n = n; p.a_cols = a_cols; p.a_col_step = a_col_step; p.image_bytes = image_bytes; p.idesc = idesc;
+  const int smem = image_bytes + 1024;
+  static int configured = 0;
+  if (int rc = ensure_dynamic_smem(umma_ts_probe_kernel, smem, &configured)) return rc;
+  umma_ts_probe_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint8_t*>(smem_image), static_cast<const uint32_t*>(a_words), p, out_128xn);
+  return launch_status();
+}

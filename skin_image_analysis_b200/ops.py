@@ -376,6 +376,20 @@ def umma_probe(image: torch.Tensor, a_descs, b_descs, n: int, repeat: int = 1, w
     return (out, cyc.value) if want_cycles else out
 
 
+def umma_ts_probe(image: torch.Tensor, a_words: torch.Tensor, a_col_step: int, b_descs, n: int, idesc: int = 0):
+    """tcgen05.mma with A in tensor memory (bring-up): a_words [128, a_cols] int32 = the words thread m stores to
+    TMEM lane m; returns the 128 x n fp32 accumulator."""
+    _need(image, torch.uint8, "image")
+    _need(a_words, torch.int32, "a_words")
+    k = len(b_descs)
+    b = (ctypes.c_uint64 * k)(*[int(d) for d in b_descs])
+    out = torch.zeros((128, n), dtype=torch.float32, device=image.device)
+    check(_lib.load().sia_debug_umma_ts_probe(ptr(image), image.numel(), ptr(a_words), a_words.shape[1], int(a_col_step),
+                                              b, k, n, int(idesc), ptr(out), stream_ptr()), "sia_debug_umma_ts_probe")
+    torch.cuda.synchronize()
+    return out
+
+
 def umma_probe_i8(image: torch.Tensor, a_descs, b_descs, n: int, idesc: int, repeat: int = 1,
                   want_cycles: bool = False):
     """kind::i8 variant of ``umma_probe``: returns the 128 x n int32 accumulator."""

@@ -403,3 +403,34 @@ def test_exploratory_tma_box_throughput():
     _, cyc = ops.tma_probe(t, (4096, 1024), (8192,), (64, 128), 128, (0, 0), repeat=rep, step_dim=0, step=64)
     out["linear_sw128_64x128"] = cyc / rep
     record("tma_cycles_per_box", True, False, {k: round(v, 1) for k, v in out.items()})
+
+
+def test_exploratory_a_operand_in_tensor_memory():
+    """tcgen05.mma with A read from TMEM (what a second product on an accumulator needs).
+    Hypothesis: for 16-bit kinds, lane m / 32-bit column c of the A region holds A[m, 2c] (low half) and A[m, 2c+1]
+    (high half), and one K = 16 instruction consumes 8 columns.  B = [I | 0] picks A's columns back out, so the
+    accumulator reveals the K index the hardware assigns to every stored half-word; a random product then checks
+    the arithmetic.  Exploratory: recorded in gpurun_out/probe_report.json."""
+    from skin_image_analysis_b200 import ops
+    k, n = 64, 64
+    a = (np.arange(128)[:, None] * 0 + np.arange(k)[None, :]).astype(np.float32)          # A[m, kk] = kk
+    a[:, 0] = np.arange(128) % 64                                                         # column 0 carries the row
+    bits = bf16_bits(a).astype(np.uint32)
+    words = (bits[:, 0::2] | (bits[:, 1::2] << 16)).astype(np.uint32).view(np.int32)      # [128, k/2]
+    img = Image(n * k * 2)
+    img.put_core_matrices(0, np.eye(n, k, dtype=np.float32), 128, (k // 8) * 128)         # B[n, kk] = delta
+    bd = [desc(kk * 256, 128, (k // 8) * 128, SW_NONE) for kk in range(k // 16)]
+    got = ops.umma_ts_probe(img.tensor(), torch.from_numpy(words.copy()).cuda(), 8, bd, n).cpu().numpy()
+    ok_map = np.array_equal(got, a[:, :n])
+    rng = np.random.default_rng(3)
+    a2, b2 = rand_int(rng, (128, k)), rand_int(rng, (n, k))
+    bits = bf16_bits(a2).astype(np.uint32)
+    words = (bits[:, 0::2] | (bits[:, 1::2] << 16)).astype(np.uint32).view(np.int32)
+    img2 = Image(n * k * 2)
+    img2.put_core_matrices(0, b2, 128, (k // 8) * 128)
+    got2 = ops.umma_ts_probe(img2.tensor(), torch.from_numpy(words.copy()).cuda(), 8, bd, n).cpu().numpy()
+    ok_rand = np.array_equal(got2, a2 @ b2.T)
+    record("explore_a_in_tmem_f16", ok_map and ok_rand, False,
+           {"mapping_ok": bool(ok_map), "random_ok": bool(ok_rand), "row0": got[0, :16].tolist(), "row5": got[5, :16].tolist(),
+            "col0": got[:8, 0].tolist()})
+    assert got.shape == (128, n)
