@@ -101,6 +101,23 @@ int sia_preprocess_tc_u8hwc(const uint8_t* src, int batch, int src_h, int src_w,
                             const void* items, int n_items, int n_blocks, int last_block_cols, int pads_in_schedule,
                             int out_h, int out_w, const float* out_scale_host, const float* out_bias_host, void* dst_nhwc4, void* stream);
 
+/* Same operator with BOTH passes on the tensor cores (csrc/preprocess_tc2.cu): the horizontal pass is a second
+ * tcgen05.mma per 120-byte column block whose A operand is the (fp16-repacked) accumulator of the vertical product, read
+ * from tensor memory.  Vertical tables as for sia_preprocess_tc_u8hwc; horizontal tables from
+ * resize_weights.build_tc2_tables:
+ *   b2        [n_blocks][16384]   the block's 64 x 128 fp16 slice of Wx in UMMA K-major core-matrix order
+ *                                 (row = 3 * pixel slot + channel, column = byte inside the block)
+ *   block_meta[n_blocks][4]       int32 {s_lo, s_hi, j_lo, 0}: the block completes pixel slots [s_lo, s_hi) = output
+ *                                 columns j_lo, j_lo + 1, ... (slots 17..20 are carried into slots 0..3 of the next block)
+ *   slot_scale[n_blocks][21]      sum(w) / sum(fp16(w)) of that output column
+ * Same geometry restrictions as the one-product kernel plus <= 4 + 13 + 4 output columns per block
+ * (the builder raises otherwise).  V is rounded to fp16: <= 2.5e-4 of full scale, <= 1 bf16 ulp. */
+int sia_preprocess_tc2_u8hwc(const uint8_t* src, int batch, int src_h, int src_w, const void* a_packed,
+                             const float* lane_scale, const int32_t* tile_row0, int n_tiles, int tile_rows,
+                             const void* b2, const int32_t* block_meta, const float* slot_scale, int n_blocks,
+                             int last_block_cols, int out_h, int out_w, const float* out_scale_host,
+                             const float* out_bias_host, void* dst_nhwc4, void* stream);
+
 /* SURVEY 8(f) row 2 -- the ToneClassifier test transform (notebooks/ToneClassifier/CNNTrialDataset.py:71-76:
  * v2.Resize((224,224)) on uint8 [bilinear, antialias] -> v2.ToDtype(float32, scale=True) -> v2.Normalize(mean, std))
  * for a batch of u8 HWC decode buffers.  torchvision's uint8 resize is ATen's fixed-point separable resampler

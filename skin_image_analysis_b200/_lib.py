@@ -30,6 +30,8 @@ SIGNATURES = {
                                      ctypes.POINTER(c_float), ctypes.POINTER(c_float), c_int, c_int, _P, _P]),
     "sia_preprocess_tc_u8hwc": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, c_int, c_int, _P, c_int, c_int, c_int,
                                         c_int, c_int, c_int, ctypes.POINTER(c_float), ctypes.POINTER(c_float), _P, _P]),
+    "sia_preprocess_tc2_u8hwc": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, c_int, c_int, _P, _P, _P, c_int, c_int,
+                                         c_int, c_int, ctypes.POINTER(c_float), ctypes.POINTER(c_float), _P, _P]),
     "sia_preprocess_tv_u8hwc": (c_int, [_P, c_int, c_int, c_int, _P, _P, c_int, c_int, _P, _P, c_int, c_int, _P, c_int,
                                         c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "sia_debug_tv_force_generic": (c_int, [c_int]),

@@ -72,6 +72,27 @@ def _tc_tables(device_index: int, src_h: int, src_w: int, out_h: int, out_w: int
     return _DeviceTcTables(t, torch.device("cuda", device_index))
 
 
+class _DeviceTc2Tables:
+    def __init__(self, t: _rw.Tc2Tables, device):
+        self.host = t
+        self.a_packed = torch.from_numpy(t.vert.a_packed).to(device)
+        self.lane_scale = torch.from_numpy(t.vert.lane_scale).to(device)
+        self.tile_row0 = torch.from_numpy(t.vert.tile_row0).to(device)
+        self.b2 = torch.from_numpy(t.b2).to(device)
+        self.block_meta = torch.from_numpy(np.ascontiguousarray(t.block_meta)).to(device)
+        self.slot_scale = torch.from_numpy(np.ascontiguousarray(t.slot_scale)).to(device)
+
+
+@lru_cache(maxsize=64)
+def _tc2_tables(device_index: int, src_h: int, src_w: int, out_h: int, out_w: int, antialias):
+    """Tables of the two-product tensor-core kernel, or None when the geometry does not fit it."""
+    try:
+        t = _rw.build_tc2_tables(src_h, src_w, out_h, out_w, antialias=antialias)
+    except ValueError:
+        return None
+    return _DeviceTc2Tables(t, torch.device("cuda", device_index))
+
+
 _LAYOUT_DTYPE = {LAYOUT_NCHW_F32: torch.float32, LAYOUT_NCHW_BF16: torch.bfloat16, LAYOUT_NHWC4_BF16: torch.bfloat16}
 
 
@@ -104,8 +125,19 @@ def preprocess_u8hwc(src: torch.Tensor, size, layout: int = LAYOUT_NCHW_F32, mea
             raise ValueError(f"out must have shape {shape}")
     osc = (ctypes.c_float * 3)(*[1.0 / float(s) for s in std])
     obi = (ctypes.c_float * 3)(*[-float(m) / float(s) for m, s in zip(mean, std)])
-    if impl not in ("auto", "cuda_core", "tensor_core"):
-        raise ValueError("impl must be 'auto', 'cuda_core' or 'tensor_core'")
+    if impl not in ("auto", "cuda_core", "tensor_core", "tensor_core2"):
+        raise ValueError("impl must be 'auto', 'cuda_core', 'tensor_core' or 'tensor_core2'")
+    if impl == "tensor_core2":
+        t2 = _tc2_tables(src.device.index, sh, sw, oh, ow, antialias) if layout == LAYOUT_NHWC4_BF16 else None
+        if t2 is None or src.data_ptr() % 16 != 0:
+            raise SiaError("two-product tensor-core preprocess does not support this geometry / layout")
+        tsc = (ctypes.c_float * 3)(*[float(scale) / float(s) for s in std])
+        v = t2.host.vert
+        check(_lib.load().sia_preprocess_tc2_u8hwc(
+            ptr(src), b, sh, sw, ptr(t2.a_packed), ptr(t2.lane_scale), ptr(t2.tile_row0), v.n_tiles, v.tile_rows,
+            ptr(t2.b2), ptr(t2.block_meta), ptr(t2.slot_scale), t2.host.n_blocks, t2.host.last_block_cols, oh, ow,
+            tsc, obi, ptr(out), stream_ptr()), "sia_preprocess_tc2_u8hwc")
+        return out
     if impl == "tensor_core" or (impl == "auto" and fixed_point and layout == LAYOUT_NHWC4_BF16):
         tc = _tc_tables(src.device.index, sh, sw, oh, ow, antialias) if layout == LAYOUT_NHWC4_BF16 else None
         if tc is not None and src.data_ptr() % 16 == 0:

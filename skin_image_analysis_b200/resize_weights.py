@@ -446,3 +446,137 @@ def tv_tile_plan(y: TvAxis, row_bytes: int, out_w: int, x_taps: int, budget: int
             if smem <= limit:
                 return tile, rows
     raise ValueError("source rows too long for the shared-memory window of the torchvision-variant kernel")
+
+
+# -------------------------------------------------------------------------------------------------
+# Tables of the two-product tensor-core kernel (csrc/preprocess_tc2.cu): horizontal pass as a second UMMA
+# -------------------------------------------------------------------------------------------------
+TC2_SLOTS_IN, TC2_SLOTS_FULL, TC2_SLOTS_OUT = 4, 13, 4      # output-pixel slots of one column block
+TC2_SLOTS = TC2_SLOTS_IN + TC2_SLOTS_FULL + TC2_SLOTS_OUT   # 21 pixels x 3 channels = 63 of the 64 UMMA columns
+TC2_N = 64
+TC2_B_BYTES = TC2_N * TC_BLOCK_COLS * 2                     # one block's slice of Wx, fp16, K-major core matrices
+
+
+@dataclass
+class Tc2Tables:
+    """Vertical operator exactly as in TcTables; horizontal operator as one fp16 matrix per 120-byte column block.
+
+    Block b owns the source bytes [120 b, 120 b + 120) of the image row (the last block: the rest) = whole pixels.
+    Every block has 21 output-pixel slots (x 3 channels = 63 of the 64 UMMA columns).  An output pixel whose taps
+    straddle blocks b and b + 1 sits in slot 17 + t of block b and in slot t of block b + 1 (t = 0..3, both sets
+    right-aligned: the kernel carries slots 17..20 into slots 0..3 of the next block in registers); one whose taps
+    all lie in block b sits after the block's incoming pixels.  The pixels a block COMPLETES are therefore the
+    contiguous slots [s_lo, s_hi), in output-column order starting at column j_lo -- which lets the kernel store them
+    as aligned 32-byte groups.  ``b2[b]`` is the [64 x 128] matrix (row = 3 * slot + channel, column = byte inside
+    the block) in UMMA K-major core-matrix order; ``slot_scale[b, s]`` = sum(w) / sum(fp16(w)) of the column slot s
+    completes."""
+    vert: TcTables
+    b2: np.ndarray            # uint8 [n_blocks, TC2_B_BYTES]
+    b2_dense: np.ndarray      # float64 [n_blocks, 64, 128] (fp16-rounded), for tests / emulation
+    block_meta: np.ndarray    # int32 [n_blocks, 4]: s_lo, s_hi, j_lo, 0
+    slot_col: np.ndarray      # int32 [n_blocks, 21]: output column completed by the slot, -1 = none (tests / emulation)
+    slot_scale: np.ndarray    # float32 [n_blocks, 21]
+    n_blocks: int
+    last_block_cols: int
+
+
+def build_tc2_tables(src_h: int, src_w: int, out_h: int, out_w: int, antialias: str | bool = "skimage") -> Tc2Tables:
+    """Raises ValueError when the geometry does not fit (the caller falls back to the one-product kernel)."""
+    vert = build_tc_tables(src_h, src_w, out_h, out_w, antialias)
+    if antialias == "skimage":
+        aa = out_h < src_h or out_w < src_w
+    else:
+        aa = bool(antialias)
+    rows_x = axis_operator_rows(src_w, out_w, aa)
+    n_blocks = vert.n_blocks
+    px_per_block = TC_BLOCK_STRIDE // 3
+
+    def owner(px: int) -> int:
+        return min(px // px_per_block, n_blocks - 1)
+
+    blocks_of = [sorted({owner(x) for x in r}) for r in rows_x]
+    if any(len(b) > 2 or (len(b) == 2 and b[1] != b[0] + 1) for b in blocks_of):
+        raise ValueError("an output column spans more than two column blocks")
+    b2_dense = np.zeros((n_blocks, TC2_N, TC_BLOCK_COLS), np.float64)
+    block_meta = np.zeros((n_blocks, 4), np.int32)
+    slot_col = np.full((n_blocks, TC2_SLOTS), -1, np.int32)
+    slot_scale = np.ones((n_blocks, TC2_SLOTS), np.float32)
+    slot_of = {}                                           # (block, output column) -> slot
+    first_out = TC2_SLOTS_IN + TC2_SLOTS_FULL              # 17
+    for b in range(n_blocks):
+        ins = [j for j in range(out_w) if blocks_of[j] == [b - 1, b]]
+        full = [j for j in range(out_w) if blocks_of[j] == [b]]
+        outs = [j for j in range(out_w) if blocks_of[j] == [b, b + 1]]
+        if len(ins) > TC2_SLOTS_IN or len(outs) > TC2_SLOTS_OUT:
+            raise ValueError("too many straddling output columns per column block")
+        done = ins + full                                  # completed here, in column order
+        if done != list(range(done[0], done[0] + len(done))) if done else False:
+            raise ValueError("the columns a block completes are not contiguous")
+        s_lo = TC2_SLOTS_IN - len(ins)
+        if s_lo + len(done) > first_out:                   # more than 13 complete columns
+            extra = s_lo + len(done) - first_out
+            if not ins and extra <= s_lo:                  # no incoming pixels: start further left
+                s_lo -= extra
+            elif not outs and b == n_blocks - 1 and s_lo + len(done) <= TC2_SLOTS:
+                pass                                       # last block: run into the unused "out" slots
+            else:
+                raise ValueError("too many output columns per column block for the slot layout")
+        for q, j in enumerate(done):
+            slot_of[(b, j)] = s_lo + q
+            slot_col[b, s_lo + q] = j
+        for q, j in enumerate(outs):
+            slot_of[(b, j)] = TC2_SLOTS - len(outs) + q
+        block_meta[b] = (s_lo, s_lo + len(done), done[0] if done else 0, 0)
+    # slot 17 + t of block b feeds slot t of block b + 1
+    for b in range(n_blocks - 1):
+        for j in [j for j in range(out_w) if blocks_of[j] == [b, b + 1]]:
+            assert slot_of[(b, j)] - first_out == slot_of[(b + 1, j)]
+    for j, r in enumerate(rows_x):
+        exact = sum(r.values())
+        s16 = sum(float(np.float16(v)) for v in r.values())
+        for x, v in r.items():
+            b = owner(x)
+            s = slot_of[(b, j)]
+            k0 = 3 * x - b * TC_BLOCK_STRIDE
+            if k0 + 3 > TC_BLOCK_COLS:
+                raise ValueError("a source pixel falls outside its block's accumulator columns")
+            for c in range(3):
+                b2_dense[b, 3 * s + c, k0 + c] += float(np.float16(v))
+        b_done = blocks_of[j][-1]
+        slot_scale[b_done, slot_of[(b_done, j)]] = exact / s16
+    # shared-memory image: (n, k) at (n/8)*SBO + (k/8)*LBO + (n%8)*16 + (k%8)*2, LBO = 128, SBO = 16 * 128
+    n = np.arange(TC2_N)[:, None]
+    k = np.arange(TC_BLOCK_COLS)[None, :]
+    dst = ((n // 8) * (TC_BLOCK_COLS // 8) * 128 + (k // 8) * 128 + (n % 8) * 16 + (k % 8) * 2) // 2
+    b2 = np.zeros((n_blocks, TC2_N * TC_BLOCK_COLS), np.float16)
+    for b in range(n_blocks):
+        b2[b, dst.reshape(-1)] = b2_dense[b].astype(np.float16).reshape(-1)
+    return Tc2Tables(vert, b2.view(np.uint8).reshape(n_blocks, -1), b2_dense, block_meta, slot_col, slot_scale,
+                     n_blocks, vert.last_block_cols)
+
+
+def tc2_emulate(u8: np.ndarray, t: Tc2Tables, out_h: int, out_w: int, scale: float = 1.0 / 255.0) -> np.ndarray:
+    """numpy model of the two-product kernel's arithmetic: fp16 vertical weights, fp32 accumulate, lane scale,
+    V rounded to fp16, fp16 horizontal weights, fp32 accumulate, carry across blocks -> [out_h, out_w, 3] float32."""
+    v = t.vert
+    src_h, src_w, _ = u8.shape
+    s = u8.reshape(src_h, src_w * 3).astype(np.float64)
+    out = np.full((out_h, out_w, 3), np.nan, np.float32)
+    for tile in range(v.n_tiles):
+        rows = np.clip(v.tile_row0[tile] + np.arange(TC_KWIN), 0, src_h - 1)
+        vv = (v.a_dense[tile] @ s[rows]).astype(np.float32) * v.lane_scale[tile][:, None]
+        vv = vv.astype(np.float16).astype(np.float64)
+        vv = np.concatenate([vv, np.zeros((TC_LANES, TC_BLOCK_COLS), np.float64)], axis=1)
+        lanes = min(v.tile_rows, out_h - tile * v.tile_rows)
+        carry = np.zeros((TC_LANES, TC2_SLOTS_OUT * 3), np.float32)
+        for b in range(t.n_blocks):
+            blk = vv[:, b * TC_BLOCK_STRIDE: b * TC_BLOCK_STRIDE + TC_BLOCK_COLS]
+            d2 = (blk @ t.b2_dense[b].T).astype(np.float32)                      # [128, 64]
+            d2[:, :TC2_SLOTS_IN * 3] += carry
+            carry = d2[:, (TC2_SLOTS_IN + TC2_SLOTS_FULL) * 3: TC2_SLOTS * 3].copy()
+            for sl in range(TC2_SLOTS):
+                j = int(t.slot_col[b, sl])
+                if j >= 0:
+                    o = d2[:lanes, 3 * sl: 3 * sl + 3] * (t.slot_scale[b, sl] * np.float32(scale))
+                    out[tile * v.tile_rows: tile * v.tile_rows + lanes, j] = o
+    return out

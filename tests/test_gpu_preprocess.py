@@ -162,3 +162,52 @@ def test_tensor_core_pass_large_batch_and_mean_std():
         const = np.full((450, 600, 3), v, np.uint8)
         out = _gpu([const], (224, 224), ops.LAYOUT_NHWC4_BF16, impl="tensor_core")[0, :, 1:225, :3].float().cpu().numpy()
         assert np.all(out == torch.tensor(np.float32(v) / 255.0).to(torch.bfloat16).float().item()), v
+
+
+@pytest.mark.parametrize("src_hw,batch", [((450, 600), 5), ((480, 640), 3)])
+def test_two_product_tensor_core_pass_matches_oracle(src_hw, batch):
+    """csrc/preprocess_tc2.cu (impl="tensor_core2": the horizontal pass is a second tcgen05.mma whose A operand is the
+    fp16-repacked accumulator of the vertical product, read from tensor memory): within one bf16 ulp of the
+    bf16-rounded oracle, <= 2.5e-4 of full scale before rounding, bit-identical to the numpy model of its arithmetic
+    up to fp32 summation order, within one ulp of the one-product kernel, zero pads, batch independent."""
+    from skin_image_analysis_b200 import ops
+    from skin_image_analysis_b200 import resize_weights as rw
+    kinds = ["noise", "smooth", "extremes", "noise", "smooth"]
+    imgs = [helpers.synthetic_u8_image(src_hw[0], src_hw[1], 300 + i, kinds[i]) for i in range(batch)]
+    got = _gpu(imgs, (224, 224), ops.LAYOUT_NHWC4_BF16, impl="tensor_core2").float().cpu().numpy()
+    assert got.shape == (batch, 224, 224 + ops.NHWC4_PAD, 4)
+    assert np.all(got[..., 3] == 0) and np.all(got[:, :, 0] == 0) and np.all(got[:, :, 225:] == 0)
+    want = np.stack([R.transform_u8(im, (224, 224)) for im in imgs]).transpose(0, 2, 3, 1)
+    want_bf = torch.from_numpy(want).to(torch.bfloat16).float().numpy()
+    px = got[:, :, 1:225, :3]
+    ulp = np.maximum(np.abs(want_bf), 2.0 ** -126) * 2.0 ** -7
+    assert np.all(np.abs(px - want_bf) <= ulp)
+    assert np.abs(px - want).max() <= 2.0 ** -8 + 2.6e-4
+    assert (px != want_bf).mean() < 0.05                      # V is rounded to fp16: ~2 % of the outputs round the other way
+    t = rw.build_tc2_tables(src_hw[0], src_hw[1], 224, 224)
+    model_bf = torch.from_numpy(rw.tc2_emulate(imgs[0], t, 224, 224)).to(torch.bfloat16).float().numpy()
+    assert (px[0] != model_bf).mean() < 1e-3                  # fp32 summation order only
+    old = _gpu(imgs, (224, 224), ops.LAYOUT_NHWC4_BF16, impl="tensor_core").float().cpu().numpy()
+    assert np.all(np.abs(got - old) <= np.maximum(np.abs(old), 2.0 ** -126) * 2.0 ** -7)
+    single = _gpu(imgs[-1:], (224, 224), ops.LAYOUT_NHWC4_BF16, impl="tensor_core2").float().cpu().numpy()
+    assert np.array_equal(single[0], got[-1])
+
+
+def test_two_product_pass_large_batches_and_flat_images():
+    """More images than CTAs per tile (pairs in flight, a single trailing image), flat images exact, unsupported
+    geometries refused loudly."""
+    from skin_image_analysis_b200 import _lib, ops
+    rng = np.random.default_rng(5)
+    base = [helpers.synthetic_u8_image(450, 600, 400 + i, "noise") for i in range(4)]
+    ref = ops.preprocess_u8hwc(torch.from_numpy(np.stack(base)).cuda(), (224, 224), ops.LAYOUT_NHWC4_BF16,
+                               impl="tensor_core2")
+    for nb in (170, 297):
+        idx = torch.from_numpy(rng.integers(0, 4, nb)).cuda()
+        x = torch.from_numpy(np.stack(base)).cuda()[idx].contiguous()
+        assert torch.equal(ops.preprocess_u8hwc(x, (224, 224), ops.LAYOUT_NHWC4_BF16, impl="tensor_core2"), ref[idx])
+    for v in (0, 1, 127, 200, 255):
+        const = np.full((450, 600, 3), v, np.uint8)
+        out = _gpu([const], (224, 224), ops.LAYOUT_NHWC4_BF16, impl="tensor_core2")[0, :, 1:225, :3].float().cpu().numpy()
+        assert np.all(out == torch.tensor(np.float32(v) / 255.0).to(torch.bfloat16).float().item()), v
+    with pytest.raises(_lib.SiaError):                        # 512 x 512 outputs do not fit the 21-slot layout
+        _gpu([base[0]], (512, 512), ops.LAYOUT_NHWC4_BF16, impl="tensor_core2")

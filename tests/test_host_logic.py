@@ -223,3 +223,34 @@ def test_tone_classifier_surface_on_cpu():
     if not torch.cuda.is_available():
         with pytest.raises(_lib.SiaError):
             tf(torch.zeros(3, 8, 8, dtype=torch.uint8))
+
+
+@pytest.mark.parametrize("shape", [(450, 600, 224, 224), (480, 640, 224, 224)])
+def test_two_product_tables_reproduce_the_oracle_operator(shape):
+    """resize_weights.build_tc2_tables: the numpy model of the two-product kernel (fp16 V, fp16 Wx slices, register
+    carry between column blocks) stays within 2.6e-4 of full scale of the oracle; every output column is completed
+    exactly once, in column order, by a contiguous slot range; slots 17..20 of a block feed slots 0..3 of the next."""
+    from skin_image_analysis_b200 import resize_weights as rw
+    sh, sw, oh, ow = shape
+    t = rw.build_tc2_tables(sh, sw, oh, ow)
+    u8 = helpers.synthetic_u8_image(sh, sw, 77, "noise")
+    em = rw.tc2_emulate(u8, t, oh, ow)
+    want = R.transform_u8(u8, (oh, ow)).transpose(1, 2, 0)
+    assert not np.isnan(em).any() and np.abs(em - want).max() <= 2.6e-4
+    done = []
+    for b in range(t.n_blocks):
+        s_lo, s_hi, j_lo, _ = (int(v) for v in t.block_meta[b])
+        assert 0 <= s_lo <= s_hi <= rw.TC2_SLOTS
+        assert [int(c) for c in t.slot_col[b, s_lo:s_hi]] == list(range(j_lo, j_lo + s_hi - s_lo))
+        assert (t.slot_col[b] >= 0).sum() == s_hi - s_lo
+        done += list(range(j_lo, j_lo + s_hi - s_lo))
+    assert done == list(range(ow))
+    flat = rw.tc2_emulate(np.full((sh, sw, 3), 200, np.uint8), t, oh, ow)
+    assert np.abs(flat - np.float32(200 / 255)).max() <= 2e-7
+
+
+def test_two_product_tables_reject_unsupported_geometry():
+    from skin_image_analysis_b200 import resize_weights as rw
+    for shape in [(450, 600, 512, 512), (300, 400, 224, 224)]:
+        with pytest.raises(ValueError):
+            rw.build_tc2_tables(*shape)

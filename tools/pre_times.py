@@ -22,7 +22,7 @@ g = torch.Generator(device="cuda").manual_seed(0)
 ring = [torch.randint(0, 256, (b, 450, 600, 3), dtype=torch.uint8, device="cuda", generator=g) for _ in range(4)]
 x4 = torch.empty((b, 224, 232, 4), dtype=torch.bfloat16, device="cuda")
 res = {"batch": b}
-for impl in ("cuda_core", "tensor_core"):
+for impl in ("cuda_core", "tensor_core", "tensor_core2"):
     k = [0]
     def fn():
         k[0] += 1
