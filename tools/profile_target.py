@@ -26,6 +26,8 @@ def main():
     # the ToneClassifier transform variant on the same decode buffers (one launch)
     from skin_image_analysis_b200 import ops
     ops.preprocess_tv_u8hwc(eng.u8[0], (OUT, OUT), ops.LAYOUT_NHWC4_BF16, out=eng.x4)
+    # the opt-in two-product tensor-core preprocess, one launch
+    ops.preprocess_u8hwc(eng.u8[0], (OUT, OUT), ops.LAYOUT_NHWC4_BF16, out=eng.x4, impl="tensor_core2")
     torch.cuda.synchronize()
     print("counted", int(eng.read_counts()[0].sum()))
 
