@@ -413,9 +413,8 @@ preprocess_tc_kernel(const __grid_constant__ CUtensorMap tmap_src, const __grid_
 #endif
         if (vec_col >= 0) {                          // uniform: 2 x 16-byte stores, 32-byte aligned
           if (store_ok) {
-            uint4* dst = reinterpret_cast<uint4*>(orow + vec_col);
-            dst[0] = make_uint4(st[0][0], st[0][1], st[1][0], st[1][1]);
-            dst[1] = make_uint4(st[2][0], st[2][1], st[3][0], st[3][1]);
+            st_global_256(orow + vec_col, make_uint4(st[0][0], st[0][1], st[1][0], st[1][1]),
+                          make_uint4(st[2][0], st[2][1], st[3][0], st[3][1]));
           }
         } else {
 #pragma unroll

@@ -347,6 +347,9 @@ preprocess_tc2_kernel(const __grid_constant__ CUtensorMap tmap_src, const __grid
     float carry[3 * T2_SLOTS_OUT];
 #pragma unroll
     for (int q = 0; q < 3 * T2_SLOTS_OUT; ++q) carry[q] = 0.f;
+    uint2 dfr[4];                                  // completed pixels of an unfinished 4-column group (see output())
+#pragma unroll
+    for (int u = 0; u < 4; ++u) dfr[u] = make_uint2(0u, 0u);
     int prev_blk = -1, prev_img = 0;               // block whose outputs are still to be written
     uint32_t prev_cnt = 0;
 
@@ -366,22 +369,27 @@ preprocess_tc2_kernel(const __grid_constant__ CUtensorMap tmap_src, const __grid
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[2 * g + b]);          // the accumulator is in registers
-      if (prev_blk == 0) {
+      if (prev_blk == 0) {                         // a new image row: no partial sums, no deferred pixels
 #pragma unroll
         for (int q = 0; q < 3 * T2_SLOTS_OUT; ++q) carry[q] = 0.f;
-      }
-      uint2* orow = p.dst + ((size_t)prev_img * p.out_h + (row_ok ? i : 0)) * pitch;
-      if (prev_blk == 0 && row_ok) {               // zero pad columns of the NHWC4 row
-        orow[0] = make_uint2(0u, 0u);
 #pragma unroll
-        for (int c = 1; c < SIA_NHWC4_PAD; ++c) orow[p.out_w + c] = make_uint2(0u, 0u);
+        for (int u = 0; u < 4; ++u) dfr[u] = make_uint2(0u, 0u);
       }
-      // the block completes the pixel slots [s_lo, s_hi) = output columns j_lo, j_lo + 1, ...: pixel of slot s lives in
-      // padded column c0 + s.  Groups of four padded columns starting at a multiple of four are one 32-byte sector
-      // per lane (two 16-byte stores); the ragged ends of the range are written pixel by pixel.
+#ifdef SIA_T2_SAMEADDR
+      uint2* orow = p.dst + ((size_t)(prev_img & 1) * p.out_h + (row_ok ? i : 0)) * pitch;   // timing experiment
+#else
+      uint2* orow = p.dst + ((size_t)prev_img * p.out_h + (row_ok ? i : 0)) * pitch;
+#endif
+      // The block completes the pixel slots [s_lo, s_hi) = output columns j_lo, j_lo + 1, ...: the pixel of slot s
+      // lives in padded column c0 + s.  Only whole groups of four padded columns starting at a multiple of four are
+      // ever written -- one 32-byte sector per lane in one 256-bit store.  The pixels of a group the block leaves
+      // unfinished are deferred in registers (dfr) and head the first group of the next block; a row starts with a
+      // zero deferred pixel (pad column 0) and its last block fills its last group and the rest of the pad columns
+      // with zeros, so no partial-sector write exists at all.
       const int4 meta = block_meta_s[prev_blk];
       const int s_lo = meta.x, s_hi = meta.y;
       const int c0 = meta.z - s_lo + 1;
+      const bool last_blk = prev_blk == p.n_blocks - 1;
       const float* scl = slot_scale_s + prev_blk * T2_SLOTS;
       float new_carry[3 * T2_SLOTS_OUT];
 #pragma unroll
@@ -402,22 +410,26 @@ preprocess_tc2_kernel(const __grid_constant__ CUtensorMap tmap_src, const __grid
 #endif
       auto emit = [&](auto a_tag) {
         constexpr int A = decltype(a_tag)::value;          // c0 & 3
-        constexpr int S0 = (4 - A) & 3;                     // first slot whose column is a multiple of four
+        constexpr int S0 = (4 - A) & 3;                     // first slot >= 0 whose column is a multiple of four
 #pragma unroll
-        for (int s = 0; s < S0; ++s)
-          if (st_ok && s >= s_lo && s < s_hi) orow[c0 + s] = px[s];
+        for (int sg = S0 - 4; sg < T2_SLOTS; sg += 4) {     // groups of four columns (the first may begin before slot 0)
+          if (sg + 4 <= s_lo || sg >= s_hi) continue;       // uniform: nothing of this block in the group
+          uint2 v[4];
 #pragma unroll
-        for (int sg = S0; sg < T2_SLOTS; sg += 4) {
-          if (sg + 4 <= T2_SLOTS && sg >= s_lo && sg + 4 <= s_hi) {                 // uniform
-            if (st_ok) {
-              uint4* dst = reinterpret_cast<uint4*>(orow + c0 + sg);
-              dst[0] = make_uint4(px[sg].x, px[sg].y, px[sg + 1].x, px[sg + 1].y);
-              dst[1] = make_uint4(px[sg + 2].x, px[sg + 2].y, px[sg + 3].x, px[sg + 3].y);
-            }
-          } else {
+          for (int u = 0; u < 4; ++u) {
+            const int sl = sg + u;                          // compile-time
+            const uint2 own = (sl >= 0 && sl < T2_SLOTS) ? px[sl >= 0 && sl < T2_SLOTS ? sl : 0] : make_uint2(0u, 0u);
+            v[u] = sl < s_lo ? dfr[u] : own;                // before s_lo: what the previous block deferred
+          }
+          if (sg + 4 <= s_hi || last_blk) {
 #pragma unroll
             for (int u = 0; u < 4; ++u)
-              if (sg + u < T2_SLOTS && st_ok && sg + u >= s_lo && sg + u < s_hi) orow[c0 + sg + u] = px[sg + u];
+              if (sg + u >= s_hi) v[u] = make_uint2(0u, 0u);                          // row end: pad columns
+            if (st_ok) st_global_256(orow + c0 + sg, make_uint4(v[0].x, v[0].y, v[1].x, v[1].y),
+                                     make_uint4(v[2].x, v[2].y, v[3].x, v[3].y));
+          } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) dfr[u] = v[u];      // unfinished group: finished by the next block
           }
         }
       };
@@ -426,6 +438,10 @@ preprocess_tc2_kernel(const __grid_constant__ CUtensorMap tmap_src, const __grid
         case 1: emit(std::integral_constant<int, 1>{}); break;
         case 2: emit(std::integral_constant<int, 2>{}); break;
         default: emit(std::integral_constant<int, 3>{}); break;
+      }
+      if (last_blk && st_ok) {                              // remaining pad columns of the row
+        for (int c = (c0 + s_hi + 3) & ~3; c < pitch; c += 4)
+          st_global_256(orow + c, make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u));
       }
 #pragma unroll
       for (int q = 0; q < 3 * T2_SLOTS_OUT; ++q) carry[q] = new_carry[q];
@@ -484,7 +500,7 @@ extern "C" int sia_preprocess_tc2_u8hwc(const uint8_t* src, int batch, int src_h
   SIA_REQUIRE(batch >= 1 && src_h >= 2 && src_w >= 8 && out_h >= 1 && out_w >= 1 && n_tiles >= 1);
   SIA_REQUIRE(tile_rows >= 1 && tile_rows <= 128 && n_tiles * tile_rows >= out_h && n_blocks >= 1);
   SIA_REQUIRE(last_block_cols >= 16 && last_block_cols <= TC_COLS && last_block_cols % 16 == 0);
-  SIA_REQUIRE(aligned(a_packed, 16) && aligned(b2, 16) && aligned(block_meta, 16) && aligned(dst_nhwc4, 16));
+  SIA_REQUIRE(aligned(a_packed, 16) && aligned(b2, 16) && aligned(block_meta, 16) && aligned(dst_nhwc4, 32));
   const int row_bytes = src_w * 3;
   if (row_bytes % 8 != 0 || src_h % 2 != 0 || !aligned(src, 16) || ((uint64_t)src_h * row_bytes) % 16 != 0)
     return SIA_E_UNSUPPORTED;

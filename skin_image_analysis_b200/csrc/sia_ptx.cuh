@@ -286,6 +286,13 @@ __host__ __device__ constexpr uint32_t make_idesc_i8(uint32_t m, uint32_t n, uin
 }
 
 // ---------------------------------- small math helpers ---------------------------------------
+// One 256-bit global store (sm_100: STG.256): a whole 32-byte sector per lane in ONE request, instead of two 16-byte
+// halves that reach L2 as partial-sector writes.  p must be 32-byte aligned.
+__device__ __forceinline__ void st_global_256(void* p, uint4 a, uint4 b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

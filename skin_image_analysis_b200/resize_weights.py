@@ -483,6 +483,8 @@ class Tc2Tables:
 def build_tc2_tables(src_h: int, src_w: int, out_h: int, out_w: int, antialias: str | bool = "skimage") -> Tc2Tables:
     """Raises ValueError when the geometry does not fit (the caller falls back to the one-product kernel)."""
     vert = build_tc_tables(src_h, src_w, out_h, out_w, antialias)
+    if out_w % 4 != 0:
+        raise ValueError("the two-product kernel stores whole groups of four output columns: out_w % 4 must be 0")
     if antialias == "skimage":
         aa = out_h < src_h or out_w < src_w
     else:
