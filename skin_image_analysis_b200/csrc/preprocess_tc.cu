@@ -470,7 +470,7 @@ extern "C" int sia_preprocess_tc_u8hwc(const uint8_t* src, int batch, int src_h,
   SIA_REQUIRE(n_items >= 8 && n_items % 8 == 0);
   SIA_REQUIRE(tile_rows >= 1 && tile_rows <= 128 && n_tiles * tile_rows >= out_h && n_blocks >= 1);
   SIA_REQUIRE(last_block_cols >= 16 && last_block_cols <= TC_COLS && last_block_cols % 16 == 0);
-  SIA_REQUIRE(aligned(a_packed, 16) && aligned(items, 16) && aligned(dst_nhwc4, 8));
+  SIA_REQUIRE(aligned(a_packed, 16) && aligned(items, 16) && aligned(dst_nhwc4, 32));   // 256-bit stores
   const int row_bytes = src_w * 3;
   // 8-byte pieces; rows paired for the TMA view; every image 16-byte aligned
   if (row_bytes % 8 != 0 || src_h % 2 != 0 || !aligned(src, 16) || ((uint64_t)src_h * row_bytes) % 16 != 0)

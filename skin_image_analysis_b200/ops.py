@@ -107,8 +107,10 @@ def preprocess_u8hwc(src: torch.Tensor, size, layout: int = LAYOUT_NCHW_F32, mea
     use the 15-bit integer-dot-product horizontal pass (<= 0.03 bf16 ulp from the fp32 pass); the fp32
     layout always uses fp32 arithmetic.  ``impl``: "cuda_core" (csrc/preprocess.cu), "tensor_core"
     (csrc/preprocess_tc.cu: vertical pass as a tcgen05 GEMM; NHWC4 layout, src_w % 8 == 0, <= 256 source rows
-    per 128 output rows) or "auto" = tensor_core whenever it applies and ``fixed_point`` allows a reduced-
-    precision pass (0.115 ms vs 0.137 ms at the bench shape), else cuda_core.
+    per 128 output rows), "tensor_core2" (csrc/preprocess_tc2.cu: the horizontal pass is a second tcgen05 product
+    too; additionally <= 4 + 13 + 4 output columns per 40-pixel block, out_w % 4 == 0) or "auto" = tensor_core2, else
+    tensor_core, whenever they apply and ``fixed_point`` allows a reduced-precision pass (0.102 / 0.109 ms vs
+    0.137 ms at the bench shape), else cuda_core.
     """
     _need(src, torch.uint8, "src")
     if src.dim() != 4 or src.shape[3] != 3:
@@ -127,10 +129,13 @@ def preprocess_u8hwc(src: torch.Tensor, size, layout: int = LAYOUT_NCHW_F32, mea
     obi = (ctypes.c_float * 3)(*[-float(m) / float(s) for m, s in zip(mean, std)])
     if impl not in ("auto", "cuda_core", "tensor_core", "tensor_core2"):
         raise ValueError("impl must be 'auto', 'cuda_core', 'tensor_core' or 'tensor_core2'")
-    if impl == "tensor_core2":
-        t2 = _tc2_tables(src.device.index, sh, sw, oh, ow, antialias) if layout == LAYOUT_NHWC4_BF16 else None
-        if t2 is None or src.data_ptr() % 16 != 0:
-            raise SiaError("two-product tensor-core preprocess does not support this geometry / layout")
+    auto_tc = impl == "auto" and fixed_point and layout == LAYOUT_NHWC4_BF16 and src.data_ptr() % 16 == 0
+    t2 = None
+    if (impl == "tensor_core2" or auto_tc) and layout == LAYOUT_NHWC4_BF16 and out.data_ptr() % 32 == 0:
+        t2 = _tc2_tables(src.device.index, sh, sw, oh, ow, antialias)
+    if impl == "tensor_core2" and (t2 is None or src.data_ptr() % 16 != 0):
+        raise SiaError("two-product tensor-core preprocess does not support this geometry / layout")
+    if t2 is not None:
         tsc = (ctypes.c_float * 3)(*[float(scale) / float(s) for s in std])
         v = t2.host.vert
         check(_lib.load().sia_preprocess_tc2_u8hwc(
