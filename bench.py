@@ -87,17 +87,22 @@ def ncu_traffic(stage: str, batch: int):
 
 
 class ClockSampler:
-    """SM clock and throttle reasons WHILE the timed region runs.  NVML polled every ~2 ms from a thread (a 20-step
-    timed region lasts ~10 ms; `nvidia-smi -lms` cannot sample faster than ~100 ms and takes a second to start on an
-    8-GPU box), `nvidia-smi` as the fallback when NVML is not importable."""
+    """SM clock and throttle reasons WHILE the timed region runs, without touching it: the host issues the K steps of
+    the region far ahead of the GPU (a step is launched in ~20 us and runs for ~450 us), so rank 0 polls NVML from the
+    MAIN thread only after every launch of the region has been issued, until the closing event has completed
+    (``sample_until``).  A polling thread -- or eight ranks polling -- delays kernel launches: NVML queries take the
+    driver for milliseconds on an 8-GPU box and cost 35 % of the timed region there.  Without NVML the fallback is
+    ``nvidia-smi -lms 100`` in a subprocess."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, enabled: bool = True):
         self.index, self.rows, self.proc, self.thread = index, [], None, None
-        self.stop = threading.Event()
         self.nvml = None
+        self.enabled = enabled
+        if not enabled:
+            return
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -111,35 +116,39 @@ class ClockSampler:
             self.nvml = pynvml
         except Exception:
             self.nvml = None
-
-    def _poll_nvml(self):
-        n = self.nvml
-        names = (("hw_slowdown", n.nvmlClocksEventReasonHwSlowdown),
-                 ("hw_thermal_slowdown", n.nvmlClocksEventReasonHwThermalSlowdown),
-                 ("sw_thermal_slowdown", n.nvmlClocksEventReasonSwThermalSlowdown),
-                 ("sw_power_cap", n.nvmlClocksEventReasonSwPowerCap))
-        while not self.stop.is_set():
+        if self.nvml is None:                      # fallback: start nvidia-smi here too, i.e. before the barrier
             try:
-                mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
-                mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
-                self.rows.append([mhz, self.max_mhz] + ["Active" if mask & bit else "Not Active" for _nm, bit in names])
+                self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                              "--format=csv,noheader,nounits", "-lms", "100"],
+                                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self.thread = threading.Thread(target=self._read, daemon=True)
+                self.thread.start()
             except Exception:
-                pass
+                self.proc = None
+
+    def _poll_once(self):
+        n = self.nvml
+        names = (n.nvmlClocksEventReasonHwSlowdown, n.nvmlClocksEventReasonHwThermalSlowdown,
+                 n.nvmlClocksEventReasonSwThermalSlowdown, n.nvmlClocksEventReasonSwPowerCap)
+        try:
+            mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+            mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+            self.rows.append([mhz, self.max_mhz] + ["Active" if mask & bit else "Not Active" for bit in names])
+        except Exception:
+            pass
+
+    def sample_until(self, event, max_seconds: float = 120.0):
+        """Call after the last launch of the timed region: polls until ``event`` (recorded at its end) has completed."""
+        if not self.enabled or self.nvml is None:
+            return
+        t0 = time.perf_counter()
+        while True:
+            self._poll_once()                      # at least one sample, taken while the GPU still works on the region
+            if event.query() or time.perf_counter() - t0 > max_seconds:
+                break
             time.sleep(0.002)
 
     def __enter__(self):
-        if self.nvml is not None:
-            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
-            self.thread.start()
-            return self
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
         return self
 
     def _read(self):
@@ -149,10 +158,6 @@ class ClockSampler:
                 self.rows.append([c[0], c[1]] + c[3:7])
 
     def __exit__(self, *a):
-        if self.nvml is not None:
-            self.stop.set()
-            self.thread.join(timeout=1)
-            return
         if self.proc is not None:
             time.sleep(0.15)
             self.proc.terminate()
@@ -387,14 +392,19 @@ def run_ours(args):
     eng.synchronize()
     eng.reset_counts()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # Only rank 0 samples (it prints the line), and only after the region's launches have been issued (ClockSampler).
+    # The sampler is set up BEFORE the barrier: NVML initialisation takes milliseconds, and a rank that enters the
+    # region late makes every other rank wait for it in the closing all-reduce (measured: +45 % at 2 GPUs).
+    clocks = ClockSampler(local, enabled=(rank == 0))
     barrier()
-    with ClockSampler(local) as clocks:
+    with clocks:
         e0.record(eng.stream)
         for s in range(warmup, total_steps):
             resident_step(s)
         with torch.cuda.stream(eng.stream):
             D.allreduce_counts(eng.counts)              # the job's single collective (576 bytes)
         e1.record(eng.stream)
+        clocks.sample_until(e1)                    # every launch of the region is issued; the GPU is still running it
         barrier()
     dt = D.max_over_ranks(e0.elapsed_time(e1) * 1e-3, device=dev)
     value = world * steps * batch / dt
