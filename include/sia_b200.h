@@ -12,6 +12,9 @@
  *   sia_preprocess_u8hwc        np.float32(img)/255            src/tone_bias_dataset.py:335
  *                               skimage.transform.resize       src/tone_bias_dataset.py:425
  *                               image.transpose((2,0,1))       src/tone_bias_dataset.py:470
+ *   sia_preprocess_tc_u8hwc,    the same three call sites for the padded NHWC4 bf16 layout, with the vertical pass
+ *   sia_preprocess_tc2_u8hwc    (tc) or both passes (tc2) of the resize on the tensor cores
+ *   sia_preprocess_tv_u8hwc     v2.Resize + v2.ToDtype + v2.Normalize     notebooks/ToneClassifier/CNNTrialDataset.py:71-76
  *   sia_conv7x7_c3_relu_pool2   Conv2d(3,32,7,'same')+ReLU+MaxPool2d   src/tone_bias_model.py:83-92, :169-172
  *   sia_conv3x3_relu_pool2      Conv2d(C,2C,3,'same')+ReLU+MaxPool2d   src/tone_bias_model.py:83-92, :174-184
  *   sia_linear_splitk           Flatten + Linear(100352,512)           src/tone_bias_model.py:100,111
