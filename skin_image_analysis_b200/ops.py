@@ -145,7 +145,7 @@ def preprocess_u8hwc(src: torch.Tensor, size, layout: int = LAYOUT_NCHW_F32, mea
         return out
     if impl == "tensor_core" or (impl == "auto" and fixed_point and layout == LAYOUT_NHWC4_BF16):
         tc = _tc_tables(src.device.index, sh, sw, oh, ow, antialias) if layout == LAYOUT_NHWC4_BF16 else None
-        if tc is not None and src.data_ptr() % 16 == 0:
+        if tc is not None and src.data_ptr() % 16 == 0 and out.data_ptr() % 32 == 0:
             tsc = (ctypes.c_float * 3)(*[float(scale) / float(s) for s in std])
             check(_lib.load().sia_preprocess_tc_u8hwc(
                 ptr(src), b, sh, sw, ptr(tc.a_packed), ptr(tc.lane_scale), ptr(tc.tile_row0), tc.host.n_tiles,
@@ -153,8 +153,8 @@ def preprocess_u8hwc(src: torch.Tensor, size, layout: int = LAYOUT_NCHW_F32, mea
                 int(tc.host.pads_in_schedule), oh, ow,
                 tsc, obi, ptr(out), stream_ptr()), "sia_preprocess_tc_u8hwc")
             return out
-        if impl == "tensor_core" or (impl == "auto" and fixed_point and layout == LAYOUT_NHWC4_BF16):
-            raise SiaError("tensor-core preprocess does not support this geometry / layout")
+        if impl == "tensor_core":                   # asked for explicitly: refuse loudly; "auto" falls through to the
+            raise SiaError("tensor-core preprocess does not support this geometry / layout")   # CUDA-core kernel
     check(_lib.load().sia_preprocess_u8hwc(
         ptr(src), b, sh, sw, ptr(tab.x_off), ptr(tab.x_w), ptr(tab.x_wq) if fixed_point else 0, tab.host.x_taps,
         ptr(tab.row_w), ptr(tab.row_emit),

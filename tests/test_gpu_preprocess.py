@@ -211,3 +211,18 @@ def test_two_product_pass_large_batches_and_flat_images():
         assert np.all(out == torch.tensor(np.float32(v) / 255.0).to(torch.bfloat16).float().item()), v
     with pytest.raises(_lib.SiaError):                        # 512 x 512 outputs do not fit the 21-slot layout
         _gpu([base[0]], (512, 512), ops.LAYOUT_NHWC4_BF16, impl="tensor_core2")
+
+
+def test_auto_falls_back_when_the_tensor_core_kernels_do_not_fit():
+    """impl="auto" on the NHWC4 layout: a geometry neither tensor-core kernel takes (131-pixel rows are not a multiple
+    of 8 bytes) goes to the CUDA-core kernel, a 512 x 512 output (too many columns per block for the two-product
+    kernel) to the one-product kernel; asking for a kernel explicitly still refuses loudly."""
+    from skin_image_analysis_b200 import _lib, ops
+    odd = helpers.synthetic_u8_image(97, 131, 8, "noise")
+    auto = _gpu([odd], (64, 64), ops.LAYOUT_NHWC4_BF16)
+    assert torch.equal(auto, _gpu([odd], (64, 64), ops.LAYOUT_NHWC4_BF16, impl="cuda_core"))
+    with pytest.raises(_lib.SiaError):
+        _gpu([odd], (64, 64), ops.LAYOUT_NHWC4_BF16, impl="tensor_core")
+    big = helpers.synthetic_u8_image(450, 600, 9, "smooth")
+    auto = _gpu([big], (512, 512), ops.LAYOUT_NHWC4_BF16)
+    assert torch.equal(auto, _gpu([big], (512, 512), ops.LAYOUT_NHWC4_BF16, impl="tensor_core"))
