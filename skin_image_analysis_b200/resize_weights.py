@@ -442,7 +442,9 @@ def tv_tile_plan(y: TvAxis, row_bytes: int, out_w: int, x_taps: int, budget: int
             for i0 in range(0, n_out, tile):
                 i1 = min(i0 + tile, n_out)
                 rows = max(rows, int(y.xmin[i1 - 1]) + y.taps - int(y.xmin[i0]))
-            smem = ((rows * row_bytes + 32 + 15) & ~15) + ((rows * hpitch + 15) & ~15) + 768 * 4 + out_w * 4 + out_w * x_taps * 2 + 16
+            # source window: the larger of the interleaved and the planar (three separately aligned planes) layouts
+            window = max((rows * row_bytes + 32 + 15) & ~15, 3 * ((rows * (row_bytes // 3) + 31) & ~15))
+            smem = window + ((rows * hpitch + 15) & ~15) + 768 * 4 + out_w * 4 + out_w * x_taps * 2 + 16
             if smem <= limit:
                 return tile, rows
     raise ValueError("source rows too long for the shared-memory window of the torchvision-variant kernel")
