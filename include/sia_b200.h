@@ -42,7 +42,7 @@ extern "C" {
 #define SIA_E_INVALID (-1)     /* bad argument (null pointer, non-positive size, misaligned pointer)  */
 #define SIA_E_UNSUPPORTED (-2) /* shape outside what the kernels were built for                       */
 #define SIA_E_DRIVER (-3)      /* could not resolve / call cuTensorMapEncodeTiled                     */
-#define SIA_E_WATCHDOG (-4)    /* a kernel's mbarrier watchdog fired (see sia_debug_watchdog)          */
+#define SIA_E_WATCHDOG (-4)    /* a kernel's mbarrier watchdog fired (see sia_watchdog_status)          */
 
 /* Output layouts of sia_preprocess_u8hwc */
 #define SIA_LAYOUT_NCHW_F32 0   /* [B,3,S,S] float32  -- what ToTensor + default collate produce        */
@@ -57,7 +57,7 @@ const char* sia_error_string(int code);
 /* Fills SM count and compute capability of the current device. */
 int sia_device_info(int* sm_count_host, int* cc_major_host, int* cc_minor_host);
 /* Returns the watchdog word of the current device (0 = never fired); reset != 0 clears it. */
-unsigned int sia_debug_watchdog(int reset);
+unsigned int sia_watchdog_status(int reset);
 
 /* ------------------------------------------------------------------------------------------
  * K1-K3  fused  u8 HWC -> (x/255) -> anti-aliased bilinear resize -> (v-mean)/std -> layout.
@@ -139,13 +139,16 @@ int sia_preprocess_tv_u8hwc(const uint8_t* src, int batch, int src_h, int src_w,
                             const int16_t* y_w, int y_taps, int y_prec, const float* lut_3x256, int out_h, int out_w,
                             int tile_rows, int max_window_rows, int layout, int planar_chw, void* dst, void* stream);
 
-/* Debug / A-B: on != 0 makes sia_preprocess_tv_u8hwc use its byte-wise kernel even where the IDP.2A instance
- * applies (the two must agree bit for bit; tests compare them). */
-int sia_debug_tv_force_generic(int on);
-
 /* Model boundary: NCHW fp32 [B,3,h,w] (the tensor the reference DataLoader feeds to model(images),
  * src/tone_bias_test.py:190-196) -> padded NHWC4 bf16 [B,h,w+8,4] (SIA_LAYOUT_NHWC4_BF16). */
 int sia_nchw_f32_to_nhwc4_bf16(const float* src, int batch, int h, int w, void* dst, void* stream);
+
+/* Floor pooling on odd sizes (tone_bias_optuna.define_isic_model with n_conv_layers >= 4: 14 -> 7 -> 3 -> 1,
+ * src/tone_bias_optuna.py:143-152; nn.MaxPool2d drops the last row / column): the conv kernels take even sizes, so
+ * an odd-sized activation [B,h,w,C] bf16 is copied into an even-sized buffer [B,out_h,out_w,C] whose cells outside
+ * the valid valid_h x valid_w corner are zero -- exactly the zero padding the next 'same' convolution would see. */
+int sia_pad_nhwc_bf16(const void* in_nhwc, int batch, int h, int w, int channels, int valid_h, int valid_w,
+                      void* out_nhwc, int out_h, int out_w, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Weight packing (one-off, at model load).  Inputs are the reference's state_dict tensors
@@ -221,63 +224,6 @@ int sia_head_tail_chain(const float* partial, int splits, int m, int n1, int n1_
  * ------------------------------------------------------------------------------------------ */
 int sia_confusion_counts(const uint8_t* pred, const uint8_t* label, const uint8_t* groups, long long n,
                          long long groups_stride, int n_attr, int n_groups, long long* counts, void* stream);
-
-/* ------------------------------------------------------------------------------------------
- * Debug / bring-up: run a list of tcgen05.mma (kind::f16, bf16 inputs) over a caller-supplied
- * shared-memory image and return the 128 x n fp32 accumulator.  Descriptor start addresses are
- * relative to the (1024-byte aligned) image base.  Used by tests/test_umma_probe.py to pin the
- * descriptor conventions the conv kernels rely on; cycles_host (optional) gets the SM-clock
- * cycles of `repeat` back-to-back issues of the list.
- * ------------------------------------------------------------------------------------------ */
-int sia_debug_umma_probe(const void* smem_image, int image_bytes, const uint64_t* a_desc_host,
-                         const uint64_t* b_desc_host, int n_mma, int n, float* out_128xn, int repeat,
-                         long long* cycles_host, void* stream);
-
-/* Same, with the MMA kind (0 = kind::f16 with bf16 inputs, 1 = kind::i8) and the 32-bit instruction
- * descriptor given by the caller (0 = default bf16 K-major); the accumulator comes back as raw 32-bit words
- * (fp32 for kind 0, int32 for kind 1). */
-int sia_debug_umma_probe_ex(const void* smem_image, int image_bytes, const uint64_t* a_desc_host,
-                            const uint64_t* b_desc_host, int n_mma, int n, int kind, uint32_t idesc,
-                            void* out_128xn_raw, int repeat, long long* cycles_host, void* stream);
-
-/* Debug (timing only): the following probes move to the other of two accumulators every switch_every MMAs
- * (0 = off), optionally with a tcgen05.commit at every switch: the cost of short accumulation chains. */
-int sia_debug_umma_probe_switch(int switch_every, int commit_each);
-
-/* Debug / bring-up: tcgen05.mma with the A operand in tensor memory.  a_words [128][a_cols] uint32 (row m = the
- * 32-bit words thread m stores to TMEM columns 0 .. a_cols-1 of lane m); UMMA i reads A at TMEM column a_col_step * i
- * and B through b_desc_host[i] (relative to the shared-memory image, as for sia_debug_umma_probe); the 128 x n fp32
- * accumulator is returned.  idesc 0 = bf16 K-major (128, n). */
-int sia_debug_umma_ts_probe(const void* smem_image, int image_bytes, const void* a_words, int a_cols, int a_col_step,
-                            const uint64_t* b_desc_host, int n_mma, int n, uint32_t idesc, float* out_128xn,
-                            void* stream);
-
-/* Debug / bring-up: one TMA tiled load of a bf16 tensor (rank 2..4; dims / box in elements, innermost
- * first; strides in bytes for dims 1..rank-1; swizzle_bytes in {0,32,64,128}) at the given coordinates;
- * `out` receives the box bytes exactly as they landed in shared memory.  repeat > 1 issues that many
- * loads back to back (coordinate step_dim advanced by step each time) and reports the SM-clock cycles
- * until all have landed in cycles_host: the TMA engine's throughput for that box shape. */
-int sia_debug_tma_probe(const void* base, int rank, const uint64_t* dims_host, const uint64_t* strides_bytes_host,
-                        const uint32_t* box_host, int swizzle_bytes, const int* coords_host, void* out,
-                        int repeat, int step_dim, int step, long long* cycles_host, void* stream);
-
-/* Debug: event trace of CTA 0 of the conv kernels: 64 tiles x 8 int64 clock64 stamps (producer stage-free /
- * TMA-issued, MMA accumulator-free / operands-landed / tile-issued, epilogue accumulator-complete / drained /
- * stored); NULL switches it off (default). */
-int sia_debug_set_trace(long long* device_buffer_or_null);
-
-/* Debug: per-CTA role timing of the conv kernels.  device_buffer holds 8 uint64 per CTA (SM-clock cycles:
- * producer wait-for-stage, MMA wait-for-accumulator, MMA wait-for-operands, MMA loop, epilogue
- * wait-for-accumulator, epilogue loop, tiles); NULL switches the instrumentation off (default). */
-int sia_debug_set_stats(unsigned long long* device_buffer_or_null);
-
-/* Debug / bring-up: lane-operations per SM clock (one resident CTA of 1024 threads) for
- * FFMA, PRMT, I2F.U8(+IADD), DP4A, DP2A, IMAD, SHF, FFMA2 -- out_host needs room for 8 doubles. */
-int sia_debug_alu_rates(double* out_host, int n);
-
-/* Debug / bring-up: TMEM read rate in bytes per SM clock of back-to-back tcgen05.ld.32x32b for
- * (warps, columns per load) = (1,32) (4,32) (8,32) (4,8) (8,8) (4,1) -- out_host needs room for 6 doubles. */
-int sia_debug_tmem_ld_rates(double* out_host, int n);
 
 #ifdef __cplusplus
 }

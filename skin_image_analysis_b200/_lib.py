@@ -12,6 +12,7 @@ from ctypes import c_char_p, c_float, c_int, c_int32, c_longlong, c_size_t, c_ui
 HERE = os.path.dirname(os.path.abspath(__file__))
 # SIA_LIB_PATH: A/B a differently built library (tools/stage_times.py); never a fallback -- it must exist
 LIB_PATH = os.environ.get("SIA_LIB_PATH") or os.path.join(HERE, "libsia_b200.so")
+DEBUG_LIB_PATH = os.path.join(HERE, "libsia_b200_debug.so")     # bring-up probes (tests / tools only)
 
 LAYOUT_NCHW_F32 = 0
 LAYOUT_NCHW_BF16 = 1
@@ -25,7 +26,7 @@ SIGNATURES = {
     "sia_version": (c_int, []),
     "sia_error_string": (c_char_p, [c_int]),
     "sia_device_info": (c_int, [_P, _P, _P]),
-    "sia_debug_watchdog": (c_uint, [c_int]),
+    "sia_watchdog_status": (c_uint, [c_int]),
     "sia_preprocess_u8hwc": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, c_int, _P, _P, _P, c_int, c_int,
                                      ctypes.POINTER(c_float), ctypes.POINTER(c_float), c_int, c_int, _P, _P]),
     "sia_preprocess_tc_u8hwc": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, c_int, c_int, _P, c_int, c_int, c_int,
@@ -36,6 +37,7 @@ SIGNATURES = {
                                         c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "sia_debug_tv_force_generic": (c_int, [c_int]),
     "sia_nchw_f32_to_nhwc4_bf16": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
+    "sia_pad_nhwc_bf16": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P]),
     "sia_pack_conv7x7_c3": (c_int, [_P, _P, _P]),
     "sia_pack_conv7x7_c3_bytes": (c_size_t, []),
     "sia_pack_conv3x3": (c_int, [_P, c_int, c_int, _P, _P]),
@@ -52,6 +54,12 @@ SIGNATURES = {
     "sia_head_tail": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int,
                               c_int, _P, _P]),
     "sia_confusion_counts": (c_int, [_P, _P, _P, c_longlong, c_longlong, c_int, c_int, _P, _P]),
+    "sia_debug_set_stats": (c_int, [_P]),
+    "sia_debug_set_trace": (c_int, [_P]),
+}
+
+# include/sia_b200_debug.h group (2): exported by libsia_b200_debug.so
+DEBUG_SIGNATURES = {
     "sia_debug_umma_probe": (c_int, [_P, c_int, ctypes.POINTER(c_uint64), ctypes.POINTER(c_uint64), c_int, c_int,
                                      _P, c_int, ctypes.POINTER(c_longlong), _P]),
     "sia_debug_umma_probe_ex": (c_int, [_P, c_int, ctypes.POINTER(c_uint64), ctypes.POINTER(c_uint64), c_int, c_int,
@@ -62,13 +70,12 @@ SIGNATURES = {
     "sia_debug_tma_probe": (c_int, [_P, c_int, ctypes.POINTER(c_uint64), ctypes.POINTER(c_uint64),
                                     ctypes.POINTER(ctypes.c_uint32), c_int, ctypes.POINTER(c_int), _P, c_int, c_int,
                                     c_int, ctypes.POINTER(c_longlong), _P]),
-    "sia_debug_set_stats": (c_int, [_P]),
-    "sia_debug_set_trace": (c_int, [_P]),
     "sia_debug_tmem_ld_rates": (c_int, [ctypes.POINTER(ctypes.c_double), c_int]),
     "sia_debug_alu_rates": (c_int, [ctypes.POINTER(ctypes.c_double), c_int]),
 }
 
 _lib = None
+_debug_lib = None
 
 
 class SiaError(RuntimeError):
@@ -93,10 +100,26 @@ def load() -> ctypes.CDLL:
     return lib
 
 
+def load_debug() -> ctypes.CDLL:
+    """The probe library (tests/test_umma_probe.py, tools/): never needed by the product path."""
+    global _debug_lib
+    if _debug_lib is not None:
+        return _debug_lib
+    if not os.path.exists(DEBUG_LIB_PATH):
+        raise SiaError(f"{DEBUG_LIB_PATH} is missing: build it with `python -m skin_image_analysis_b200.build`")
+    lib = ctypes.CDLL(DEBUG_LIB_PATH)
+    for name, (res, args) in DEBUG_SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _debug_lib = lib
+    return lib
+
+
 def check(rc: int, what: str = "") -> None:
     if rc != 0:
         msg = load().sia_error_string(rc).decode()
-        wd = load().sia_debug_watchdog(0)
+        wd = load().sia_watchdog_status(0)
         extra = f" [watchdog 0x{wd:08x}]" if wd not in (0, 0xFFFFFFFF) else ""
         raise SiaError(f"{what or 'sia call'} failed: {msg} (code {rc}){extra}")
 

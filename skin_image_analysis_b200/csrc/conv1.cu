@@ -414,7 +414,7 @@ extern "C" int sia_conv7x7_c3_relu_pool2_strided(const void* in_nhwc4, int batch
   const int total = tiles_y * tiles_x * batch;
   const int smem = 1024 + C1_B_BYTES + C1_NSTAGE * C1_STAGE_STRIDE + ONES_BYTES + C1_BIAS_BYTES +
                    (2 * C1_NSTAGE + 2 * C1_NACC + 2) * 8;
-  static int configured = 0;
+  static SmemSlots configured = {};
   if (int rc2 = ensure_dynamic_smem(conv1_kernel, smem, &configured)) return rc2;
   const int grid = total < sm_count() ? total : sm_count();
   conv1_kernel<<<grid, C1_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(

@@ -768,7 +768,7 @@ static int launch_conv3x3_pair(const void* in, int batch, int h, int w, const vo
   const int total = tiles_y * tiles_x * batch;
   const int smem = 1024 + CP_B_BYTES + CP_NSTAGE * CP_STAGE_STRIDE + ONES_BYTES + CP_BIAS_BYTES +
                    (2 * CP_NSTAGE + 2 * CV_NACC + 2) * 8;
-  static int configured = 0;
+  static SmemSlots configured = {};
   if (int rc2 = ensure_dynamic_smem(conv3x3_pair_kernel, smem, &configured)) return rc2;
   const int grid = total < sm_count() ? total : sm_count();
   conv3x3_pair_kernel<<<grid, CV_THREADS, smem, st>>>(tmap, static_cast<const uint8_t*>(w_packed), bias,
@@ -819,7 +819,7 @@ static int launch_conv3x3(const void* in, int batch, int h, int w, const void* w
   const int smem = 1024 + C::B_BYTES + NSTAGE * C::STAGE_STRIDE + ONES_BYTES + C::BIAS_BYTES +
                    (2 * NSTAGE + 2 * CV_NACC + 2) * 8;
   auto kern = conv3x3_kernel<CIN, COUT, NSTAGE>;
-  static int configured = 0;
+  static SmemSlots configured = {};
   if (int rc2 = ensure_dynamic_smem(kern, smem, &configured)) return rc2;
   const int grid = total < sm_count() ? total : sm_count();
   kern<<<grid, CV_THREADS, smem, st>>>(tmap, static_cast<const uint8_t*>(w_packed), bias,
@@ -838,7 +838,7 @@ static int launch_conv3x3_stream_t(const CUtensorMap& tmap, int nchunk, int batc
   const int smem = 1024 + CS_NB * COUT * 128 + TILES * nchunk * CS_CHUNK_STRIDE + ONES_BYTES + COUT * 32 +
                    (2 * CS_NB + 6) * 8;
   auto kern = conv3x3_stream_kernel<COUT, TILES>;
-  static int configured = 0;
+  static SmemSlots configured = {};
   if (int rc2 = ensure_dynamic_smem(kern, smem, &configured)) return rc2;
   const int grid = passes < sm_count() ? passes : sm_count();
   kern<<<grid, CV_THREADS, smem, st>>>(tmap, static_cast<const uint8_t*>(w_packed), bias,

@@ -1,6 +1,7 @@
 // Library-wide state and the small informational entry points of the C ABI.
 #include "sia_host.cuh"
 #include "sia_ptx.cuh"
+#include "../../include/sia_b200_debug.h"
 
 namespace sia {
 
@@ -9,22 +10,47 @@ static volatile unsigned int* g_wd_host = nullptr;
 volatile unsigned int* watchdog_host_word() { return g_wd_host; }
 
 int ensure_watchdog() {
-  if (g_wd_host != nullptr) return 0;
-  unsigned int* h = nullptr;
-  cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&h), sizeof(unsigned int), cudaHostAllocMapped);
-  if (e != cudaSuccess) return (int)e;
-  *h = 0;
+  // one pinned host word per process; the device-side pointer to it is a per-DEVICE symbol
+  static bool uploaded[kMaxDevices] = {false};
+  const int dev = current_device();
+  if (g_wd_host != nullptr && uploaded[dev]) return 0;
+  if (g_wd_host == nullptr) {
+    unsigned int* h = nullptr;
+    cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&h), sizeof(unsigned int),
+                                  cudaHostAllocMapped | cudaHostAllocPortable);
+    if (e != cudaSuccess) return (int)e;
+    *h = 0;
+    g_wd_host = h;
+  }
   unsigned int* d = nullptr;
-  e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&d), h, 0);
+  cudaError_t e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&d), const_cast<unsigned int*>(g_wd_host), 0);
   if (e != cudaSuccess) return (int)e;
   e = cudaMemcpyToSymbol(g_watchdog_word, &d, sizeof(d));
   if (e != cudaSuccess) return (int)e;
-  g_wd_host = h;
+  uploaded[dev] = true;
   return 0;
+}
+
+// [B,h,w,C] bf16 -> [B,hp,wp,C] bf16: copies the valid hv x wv corner, zero everywhere else (16-byte vectors).
+__global__ void pad_nhwc_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int h, int w, int hp, int wp,
+                                int hv, int wv, int c8, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cc = (int)(i % c8);
+    long long r = i / c8;
+    const int x = (int)(r % wp);
+    r /= wp;
+    const int y = (int)(r % hp);
+    const long long b = r / hp;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (y < hv && x < wv) v = in[((b * h + y) * w + x) * c8 + cc];
+    out[i] = v;
+  }
 }
 
 }  // namespace sia
 
+#ifndef SIA_DEBUG_LIB
 extern "C" int sia_debug_set_trace(long long* device_buffer_or_null) {
 #ifndef SIA_INSTRUMENT
   if (device_buffer_or_null != nullptr) return SIA_E_UNSUPPORTED;   // needs a -DSIA_INSTRUMENT build
@@ -66,7 +92,22 @@ int sia_device_info(int* sm_count_host, int* cc_major_host, int* cc_minor_host) 
   return 0;
 }
 
-unsigned int sia_debug_watchdog(int reset) {
+int sia_pad_nhwc_bf16(const void* in_nhwc, int batch, int h, int w, int channels, int valid_h, int valid_w,
+                      void* out_nhwc, int out_h, int out_w, void* stream) {
+  using namespace sia;
+  SIA_REQUIRE(in_nhwc && out_nhwc && batch >= 1 && h >= 1 && w >= 1 && out_h >= 1 && out_w >= 1);
+  SIA_REQUIRE(valid_h >= 0 && valid_w >= 0 && valid_h <= h && valid_w <= w && valid_h <= out_h && valid_w <= out_w);
+  SIA_REQUIRE(channels >= 8 && channels % 8 == 0 && aligned(in_nhwc, 16) && aligned(out_nhwc, 16));
+  const int c8 = channels / 8;
+  const long long total = (long long)batch * out_h * out_w * c8;
+  const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  pad_nhwc_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(in_nhwc), static_cast<uint4*>(out_nhwc), h, w, out_h, out_w, valid_h, valid_w, c8,
+      total);
+  return launch_status();
+}
+
+unsigned int sia_watchdog_status(int reset) {
   volatile unsigned int* w = sia::watchdog_host_word();
   if (w == nullptr) return 0;
   const unsigned int v = *w;
@@ -75,3 +116,4 @@ unsigned int sia_debug_watchdog(int reset) {
 }
 
 }  // extern "C"
+#endif  // SIA_DEBUG_LIB

@@ -2,7 +2,6 @@
 // relocatable device code, one nvcc invocation (see skin_image_analysis_b200/build.py).
 #include "core.cu"
 #include "tmap.cu"
-#include "probe.cu"
 #include "counts.cu"
 #include "preprocess.cu"
 #include "preprocess_tc.cu"

@@ -354,7 +354,7 @@ extern "C" int sia_linear_splitk(const void* a_bf16, const void* w_bf16, int m, 
     if (rc != 0) return rc;
   }
   const int smem = 1024 + LN_NSTAGE * LN_STAGE_BYTES + (2 * LN_NSTAGE + 2) * 8;
-  static int configured = 0;
+  static SmemSlots configured = {};
   if (int rc2 = ensure_dynamic_smem(linear_splitk_kernel, smem, &configured)) return rc2;
   dim3 grid((m + LN_BM - 1) / LN_BM, n / LN_BN, splits);
   linear_splitk_kernel<<<grid, LN_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(ta, tw, partial, m, n,

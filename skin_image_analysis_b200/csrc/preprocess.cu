@@ -276,15 +276,15 @@ extern "C" int sia_preprocess_u8hwc(const uint8_t* src, int batch, int src_h, in
   const bool fast = x_wq != nullptr && x_taps == 8 && layout != SIA_LAYOUT_NCHW_F32;
   if (fast) {
     for (int c = 0; c < 3; ++c) p.scale[c] *= (1.0f / 32768.0f);   // the integer pass carries a 2^15 factor
-    static int configured = 0;
+    static SmemSlots configured = {};
     if (int rc2 = ensure_dynamic_smem(preprocess_kernel<8, true>, smem, &configured)) return rc2;
     preprocess_kernel<8, true><<<grid, PRE_THREADS, smem, st>>>(p);
   } else if (x_taps == 8) {
-    static int configured = 0;
+    static SmemSlots configured = {};
     if (int rc2 = ensure_dynamic_smem(preprocess_kernel<8, false>, smem, &configured)) return rc2;
     preprocess_kernel<8, false><<<grid, PRE_THREADS, smem, st>>>(p);
   } else {
-    static int configured = 0;
+    static SmemSlots configured = {};
     if (int rc2 = ensure_dynamic_smem(preprocess_kernel<16, false>, smem, &configured)) return rc2;
     preprocess_kernel<16, false><<<grid, PRE_THREADS, smem, st>>>(p);
   }

@@ -538,7 +538,7 @@ extern "C" int sia_preprocess_tc2_u8hwc(const uint8_t* src, int batch, int src_h
     if (smem <= 227 * 1024) break;
   }
   if (p.n_raw < 2) return SIA_E_UNSUPPORTED;
-  static int configured = 0;
+  static SmemSlots configured = {};
   if (int rc2 = ensure_dynamic_smem(preprocess_tc2_kernel, smem, &configured)) return rc2;
   int grid = (sm_count() / n_tiles) * n_tiles;
   if (grid > batch * n_tiles) grid = batch * n_tiles;

@@ -399,7 +399,7 @@ extern "C" int sia_preprocess_tv_u8hwc(const uint8_t* src, int batch, int src_h,
   // 7 x 7 taps = down-sampling by 2..3 on both axes (600x450 -> 224x224, the case the transform is used for)
   const bool unrolled = x_taps == 7 && y_taps == 7;
   const bool fast = unrolled && !planar_chw && (src_w * 3) % 4 == 0 && out_w % 4 == 0 && !g_tv_force_generic;
-  static int configured[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  static SmemSlots configured[9] = {};
 #define SIA_TV_LAUNCH_FAST(LAYOUT, SLOT)                                                                     \
   do {                                                                                                       \
     if (int rc = ensure_dynamic_smem(preprocess_tv_fast_kernel<LAYOUT>, (int)smem, &configured[SLOT])) return rc; \

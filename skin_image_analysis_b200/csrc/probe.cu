@@ -153,7 +153,7 @@ extern "C" int sia_debug_umma_probe_ex(const void* smem_image, int image_bytes, 
   long long* d_cycles = nullptr;
   if (cycles_host) SIA_CUDA_OK(cudaMalloc(&d_cycles, sizeof(long long)));
   const int smem = image_bytes + 1024;
-  static int configured = 0;
+  static SmemSlots configured = {};
   if (int rc2 = ensure_dynamic_smem(umma_probe_kernel, smem, &configured)) return rc2;
   umma_probe_kernel<<<1, 128, smem, st>>>(static_cast<const uint8_t*>(smem_image), p, out_128xn, d_cycles);
   int rc = launch_status();
@@ -249,7 +249,7 @@ extern "C" int sia_debug_tma_probe(const void* base, int rank, const uint64_t* d
   SIA_REQUIRE(bytes % 16 == 0 && bytes <= 48 * 1024 && bytes * (uint64_t)repeat < (1u << 20));
   p.box_bytes = (uint32_t)bytes;
   const int smem = 4 * (((int)bytes + 1023) & ~1023) + 1024;
-  static int configured = 0;
+  static SmemSlots configured = {};
   if (int rc2 = ensure_dynamic_smem(tma_probe_kernel, smem, &configured)) return rc2;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   long long* d_cycles = nullptr;
@@ -555,7 +555,7 @@ extern "C" int sia_debug_umma_ts_probe(const void* smem_image, int image_bytes, 
   for (int i = 0; i < n_mma; ++i) p.b_desc[i] = b_desc_host[i];
   p.n_mma = n_mma; p.n = n; p.a_cols = a_cols; p.a_col_step = a_col_step; p.image_bytes = image_bytes; p.idesc = idesc;
   const int smem = image_bytes + 1024;
-  static int configured = 0;
+  static SmemSlots configured = {};
   if (int rc = ensure_dynamic_smem(umma_ts_probe_kernel, smem, &configured)) return rc;
   umma_ts_probe_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint8_t*>(smem_image), static_cast<const uint32_t*>(a_words), p, out_128xn);

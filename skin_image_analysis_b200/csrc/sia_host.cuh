@@ -33,24 +33,34 @@ inline int launch_status() {
 
 inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
-inline int sm_count() {
-  static int cached = 0;
-  if (cached == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) cached = 148;
-  }
-  return cached;
+constexpr int kMaxDevices = 64;     // per-device caches below are indexed by the CUDA device ordinal
+
+inline int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 0;
+  return dev;
 }
 
-// Raises the dynamic shared-memory limit of a kernel once (per process, i.e. per GPU): keeps
-// cudaFuncSetAttribute out of CUDA-graph capture after the first, un-captured, warm-up launch.
+inline int sm_count() {
+  static int cached[kMaxDevices] = {0};
+  const int dev = current_device();
+  if (cached[dev] == 0) {
+    if (cudaDeviceGetAttribute(&cached[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) cached[dev] = 148;
+  }
+  return cached[dev];
+}
+
+// Raises the dynamic shared-memory limit of a kernel once PER DEVICE (function attributes are per device): keeps
+// cudaFuncSetAttribute out of CUDA-graph capture after the first, un-captured, warm-up launch on that device.
+// `configured` is the call site's own static table, one slot per device ordinal.
+struct SmemSlots { int bytes[kMaxDevices]; };
 template <typename Kernel>
-inline int ensure_dynamic_smem(Kernel kern, int bytes, int* configured) {
-  if (*configured < bytes) {
+inline int ensure_dynamic_smem(Kernel kern, int bytes, SmemSlots* configured) {
+  int& have = configured->bytes[current_device()];
+  if (have < bytes) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return (int)e;
-    *configured = bytes;
+    have = bytes;
   }
   return 0;
 }

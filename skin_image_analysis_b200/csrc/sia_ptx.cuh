@@ -16,7 +16,7 @@ namespace sia {
 // ------------------------------------------------------------------------------------------
 // The library is built as ONE translation unit (libsia_unity.cu), so this is the single copy.
 // It points at a word of pinned, device-mapped HOST memory: a trap kills the CUDA context, the
-// host word survives and sia_debug_watchdog() can still say which wait timed out.
+// host word survives and sia_watchdog_status() can still say which wait timed out.
 static __device__ volatile unsigned int* g_watchdog_word = nullptr;
 
 // Optional per-CTA role timing (sia_debug_set_stats): 8 counters per CTA, SM clock cycles.

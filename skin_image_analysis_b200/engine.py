@@ -70,8 +70,8 @@ class EvalEngine:
             self.slot_ready = [torch.cuda.Event() for _ in range(n_slots)]     # H2D into the slot finished
             self.slot_free = [torch.cuda.Event() for _ in range(n_slots)]      # kernels reading the slot finished
             self.graphs = [None] * n_slots
-            # preprocess + first block (one launch per 32 output channels) + 3x3 blocks + fc1 + tail
-            self.launches_per_batch = 1 + len(self.plan.convs[0][0]) + (len(self.plan.convs) - 1) + 2
+            # preprocess + the forward pass (first block: one launch per 32 output channels, 3x3 blocks, fc1, tail)
+            self.launches_per_batch = 1 + self.plan.launches
             if use_graph:
                 self._capture()
 

@@ -19,13 +19,17 @@ from ._lib import (LAYOUT_NCHW_BF16, LAYOUT_NCHW_F32, LAYOUT_NHWC4_BF16, NHWC4_P
 __all__ = [
     "preprocess_u8hwc", "nchw_f32_to_nhwc4", "pack_conv7x7_c3", "pack_conv3x3", "pack_linear_chw_to_hwc",
     "conv7x7_c3_relu_pool2", "conv3x3_relu_pool2", "linear_splitk", "head_tail", "head_tail_chain", "confusion_counts",
-    "umma_probe", "tma_probe", "LAYOUT_NCHW_F32", "LAYOUT_NCHW_BF16", "LAYOUT_NHWC4_BF16", "NHWC4_PAD",
+    "pad_nhwc", "LAYOUT_NCHW_F32", "LAYOUT_NCHW_BF16", "LAYOUT_NHWC4_BF16", "NHWC4_PAD",
 ]
 
 
 def _need(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
         raise SiaError(f"{name}: expected a CUDA tensor (there is no CPU fallback)")
+    if t.device.index != torch.cuda.current_device():
+        # launches go to the CURRENT device's stream: one process per GPU, or wrap the call in torch.cuda.device(...)
+        raise SiaError(f"{name}: tensor lives on {t.device} but the current CUDA device is "
+                       f"cuda:{torch.cuda.current_device()}")
     if t.dtype != dtype:
         raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
     if not t.is_contiguous():
@@ -297,6 +301,20 @@ def conv3x3_relu_pool2(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tens
     return out
 
 
+def pad_nhwc(x: torch.Tensor, valid_hw, out_hw, out: torch.Tensor | None = None) -> torch.Tensor:
+    """[B,h,w,C] bf16 -> [B,out_h,out_w,C] bf16 holding the valid corner of ``x``, zero elsewhere (floor pooling on
+    odd sizes: the next conv kernel wants even sizes and zero padding beyond the valid corner)."""
+    _need(x, torch.bfloat16, "x")
+    b, h, w, c = x.shape
+    if out is None:
+        out = torch.empty((b, out_hw[0], out_hw[1], c), dtype=torch.bfloat16, device=x.device)
+    else:
+        _need(out, torch.bfloat16, "out")
+    check(_lib.load().sia_pad_nhwc_bf16(ptr(x), b, h, w, c, int(valid_hw[0]), int(valid_hw[1]), ptr(out),
+                                        int(out_hw[0]), int(out_hw[1]), stream_ptr()), "sia_pad_nhwc_bf16")
+    return out
+
+
 # -------------------------------------------------------------------------------------------------
 # K5 / K6 linear part
 # -------------------------------------------------------------------------------------------------
@@ -359,6 +377,8 @@ def head_tail_chain(partial, n1: int, b1, layers, label=None, groups=None, n_gro
         _need(label, torch.uint8, "label")
         _need(groups, torch.uint8, "groups")
         n_attr, stride = groups.shape
+        if tuple(counts.shape) != (n_attr, n_groups, 2, 2):
+            raise ValueError("counts must be [n_attr, n_groups, 2, 2]")
     k = len(layers)
     wt_arr = (ctypes.c_void_p * k)(*[wt.data_ptr() for wt, _ in layers])
     b_arr = (ctypes.c_void_p * k)(*[b.data_ptr() for _, b in layers])
@@ -394,71 +414,3 @@ def confusion_counts(pred: torch.Tensor, label: torch.Tensor, groups: torch.Tens
     check(_lib.load().sia_confusion_counts(ptr(pred), ptr(label), ptr(groups), n, n, n_attr, n_groups, ptr(counts),
                                            stream_ptr()), "sia_confusion_counts")
     return counts
-
-
-# -------------------------------------------------------------------------------------------------
-# bring-up probe
-# -------------------------------------------------------------------------------------------------
-def umma_probe(image: torch.Tensor, a_descs, b_descs, n: int, repeat: int = 1, want_cycles: bool = False):
-    _need(image, torch.uint8, "image")
-    k = len(a_descs)
-    a = (ctypes.c_uint64 * k)(*[int(d) for d in a_descs])
-    b = (ctypes.c_uint64 * k)(*[int(d) for d in b_descs])
-    out = torch.zeros((128, n), dtype=torch.float32, device=image.device)
-    cyc = ctypes.c_longlong(0)
-    check(_lib.load().sia_debug_umma_probe(ptr(image), image.numel(), a, b, k, n, ptr(out), repeat,
-                                           ctypes.byref(cyc) if want_cycles else None, stream_ptr()),
-          "sia_debug_umma_probe")
-    torch.cuda.synchronize()
-    return (out, cyc.value) if want_cycles else out
-
-
-def umma_ts_probe(image: torch.Tensor, a_words: torch.Tensor, a_col_step: int, b_descs, n: int, idesc: int = 0):
-    """tcgen05.mma with A in tensor memory (bring-up): a_words [128, a_cols] int32 = the words thread m stores to
-    TMEM lane m; returns the 128 x n fp32 accumulator."""
-    _need(image, torch.uint8, "image")
-    _need(a_words, torch.int32, "a_words")
-    k = len(b_descs)
-    b = (ctypes.c_uint64 * k)(*[int(d) for d in b_descs])
-    out = torch.zeros((128, n), dtype=torch.float32, device=image.device)
-    check(_lib.load().sia_debug_umma_ts_probe(ptr(image), image.numel(), ptr(a_words), a_words.shape[1], int(a_col_step),
-                                              b, k, n, int(idesc), ptr(out), stream_ptr()), "sia_debug_umma_ts_probe")
-    torch.cuda.synchronize()
-    return out
-
-
-def umma_probe_i8(image: torch.Tensor, a_descs, b_descs, n: int, idesc: int, repeat: int = 1,
-                  want_cycles: bool = False):
-    """kind::i8 variant of ``umma_probe``: returns the 128 x n int32 accumulator."""
-    _need(image, torch.uint8, "image")
-    k = len(a_descs)
-    a = (ctypes.c_uint64 * k)(*[int(d) for d in a_descs])
-    b = (ctypes.c_uint64 * k)(*[int(d) for d in b_descs])
-    out = torch.zeros((128, n), dtype=torch.int32, device=image.device)
-    cyc = ctypes.c_longlong(0)
-    check(_lib.load().sia_debug_umma_probe_ex(ptr(image), image.numel(), a, b, k, n, 1, int(idesc), ptr(out), repeat,
-                                              ctypes.byref(cyc) if want_cycles else None, stream_ptr()),
-          "sia_debug_umma_probe_ex")
-    torch.cuda.synchronize()
-    return (out, cyc.value) if want_cycles else out
-
-
-def tma_probe(t: torch.Tensor, dims, strides_bytes, box, swizzle_bytes: int, coords, repeat: int = 1,
-              step_dim: int = 0, step: int = 0):
-    """One TMA box load of a bf16 tensor -> the shared-memory bytes as uint8 (bring-up tests).  With
-    repeat > 1 returns (bytes, cycles): `repeat` loads in flight, coordinate step_dim advanced by step."""
-    _need(t, torch.bfloat16, "t")
-    rank = len(dims)
-    nbytes = 2
-    for b in box:
-        nbytes *= int(b)
-    out = torch.zeros(nbytes, dtype=torch.uint8, device=t.device)
-    cyc = ctypes.c_longlong(0)
-    check(_lib.load().sia_debug_tma_probe(
-        ptr(t), rank, (ctypes.c_uint64 * rank)(*[int(d) for d in dims]),
-        (ctypes.c_uint64 * max(1, rank - 1))(*[int(s) for s in strides_bytes]),
-        (ctypes.c_uint32 * rank)(*[int(b) for b in box]), int(swizzle_bytes),
-        (ctypes.c_int * rank)(*[int(c) for c in coords]), ptr(out), int(repeat), int(step_dim), int(step),
-        ctypes.byref(cyc) if repeat > 1 else None, stream_ptr()), "sia_debug_tma_probe")
-    torch.cuda.synchronize()
-    return (out, cyc.value) if repeat > 1 else out

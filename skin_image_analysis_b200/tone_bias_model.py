@@ -28,6 +28,52 @@ def _round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
+def infer_image_size(n_blocks: int, c_last: int, in_features: int, prefer: int = 224) -> int:
+    """Image size from the first Linear: in_features = c_last * side^2 with side = the image size floor-halved
+    n_blocks times.  The reference hard-codes 224 (tone_bias_model.py:69-70, tone_bias_optuna.py:130): 224 wins
+    whenever it is consistent; otherwise the smallest consistent size (side << n_blocks)."""
+    side = int(round((in_features / c_last) ** 0.5))
+    if side < 1 or c_last * side * side != in_features:
+        raise SiaError(f"first Linear ({in_features} inputs) does not match {c_last} channels of a square image")
+    if (prefer >> n_blocks) == side:
+        return prefer
+    return side << n_blocks
+
+
+def fold_batchnorm(weight: torch.Tensor, bias: torch.Tensor, bn: nn.BatchNorm2d):
+    """Eval-mode BatchNorm2d after a convolution (the layer the reference keeps commented out between conv and ReLU,
+    tone_bias_model.py:88) folded into the convolution: y = g * (conv(x) + b - mean) / sqrt(var + eps) + beta
+    == conv'(x) + b' with w' = w * s, b' = (b - mean) * s + beta, s = g / sqrt(var + eps).  The kernels' fused
+    bias + ReLU + pool epilogue then needs no extra pass."""
+    if bn.running_mean is None or bn.running_var is None:
+        raise SiaError("BatchNorm2d without running statistics cannot be evaluated in eval mode")
+    s = (bn.running_var.detach().float() + bn.eps).rsqrt()
+    beta = torch.zeros_like(s)
+    if bn.affine:
+        s = s * bn.weight.detach().float()
+        beta = bn.bias.detach().float()
+    w = weight.detach().float() * s.view(-1, 1, 1, 1)
+    b = (bias.detach().float() - bn.running_mean.detach().float()) * s + beta
+    return w, b
+
+
+def conv_bn_fc_params(modules):
+    """Leaf modules in forward order -> ([(conv weight, bias) with a directly following BatchNorm2d folded in],
+    [(linear weight, bias)])."""
+    convs, fcs = [], []
+    mods = [m for m in modules if isinstance(m, (nn.Conv2d, nn.BatchNorm2d, nn.Linear))]
+    for i, m in enumerate(mods):
+        if isinstance(m, nn.Conv2d):
+            bias = m.bias if m.bias is not None else torch.zeros(m.out_channels, device=m.weight.device)
+            nxt = mods[i + 1] if i + 1 < len(mods) else None
+            convs.append(fold_batchnorm(m.weight, bias, nxt) if isinstance(nxt, nn.BatchNorm2d) else (m.weight, bias))
+        elif isinstance(m, nn.Linear):
+            fcs.append((m.weight, m.bias))
+        elif i == 0 or not isinstance(mods[i - 1], nn.Conv2d):
+            raise SiaError("BatchNorm2d is only supported directly after a convolution")
+    return convs, fcs
+
+
 class CnnPlan:
     """Packed bf16 weights + the launch sequence for one architecture on one device.
 
@@ -45,11 +91,10 @@ class CnnPlan:
         self.device = dev
         widths = [int(w.shape[0]) for w, _ in conv_params]
         if image_size is None:
-            # the reference hard-codes 224 (tone_bias_model.py:69-70); other sizes follow from the first Linear:
-            # in_features = c_last * (image_size / 2^n_conv)^2
-            side = int(round((fc_params[0][0].shape[1] / widths[-1]) ** 0.5))
-            image_size = side << len(conv_params)
+            image_size = infer_image_size(len(conv_params), widths[-1], int(fc_params[0][0].shape[1]))
         self.image_size = image_size
+        if image_size % 2 != 0:
+            raise SiaError(f"image size {image_size} is odd: the first block pools 2x2 over an even-sized input")
         if len(fc_params) < 2 or fc_params[-1][0].shape[0] != 2:
             raise SiaError("the fused tail handles exactly two classes (benign / malignant) after >= 1 hidden Linear")
         legacy = widths in LEGACY_WIDTHS
@@ -58,8 +103,27 @@ class CnnPlan:
             raise SiaError("conv widths above 256 channels are not supported")
         self.pads = pads
         self.widths = widths
+        # Spatial bookkeeping.  nn.MaxPool2d floors: valid[k] = valid[k-1] // 2 (224 -> 112 -> 56 -> 28 -> 14 -> 7 -> 3 -> 1
+        # for the 7 blocks define_isic_model can ask for).  The conv kernels take even-sized inputs and write h/2 x w/2
+        # outputs, so where the valid size turns odd (or the producing block already ran on a padded buffer and its last
+        # output row / column is not a real pooled value) the activation is copied into an even-sized buffer that is
+        # zero outside the valid corner (sia_pad_nhwc_bf16) -- the zero padding the next 'same' convolution expects.
+        n_blocks = len(conv_params)
+        self.valid = [image_size]
+        for _ in range(n_blocks):
+            self.valid.append(self.valid[-1] // 2)
+        if self.valid[-1] < 1:
+            raise SiaError(f"{n_blocks} pooling blocks reduce a {image_size}x{image_size} image to nothing")
+        self.in_hw, self.raw_hw, self.needs_pad = [image_size], [], []
+        for k in range(n_blocks):
+            raw = self.in_hw[k] // 2
+            self.raw_hw.append(raw)
+            last = k == n_blocks - 1
+            pad = (not last) and (raw != self.valid[k + 1] or raw % 2 != 0)
+            self.needs_pad.append(pad)
+            if not last:
+                self.in_hw.append(_round_up(self.valid[k + 1], 2) if pad else raw)
         self.convs = []          # (packed | [packed chunks], bias | [bias chunks], cin_pad, cout_pad)
-        side = image_size
         for i, (w, b) in enumerate(conv_params):
             w = w.detach().float().contiguous()
             b = b.detach().float().contiguous()
@@ -82,15 +146,20 @@ class CnnPlan:
                 bp = torch.zeros((pads[i],), dtype=torch.float32, device=dev)
                 bp[:cout] = b
                 self.convs.append((ops.pack_conv3x3(w, pads[i - 1], pads[i]), bp, pads[i - 1], pads[i]))
-            side //= 2
         c_last, c_last_pad = widths[-1], pads[-1]
+        side, raw = self.valid[-1], self.raw_hw[-1]
         (w1, b1) = fc_params[0]
         if w1.shape[1] != c_last * side * side:
             raise SiaError("first Linear does not match the flattened conv output")
+        w1 = w1.detach().float()
+        if raw != side:           # the last block ran on a padded buffer: its extra output row / column gets zero weights
+            w1p = torch.zeros((w1.shape[0], c_last, raw, raw), dtype=torch.float32, device=dev)
+            w1p[:, :, :side, :side] = w1.view(-1, c_last, side, side)
+            w1 = w1p.view(w1.shape[0], -1)
         # nn.Flatten on NCHW orders features (C,H,W); activations here are NHWC -> permute columns once
         self.n1 = int(w1.shape[0])
         self.n1_pad = _round_up(self.n1, 128)
-        self.w1 = ops.pack_linear_chw_to_hwc(w1.detach().float().contiguous(), c_last, side * side, self.n1_pad, c_last_pad)
+        self.w1 = ops.pack_linear_chw_to_hwc(w1.contiguous(), c_last, raw * raw, self.n1_pad, c_last_pad)
         self.b1 = b1.detach().float().contiguous()
         self.feat = self.w1.shape[1]
         rest = [(w.detach().float(), b.detach().float().contiguous()) for w, b in fc_params[1:]]
@@ -104,6 +173,8 @@ class CnnPlan:
             if self.n1 > 512 or any(w.shape[0] > 512 for w, _ in rest):
                 raise SiaError("Linear layers wider than 512 are not supported by the tail kernel")
             self.chain = [(w.t().contiguous(), b) for w, b in rest]
+        # kernel launches of one forward pass: first block (one per 32 output channels) + 3x3 blocks + pad copies + fc1 + tail
+        self.launches = len(self.convs[0][0]) + (n_blocks - 1) + sum(self.needs_pad) + 2
         self._ws = {}
         torch.cuda.current_stream(dev).synchronize()
 
@@ -115,14 +186,15 @@ class CnnPlan:
     def workspace(self, batch: int):
         ws = self._ws.get(batch)
         if ws is None:
-            s = self.image_size
-            acts = []
-            for (_p, _b, _cin, cout_pad) in self.convs:
-                s //= 2
+            acts, padded = [], []
+            for k, (_p, _b, _cin, cout_pad) in enumerate(self.convs):
                 # zero-initialised: padded channels are never written by the first block and must read as zero
-                acts.append(torch.zeros((batch, s, s, cout_pad), dtype=torch.bfloat16, device=self.device))
+                acts.append(torch.zeros((batch, self.raw_hw[k], self.raw_hw[k], cout_pad), dtype=torch.bfloat16,
+                                        device=self.device))
+                padded.append(torch.zeros((batch, self.in_hw[k + 1], self.in_hw[k + 1], cout_pad), dtype=torch.bfloat16,
+                                          device=self.device) if self.needs_pad[k] else None)
             splits = self.splits_for(batch)
-            ws = dict(acts=acts, splits=splits,
+            ws = dict(acts=acts, padded=padded, splits=splits,
                       partial=torch.empty((splits, batch, self.n1_pad), dtype=torch.float32, device=self.device),
                       logp=torch.empty((batch, 2), dtype=torch.float32, device=self.device),
                       pred=torch.empty((batch,), dtype=torch.uint8, device=self.device))
@@ -151,40 +223,47 @@ class CnnPlan:
         h = x4
         for i in range(len(self.convs)):
             h = self.conv_block(i, h, ws["acts"][i])
+            if self.needs_pad[i]:
+                v = self.valid[i + 1]
+                h = ops.pad_nhwc(h, (v, v), (self.in_hw[i + 1],) * 2, out=ws["padded"][i])
         part = ops.linear_splitk(h.view(batch, -1), self.w1, ws["splits"], out=ws["partial"])
         return self.tail(part, label=label, groups=groups, n_groups=n_groups, counts=counts, logp=ws["logp"],
                          pred=ws["pred"])
 
 
 class _B200Eval(nn.Module):
-    """Shared forward of both architectures."""
+    """Shared forward of every architecture of the path."""
 
-    def _conv_fc(self):
-        raise NotImplementedError
+    image_size = 224            # tone_bias_model.py:69-70, tone_bias_optuna.py:130
 
     def _plan(self) -> CnnPlan:
-        params = list(self.parameters())
-        key = tuple((p.data_ptr(), p._version) for p in params)
+        tensors = list(self.parameters()) + list(self.buffers())
+        key = tuple((p.data_ptr(), p._version) for p in tensors)
         if getattr(self, "_plan_key", None) != key:
-            convs, fcs = self._conv_fc()
-            self._plan_obj = CnnPlan([(m.weight, m.bias) for m in convs], [(m.weight, m.bias) for m in fcs])
+            convs, fcs = conv_bn_fc_params(self.modules())
+            self._plan_obj = CnnPlan(convs, fcs, image_size=self.image_size)
             self._plan_key = key
         return self._plan_obj
 
-    def forward(self, x):
+    def predict(self, x):
+        """(log-probabilities [B,2] f32, predicted class [B] u8) of one batch, both from the tail kernel: the label is
+        the first maximal index, the tie rule of ``torch.max(outputs, 1)`` (tone_bias_test.py:199)."""
         if self.training:
             raise SiaError("this build implements the evaluation path only: call model.eval() first "
                            "(the reference does, tone_bias_test.py:175)")
         if not isinstance(x, torch.Tensor) or not x.is_cuda:
             raise SiaError("model input must be a CUDA tensor: the sm_100a path has no CPU fallback")
-        with torch.no_grad():
+        with torch.no_grad(), torch.cuda.device(x.device):
             plan = self._plan()
             if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != plan.image_size or x.shape[3] != plan.image_size:
                 raise ValueError(f"expected input [B,3,{plan.image_size},{plan.image_size}] (the reference hard-codes "
-                                 "224, tone_bias_model.py:69-70; the size follows from the first Linear)")
+                                 "224, tone_bias_model.py:69-70)")
             x4 = ops.nchw_f32_to_nhwc4(x.float().contiguous())
-            logp, _pred = plan.forward_nhwc4(x4)
-            return logp.clone()
+            logp, pred = plan.forward_nhwc4(x4)
+            return logp.clone(), pred.clone()
+
+    def forward(self, x):
+        return self.predict(x)[0]
 
     def get_class_names(self):
         return self.class_names
@@ -193,7 +272,8 @@ class _B200Eval(nn.Module):
 class SkinCancerListModel(_B200Eval):
     """3 conv blocks + 2 linear blocks + classifier + LogSoftmax (reference :56-152)."""
 
-    def __init__(self, class_names):
+
+    def __init__(self, class_names, batch_norm: bool = False):
         super().__init__()
         self.class_names = class_names
         layers = []
@@ -202,7 +282,9 @@ class SkinCancerListModel(_B200Eval):
         for i, out_features in enumerate([32, 64, 128]):
             conv = nn.Conv2d(in_features, out_features, kernel_size=7 if i == 0 else 3, stride=1, padding="same")
             nn.init.xavier_normal_(conv.weight)
-            layers += [conv, nn.ReLU(), nn.MaxPool2d(kernel_size=(2, 2))]
+            # batch_norm=True enables the layer the reference keeps commented out (:88); folded into the conv at run time
+            layers += [conv] + ([nn.BatchNorm2d(out_features)] if batch_norm else [])
+            layers += [nn.ReLU(), nn.MaxPool2d(kernel_size=(2, 2))]
             width, height = width // 2, height // 2
             in_features = out_features
         layers.append(nn.Flatten())
@@ -217,9 +299,6 @@ class SkinCancerListModel(_B200Eval):
         layers += [head, nn.LogSoftmax(dim=1)]
         self.layers = nn.Sequential(*layers)
 
-    def _conv_fc(self):
-        L = self.layers
-        return [L[0], L[3], L[6]], [L[10], L[13], L[16]]
 
 
 class SkinCancerModel(_B200Eval):
@@ -246,8 +325,6 @@ class SkinCancerModel(_B200Eval):
         for m in (self.conv1, self.conv2, self.conv3, self.conv4, self.fc4, self.fc5, self.fc6):
             nn.init.xavier_normal_(m.weight)
 
-    def _conv_fc(self):
-        return [self.conv1, self.conv2, self.conv3, self.conv4], [self.fc4, self.fc5, self.fc6]
 
 
 def create_loss_function():
@@ -280,14 +357,46 @@ def load_model(model_path, class_names):
         for k, v in saved.items():
             if v is None:
                 sys.modules.pop(k, None)
+    return _adopt(obj, class_names)
+
+
+def _sequential_from_state_dict(state: dict):
+    """A digit-keyed ``state_dict`` (an ``nn.Sequential`` such as tone_bias_optuna.define_isic_model's) -> a B200
+    Sequential with the same keys: conv / linear modules are rebuilt from the tensor shapes, and the parameter-free
+    layers between them (ReLU, MaxPool2d, Flatten, Dropout, LogSoftmax) only matter as index placeholders."""
+    from .tone_bias_optuna import _B200Sequential
+    names = sorted({k.rsplit(".", 1)[0] for k in state}, key=int)
+    layers = [nn.Identity() for _ in range(int(names[-1]) + 2)]
+    for n in names:
+        w = state[n + ".weight"]
+        if w.dim() == 4:
+            layers[int(n)] = nn.Conv2d(w.shape[1], w.shape[0], kernel_size=w.shape[2], stride=1, padding="same")
+        elif w.dim() == 2:
+            layers[int(n)] = nn.Linear(w.shape[1], w.shape[0])
+        elif w.dim() == 1 and n + ".running_mean" in state:
+            layers[int(n)] = nn.BatchNorm2d(w.shape[0])
+        else:
+            raise TypeError(f"cannot rebuild layer {n} from a parameter of shape {tuple(w.shape)}")
+    model = _B200Sequential(*layers)
+    model.load_state_dict(state)
+    return model
+
+
+def _adopt(obj, class_names):
+    """Whatever ``torch.load`` produced -> a module of this package holding the same parameters."""
     if isinstance(obj, dict):
+        if all(k.split(".")[0].isdigit() for k in obj):
+            return _sequential_from_state_dict(obj)
         kind = SkinCancerListModel if any(k.startswith("layers.") for k in obj) else SkinCancerModel
         model = kind(class_names)
         model.load_state_dict(obj)
         return model
     if isinstance(obj, _B200Eval):
         return obj
-    if isinstance(obj, nn.Module):      # a genuine reference object (reference module importable)
+    if isinstance(obj, nn.Sequential):      # e.g. a pickled define_isic_model() of the reference
+        from .tone_bias_optuna import _B200Sequential
+        return _B200Sequential.from_modules(obj.children())
+    if isinstance(obj, nn.Module):          # a genuine reference object (reference module importable)
         kind = SkinCancerListModel if hasattr(obj, "layers") else SkinCancerModel
         model = kind(class_names)
         model.load_state_dict(obj.state_dict())

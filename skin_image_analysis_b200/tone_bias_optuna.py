@@ -79,10 +79,10 @@ class _B200Sequential(_B200Eval, nn.Sequential):
         nn.Sequential.__init__(self, *layers)
         self.class_names = None
 
-    def _conv_fc(self):
-        convs = [m for m in self if isinstance(m, nn.Conv2d)]
-        fcs = [m for m in self if isinstance(m, nn.Linear)]
-        return convs, fcs
+    @classmethod
+    def from_modules(cls, modules):
+        """Same children as an existing ``nn.Sequential`` (e.g. the reference's own, un-pickled) -- parameters shared."""
+        return cls(*list(modules))
 
 
 def define_isic_model(classes, trial):

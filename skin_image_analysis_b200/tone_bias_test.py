@@ -292,16 +292,25 @@ def analyse_predictions(instances):
     return results_from_counts(_count_instances(instances))
 
 
+def _predicted_labels(model, images):
+    """Predicted class index per image.  Models of this package return the label computed by the tail kernel itself
+    (``predict``: first maximal index, the tie rule of ``torch.max(outputs, 1)``, reference :199); any other module
+    goes through ``torch.max`` like the reference."""
+    predict = getattr(model, "predict", None)
+    if callable(predict):
+        return predict(images)[1].long()
+    return torch.max(model(images).data, 1)[1]
+
+
 def predict_with_instance(model, device, test_loader, test_dataset, class_names):
-    """Batched inference -> dict[index -> instance dict + 'prediction'] (reference :161-237)."""
+    """Batched inference -> dict[index -> instance dict + 'prediction'] (reference :161-237).  ``images.to(device)``
+    is also where a deferred DataLoader batch (tone_bias_dataset.DeferredBatch) runs its fused resize kernel."""
     model.eval()
     instances = dict()
     with torch.no_grad():
         for images, labels, indexes in test_loader:
             images = images.to(device)
-            outputs = model(images)
-            _, predicted = torch.max(outputs.data, 1)          # first maximum on ties (:199)
-            predicted = predicted.cpu().tolist()
+            predicted = _predicted_labels(model, images).cpu().tolist()
             for i, pred in enumerate(predicted):
                 index = int(indexes[i])
                 instance = test_dataset.lookup_path(index)
@@ -318,7 +327,7 @@ def evaluate_model(device, model, testloader):
         for batch_number, (images, labels, indexes) in enumerate(testloader):
             images, labels = images.to(device), labels.to(device)
             print(f"BATCH {batch_number}: indexes {indexes}")
-            _, predicted = torch.max(model(images).data, 1)
+            predicted = _predicted_labels(model, images)
             total += labels.size(0)
             correct += (predicted == labels).sum().item()
     print(f"Accuracy of the network on the {len(testloader)} batches")
@@ -332,7 +341,7 @@ def evaluate_model_by_class(device, model, testloader, class_names):
     with torch.no_grad():
         for images, labels, indexes in testloader:
             images, labels = images.to(device), labels.to(device)
-            _, predictions = torch.max(model(images), 1)
+            predictions = _predicted_labels(model, images)
             for label, prediction in zip(labels.cpu().tolist(), predictions.cpu().tolist()):
                 if label == prediction:
                     correct_pred[class_names[label]] += 1

@@ -41,7 +41,7 @@ def pytest_runtest_makereport(item, call):
     if rep.when == "call" and rep.failed and "gpu" in item.keywords:
         try:
             from skin_image_analysis_b200 import _lib
-            wd = _lib.load().sia_debug_watchdog(0)
+            wd = _lib.load().sia_watchdog_status(0)
             rep.sections.append(("sia watchdog", f"0x{wd:08x} (site {(wd >> 16) & 0x7fff}, block {wd & 0xffff})"))
         except Exception as exc:      # pragma: no cover
             rep.sections.append(("sia watchdog", f"unavailable: {exc}"))

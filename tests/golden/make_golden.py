@@ -259,8 +259,157 @@ def gen_optuna_best(ref):
     assert float((got - logp).abs().max()) < 1e-6
 
 
+def _tiny_storage_(param, shape_of_one):
+    """Replaces a big parameter by a stride-0 expansion of a small random block: torch.save keeps the small storage,
+    so a genuine whole-module pickle of the reference class stays under a megabyte.  The model is still a perfectly
+    valid set of weights -- its reference outputs are what the fixture pins."""
+    if param.dim() == 2:          # a Linear: one positive scalar, sized so that the pre-activations stay O(1)
+        small = torch.full(shape_of_one, 4.0 / param.shape[1])
+    else:
+        small = torch.randn(shape_of_one) * (2.0 / float(np.prod(param.shape[1:])) ** 0.5)
+    param.data = small.expand(param.shape)
+
+
+def gen_session_models(ref):
+    """session_model_<kind>.pth: WHOLE-MODULE pickles written by the reference's own ``save_model``
+    (tone_bias_model.py:305-315) from the reference's own classes (module paths ``tone_bias_model.SkinCancerListModel``
+    and ``jgi_hiba_2022_model.SkinCancerModel``), plus the reference's log-probabilities for a seeded batch
+    (session_models.npz).  ``load_model`` of the drop-in must open these files."""
+    import tempfile
+    out = {}
+    x = helpers.synthetic_batch_f32(3, 224, seed=55) * torch.tensor([0.3, 0.65, 1.0]).view(3, 1, 1, 1)
+    for kind, mod, cls in [(omodel.LIST_MODEL, ref.model, "SkinCancerListModel"),
+                           (omodel.FOUR_CONV_MODEL, ref.hiba, "SkinCancerModel")]:
+        torch.manual_seed(77)
+        m = getattr(mod, cls)(helpers.CLASS_NAMES).eval()
+        with torch.no_grad():                      # He-scaled weights: the activations (and the logits) vary per image
+            for p in m.parameters():
+                if p.dim() > 1:
+                    p.copy_(torch.randn(p.shape) * (2.0 / p[0].numel()) ** 0.5)
+                else:
+                    p.copy_((torch.rand(p.shape) - 0.5) * 0.2)
+        big = [p for _n, p in m.named_parameters() if p.numel() > 200_000]
+        for p in big:
+            _tiny_storage_(p, (1,) + tuple(p.shape[1:]) if p.dim() == 4 else (1, 1))
+        # size the first Linear's scalar on the actual features so that its pre-activations stay O(1)
+        first_fc = next(mm for mm in m.modules() if isinstance(mm, torch.nn.Linear))
+        seen = {}
+        def _see(_m, inp, _o):
+            seen["s"] = float(inp[0].sum(1).max())
+        hook = first_fc.register_forward_hook(_see)
+        with torch.no_grad():
+            m(x)
+        hook.remove()
+        first_fc.weight.data = torch.full((1, 1), 2.0 / seen["s"]).expand(first_fc.weight.shape)
+        with torch.no_grad():
+            # give the head a visible margin between images
+            logp = m(x)
+        path = os.path.join(HERE, f"session_model_{kind}.pth")
+        mod.save_model(m, path)
+        assert os.path.getsize(path) < 1_000_000, os.path.getsize(path)
+        again = mod.load_model(path, helpers.CLASS_NAMES)             # the reference's own loader reads it back
+        with torch.no_grad():
+            assert torch.equal(again(x), logp)
+        out[kind + "_logp"] = logp.numpy()
+        out[kind + "_class"] = np.array(type(m).__module__ + "." + type(m).__qualname__)
+    np.savez(os.path.join(HERE, "session_models.npz"), **out)
+
+
+DEEP_TRIALS = {
+    # define_isic_model search-space corners (tone_bias_optuna.py:123-173): 5 and 7 pooling blocks -> 7x7 and 1x1 maps
+    "deep5": {"n_conv_layers": 4, "n_units_l0": 16, "n_units_conv_l0": 24, "n_units_conv_l1": 16, "n_units_conv_l2": 40,
+              "n_units_conv_l3": 16, "n_linear_layers": 2, "n_units_linear_l0": 32, "dropout_l0": 0.3,
+              "n_units_linear_l1": 16, "dropout_l1": 0.3},
+    "deep7": {"n_conv_layers": 6, "n_units_l0": 16, "n_units_conv_l0": 16, "n_units_conv_l1": 32, "n_units_conv_l2": 16,
+              "n_units_conv_l3": 48, "n_units_conv_l4": 16, "n_units_conv_l5": 64, "n_linear_layers": 3,
+              "n_units_linear_l0": 64, "dropout_l0": 0.2, "n_units_linear_l1": 32, "dropout_l1": 0.2,
+              "n_units_linear_l2": 16, "dropout_l2": 0.2},
+}
+
+
+def gen_deep_sequential(ref):
+    """session_model_<deepN>.pth: the reference's ``define_isic_model`` (an ``nn.Sequential``) with 5 / 7 pooling blocks,
+    He-initialised so the activations survive, pickled whole; + its CPU log-probabilities.  Pins MaxPool2d's floor on
+    odd sizes (14 -> 7 -> 3 -> 1) and ``load_model`` on a Sequential pickle."""
+    import importlib
+    ro = importlib.import_module("tone_bias_optuna")
+    out = {}
+    x = helpers.synthetic_batch_f32(5, 224, seed=66)
+    for name, hp in DEEP_TRIALS.items():
+        torch.manual_seed(88)
+        with contextlib.redirect_stdout(io.StringIO()):
+            m = ro.define_isic_model(2, ro.TrialDummy(dict(hp))).eval()
+        gen = torch.Generator().manual_seed(5)
+        with torch.no_grad():
+            for k, v in m.state_dict().items():
+                if k.endswith(".weight"):
+                    v.copy_(torch.randn(v.shape, generator=gen) * (2.0 / v[0].numel()) ** 0.5)
+                else:
+                    v.copy_((torch.rand(v.shape, generator=gen) - 0.5) * 0.2)
+            logp = m(x)
+        path = os.path.join(HERE, f"session_model_{name}.pth")
+        torch.save(m, path)                                            # what tone_bias_model.save_model does (:315)
+        assert os.path.getsize(path) < 1_000_000, os.path.getsize(path)
+        out[name + "_logp"] = logp.numpy()
+    np.savez(os.path.join(HERE, "deep_sequential.npz"), **out)
+
+
+def gen_dataset_and_eval(ref):
+    """dataset_eval.json: (a) the reference's own ``HibaDataset`` (tone_bias_dataset.py:258-393) on a seeded dataframe
+    and lossless image files -- ``len``, ``lookup_path`` dicts, labels, the image ``__getitem__`` returns without a
+    transform (``skimage.io.imread`` is bound to a PIL reader: scikit-image is not installable here);
+    (b) stdout of the reference's ``evaluate_model`` / ``evaluate_model_by_class`` (tone_bias_test.py:99-159) on the
+    seeded stand-in model / loader of tests/helpers.py; (c) the reference's ``predict_with_instance`` (:161-237) on the
+    same stand-ins with the reference dataset supplying ``lookup_path``."""
+    import tempfile
+    from PIL import Image
+    sk_io = sys.modules["skimage.io"]
+    sk_io.imread = lambda path: np.asarray(Image.open(path).convert("RGB"), dtype=np.uint8)
+    ref.dataset.skimage.io.imread = sk_io.imread
+    out = {}
+    df = helpers.synthetic_metadata_df(6, seed=21)
+    with tempfile.TemporaryDirectory() as d:
+        imgs = helpers.write_image_files(d, df, 20, 28, seed=400, kind="noise")
+        ds = ref.dataset.HibaDataset(df, helpers.CLASS_NAMES, root_dir=d, transform=None)
+        items = [ds[i] for i in range(len(ds))]
+        for (im, _l, _i), u8 in zip(items, imgs):
+            assert im.dtype == np.float32 and np.array_equal(im, np.float32(u8) / 255.0)
+        look = []
+        for i in range(len(ds)):
+            inst = ds.lookup_path(i)
+            inst["file_path"] = os.path.relpath(inst["file_path"], d)
+            look.append(_jsonable(inst))
+        out["dataset"] = {"len": len(ds), "labels": [int(it[1]) for it in items], "indexes": [int(it[2]) for it in items],
+                          "lookup": look, "class_names": ds.get_class_names(), "class_1": ds.get_class(1),
+                          "image_sums": [float(np.float64(it[0]).sum()) for it in items]}
+        model, loader = helpers.FixedLogitModel(3), helpers.fixed_eval_loader(4, 6, seed=9)
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            ref.test.evaluate_model("cpu", model, loader)
+        out["evaluate_model_stdout"] = buf.getvalue()
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            ref.test.evaluate_model_by_class("cpu", model, loader, helpers.CLASS_NAMES)
+        out["evaluate_model_by_class_stdout"] = buf.getvalue()
+        small = [(im[:, :, :4, :4], lab % 2, idx % len(ds)) for im, lab, idx in loader][:1]
+        inst = ref.test.predict_with_instance(model, "cpu", small, ds, helpers.CLASS_NAMES)
+        for v in inst.values():
+            v["file_path"] = os.path.relpath(v["file_path"], d)
+        out["predict_with_instance"] = _jsonable(inst)
+    with open(os.path.join(HERE, "dataset_eval.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+
+
 def main():
     ref = ref_import.load()
+    if "--new" in sys.argv:                       # only the fixtures added in round 2 (the others stay untouched)
+        gen_session_models(ref)
+        gen_deep_sequential(ref)
+        gen_dataset_and_eval(ref)
+        return
+    gen_session_models(ref)
+    gen_deep_sequential(ref)
+    gen_dataset_and_eval(ref)
     gen_notebook()
     gen_optuna_best(ref)
     gen_experiments(ref)

@@ -89,3 +89,73 @@ def counter_metadata(index: np.ndarray, seed: int):
 
 def close(a, b, rel=1e-12):
     return math.isclose(a, b, rel_tol=rel, abs_tol=1e-15)
+
+
+def synthetic_metadata_df(n: int, seed: int):
+    """ISIC-metadata-shaped dataframe with the columns ``HibaDataset.lookup_path`` reads
+    (tone_bias_dataset.py:366-392); one NaN ``sex`` so the "falls in no group" rule is exercised."""
+    import pandas as pd
+    rng = np.random.default_rng(seed)
+    ftype = rng.choice(6, n, p=[0.3, 0.3, 0.15, 0.1, 0.1, 0.05])
+    label = rng.integers(0, 2, n)
+    sex = np.where(rng.integers(0, 2, n) == 0, "male", "female").astype(object)
+    if n > 3:
+        sex[3] = float("nan")
+    types = [FITZPATRICK[t] for t in ftype]
+    return pd.DataFrame({
+        "isic_id": [f"ISIC_{9000000 + 7 * i:07d}" for i in range(n)],
+        "patient_id": [f"IP_{1000 + i % 5}" for i in range(n)],
+        "diagnosis": ["melanoma" if v else "nevus" for v in label],
+        "benign_malignant": [CLASS_NAMES[v] for v in label],
+        "age_approx": [float(30 + 5 * (i % 9)) for i in range(n)],
+        "sex": sex,
+        "anatom_site_general": ["torso" if i % 2 else "lower extremity" for i in range(n)],
+        "fitzpatrick_skin_type": types,
+        "skin_tone": ["light" if t in ("I", "II") else "dark" for t in types],
+        "control": ["rich" if v == 0 else "poor" for v in rng.integers(0, 2, n)],
+    })
+
+
+def write_image_files(root_dir: str, df, h: int, w: int, seed: int, kind: str = "smooth"):
+    """One LOSSLESS image file per row under the ``<isic_id>.jpg`` name ``HibaDataset.get_file_path`` builds
+    (tone_bias_dataset.py:354-360).  The bytes are PNG (readers sniff the content, not the suffix), so the decode
+    buffer is exactly the seeded array returned here -- JPEG would make it decoder-dependent."""
+    from PIL import Image
+    images = []
+    for i, name in enumerate(df["isic_id"]):
+        u8 = synthetic_u8_image(h, w, seed + i, kind)
+        Image.fromarray(u8, "RGB").save(__import__("os").path.join(root_dir, name + ".jpg"), format="PNG")
+        images.append(u8)
+    return images
+
+
+class FixedLogitModel:
+    """Stand-in "model" for the evaluate_model / evaluate_model_by_class stdout fixtures: log-probabilities are a
+    fixed seeded function of the per-image mean, so the reference functions and the drop-ins see the same outputs."""
+
+    def __init__(self, seed: int):
+        import torch
+        g = torch.Generator().manual_seed(seed)
+        self.w = torch.randn(2, generator=g)
+
+    def eval(self):
+        return self
+
+    def __call__(self, images):
+        import torch
+        m = images.float().mean(dim=(1, 2, 3)) - 0.5
+        z = torch.stack([m * self.w[0], m * self.w[1] + 0.01], 1)
+        return torch.log_softmax(z * 40.0, 1)
+
+
+def fixed_eval_loader(n_batches: int, batch: int, seed: int):
+    """List-of-batches stand-in for a DataLoader: (images [b,3,8,8], labels [b], indexes [b]); last batch ragged."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    out, k = [], 0
+    for b in range(n_batches):
+        nb = batch if b < n_batches - 1 else max(1, batch - 3)
+        out.append((torch.rand(nb, 3, 8, 8, generator=g), torch.randint(0, 2, (nb,), generator=g),
+                    torch.arange(k, k + nb)))
+        k += nb
+    return out

@@ -1,4 +1,7 @@
-"""K4-K6 parity: conv / linear / tail kernels and the nn.Module drop-ins vs the fp32 oracle."""
+"""K4-K6 parity: conv / linear / tail kernels and the nn.Module drop-ins vs the fp32 oracle.
+
+The oracle forward always runs ON THE CPU (true IEEE fp32, like the reference's own CPU path); on the GPU torch's
+convolutions default to TF32, which is not the reference arithmetic."""
 import os
 
 import numpy as np
@@ -148,11 +151,11 @@ def test_batch_32_vs_oracle_with_margin_rule():
     from skin_image_analysis_b200 import tone_bias_model as tm
     state = om.synthetic_state_dict(om.LIST_MODEL, seed=3)
     x = helpers.synthetic_batch_f32(32, 224, seed=5)
-    ref = om.forward(om.LIST_MODEL, {k: v.cuda() for k, v in state.items()}, x.cuda()).cpu()
+    ref = om.forward(om.LIST_MODEL, state, x)
     # centre the head so both classes occur, same shift on both sides
     shift = float((ref[:, 1] - ref[:, 0]).median())
     state["layers.16.bias"][1] -= shift
-    ref = om.forward(om.LIST_MODEL, {k: v.cuda() for k, v in state.items()}, x.cuda()).cpu()
+    ref = om.forward(om.LIST_MODEL, state, x)
     model = tm.SkinCancerListModel(helpers.CLASS_NAMES)
     model.load_state_dict(state)
     got = model.cuda().eval()(x.cuda()).cpu()
@@ -174,9 +177,9 @@ def test_engine_end_to_end_counts_bit_exact_given_predictions():
     state = om.synthetic_state_dict(om.LIST_MODEL, seed=11)
     imgs = np.stack([helpers.synthetic_u8_image(450, 600, 300 + i, "smooth") for i in range(batch)])
     x_ref = torch.from_numpy(np.stack([R.transform_u8(im, (224, 224)) for im in imgs]))
-    ref = om.forward(om.LIST_MODEL, {k: v.cuda() for k, v in state.items()}, x_ref.cuda()).cpu()
+    ref = om.forward(om.LIST_MODEL, state, x_ref)
     state["layers.16.bias"][1] -= float((ref[:, 1] - ref[:, 0]).median())
-    ref = om.forward(om.LIST_MODEL, {k: v.cuda() for k, v in state.items()}, x_ref.cuda()).cpu()
+    ref = om.forward(om.LIST_MODEL, state, x_ref)
     label, ftype, sex, control = helpers.counter_metadata(np.arange(batch), seed=1)
     eng = EvalEngine(state, batch)
     for use_graph_replays in range(2):
@@ -207,9 +210,9 @@ def test_four_conv_model_batch_vs_oracle():
     from skin_image_analysis_b200 import tone_bias_model as tm
     state = om.synthetic_state_dict(om.FOUR_CONV_MODEL, seed=4)
     x = helpers.synthetic_batch_f32(24, 224, seed=6)
-    ref = om.forward(om.FOUR_CONV_MODEL, {k: v.cuda() for k, v in state.items()}, x.cuda()).cpu()
+    ref = om.forward(om.FOUR_CONV_MODEL, state, x)
     state["fc6.bias"][1] -= float((ref[:, 1] - ref[:, 0]).median())
-    ref = om.forward(om.FOUR_CONV_MODEL, {k: v.cuda() for k, v in state.items()}, x.cuda()).cpu()
+    ref = om.forward(om.FOUR_CONV_MODEL, state, x)
     model = tm.create_model(helpers.CLASS_NAMES)
     assert isinstance(model, tm.SkinCancerModel)
     model.load_state_dict(state)
@@ -229,7 +232,7 @@ def test_engine_high_resolution_512():
     state = random_state_dict(om.LIST_MODEL, 512, seed=2)
     imgs = np.stack([helpers.synthetic_u8_image(450, 600, 500 + i, "smooth") for i in range(batch)])
     x_ref = torch.from_numpy(np.stack([R.transform_u8(im, (512, 512)) for im in imgs]))
-    ref = om.forward(om.LIST_MODEL, {k: v.cuda() for k, v in state.items()}, x_ref.cuda()).cpu()
+    ref = om.forward(om.LIST_MODEL, state, x_ref)
     eng = EvalEngine(state, batch, (450, 600), 512, use_graph=False)
     label = torch.zeros(batch, dtype=torch.uint8, device="cuda")
     groups = torch.zeros((3, batch), dtype=torch.uint8, device="cuda")
@@ -306,9 +309,9 @@ def test_optuna_best_model_matches_reference_fixture_and_oracle(golden_dir):
         else:
             state[k] = (torch.rand(v.shape, generator=gen) - 0.5) * 0.2
     xb = helpers.synthetic_batch_f32(16, 224, seed=34)
-    ref = om.forward_sequential({k: v.cuda() for k, v in state.items()}, xb.cuda()).cpu()
+    ref = om.forward_sequential(state, xb)
     state["22.bias"][1] -= float((ref[:, 1] - ref[:, 0]).median())
-    ref = om.forward_sequential({k: v.cuda() for k, v in state.items()}, xb.cuda()).cpu()
+    ref = om.forward_sequential(state, xb)
     model.load_state_dict(state)
     got = model.cuda().eval()(xb.cuda()).cpu()
     # He-init weights keep the activations O(1) through all 8 layers (the reference's default init lets them decay,

@@ -18,16 +18,30 @@ from tests import helpers
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _declared(header_name):
+    header = open(os.path.join(ROOT, "include", header_name)).read()
+    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    return re.findall(r"\b(sia_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S)
+
+
 def test_library_exports_every_declared_symbol():
+    """include/sia_b200.h == the product library's bound symbols (plus the three instrumentation switches of
+    sia_b200_debug.h group 1); the probes of group 2 live in libsia_b200_debug.so and NOT in the product library."""
     from skin_image_analysis_b200 import _lib, build
     build.build()
-    lib = _lib.load()
-    header = open(os.path.join(ROOT, "include", "sia_b200.h")).read()
-    declared = set(re.findall(r"\b(sia_[a-z0-9_]+)\s*\(", header))
-    assert declared, "no declarations found"
-    for name in sorted(declared):
-        assert hasattr(lib, name), f"{name} declared in sia_b200.h but not exported"
-    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib, dbg = _lib.load(), _lib.load_debug()
+    product = {n for n, _ in _declared("sia_b200.h")}
+    debug = {n for n, _ in _declared("sia_b200_debug.h")}
+    assert product and debug and not (product & debug)
+    switches = {"sia_debug_tv_force_generic", "sia_debug_set_trace", "sia_debug_set_stats"}
+    assert not any(n.startswith("sia_debug") for n in product)
+    for name in sorted(product | switches):
+        assert hasattr(lib, name), f"{name} declared but not exported by libsia_b200.so"
+    for name in sorted(debug - switches):
+        assert hasattr(dbg, name), f"{name} declared but not exported by libsia_b200_debug.so"
+        assert not hasattr(lib, name), f"probe {name} leaked into the product library"
+    assert product | switches == set(_lib.SIGNATURES), (product | switches) ^ set(_lib.SIGNATURES)
+    assert debug - switches == set(_lib.DEBUG_SIGNATURES), (debug - switches) ^ set(_lib.DEBUG_SIGNATURES)
     assert lib.sia_version() == 100
     assert lib.sia_error_string(-2).decode().startswith("sia:")
     assert lib.sia_pack_conv7x7_c3_bytes() == 128 * 256 * 2
@@ -35,18 +49,18 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_ctypes_signatures_match_the_header_prototypes():
-    """Every prototype of include/sia_b200.h against _lib.SIGNATURES: same number of parameters, pointers bound
-    as pointers and integers as integers (a missing argument shifts the stream handle and crashes on the GPU box)."""
+    """Every prototype of include/sia_b200.h and sia_b200_debug.h against _lib.SIGNATURES / DEBUG_SIGNATURES: same
+    number of parameters, pointers bound as pointers and integers as integers (a missing argument shifts the stream
+    handle and crashes on the GPU box)."""
     import ctypes
     from skin_image_analysis_b200 import _lib
-    header = open(os.path.join(ROOT, "include", "sia_b200.h")).read()
-    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
-    protos = re.findall(r"\b(sia_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S)
-    assert len(protos) == len(_lib.SIGNATURES)
+    protos = _declared("sia_b200.h") + _declared("sia_b200_debug.h")
+    bound = {**_lib.SIGNATURES, **_lib.DEBUG_SIGNATURES}
+    assert len(protos) == len(bound)
     for name, params in protos:
         params = " ".join(params.split())
         plist = [] if params in ("", "void") else [q.strip() for q in params.split(",")]
-        _res, args = _lib.SIGNATURES[name]
+        _res, args = bound[name]
         assert len(plist) == len(args), f"{name}: header has {len(plist)} parameters, _lib binds {len(args)}"
         for q, a in zip(plist, args):
             is_ptr = "*" in q

@@ -39,7 +39,7 @@ def put_mn_major(buf, base, mat_kn, lbo, sbo):
 
 @pytest.mark.parametrize("n", [96, 128, 256])
 def test_i8_k_major_both(n):
-    from skin_image_analysis_b200 import ops
+    from skin_image_analysis_b200 import debug_probes as probes
     rng = np.random.default_rng(n)
     k = 64
     a = rng.integers(0, 256, (128, k), dtype=np.uint8)
@@ -50,7 +50,7 @@ def test_i8_k_major_both(n):
     put_k_major(buf, b_base, b, 128, (k // 16) * 128)
     ad = [desc(s * 256, 128, (k // 16) * 128, SW_NONE) for s in range(k // 32)]
     bd = [desc(b_base + s * 256, 128, (k // 16) * 128, SW_NONE) for s in range(k // 32)]
-    got = ops.umma_probe_i8(torch.from_numpy(buf).cuda(), ad, bd, n, idesc_i8(128, n)).cpu().numpy()
+    got = probes.umma_probe_i8(torch.from_numpy(buf).cuda(), ad, bd, n, idesc_i8(128, n)).cpu().numpy()
     want = a.astype(np.int64) @ b.astype(np.int64).T
     ok = np.array_equal(got, want)
     record(f"i8_k_major_n{n}", ok, True, {"maxerr": float(np.abs(got - want).max())})
@@ -60,7 +60,7 @@ def test_i8_k_major_both(n):
 @pytest.mark.parametrize("n,k,pad", [(96, 64, 16), (96, 256, 16), (128, 64, 0), (256, 96, 16)])
 def test_i8_b_mn_major(n, k, pad):
     """B = [K source rows, N bytes of the image row] exactly as the preprocess loader lays it out."""
-    from skin_image_analysis_b200 import ops
+    from skin_image_analysis_b200 import debug_probes as probes
     rng = np.random.default_rng(n + k)
     a = rng.integers(0, 256, (128, k), dtype=np.uint8)
     s = rng.integers(0, 256, (k, n), dtype=np.uint8)          # s[r, byte]
@@ -72,12 +72,12 @@ def test_i8_b_mn_major(n, k, pad):
     put_mn_major(buf, b_base, s, b_lbo, b_sbo)
     ad = [desc(st * 256, 128, a_sbo, SW_NONE) for st in range(k // 32)]
     bd = [desc(b_base + st * 4 * b_lbo, b_lbo, b_sbo, SW_NONE) for st in range(k // 32)]
-    got = ops.umma_probe_i8(torch.from_numpy(buf).cuda(), ad, bd, n, idesc_i8(128, n, b_mn=1)).cpu().numpy()
+    got = probes.umma_probe_i8(torch.from_numpy(buf).cuda(), ad, bd, n, idesc_i8(128, n, b_mn=1)).cpu().numpy()
     want = a.astype(np.int64) @ s.astype(np.int64)
     ok = np.array_equal(got, want)
     if not ok:      # the other reading of LBO / SBO for MN-major operands
         bd2 = [desc(b_base + st * 4 * b_lbo, b_sbo, b_lbo, SW_NONE) for st in range(k // 32)]
-        got2 = ops.umma_probe_i8(torch.from_numpy(buf).cuda(), ad, bd2, n, idesc_i8(128, n, b_mn=1)).cpu().numpy()
+        got2 = probes.umma_probe_i8(torch.from_numpy(buf).cuda(), ad, bd2, n, idesc_i8(128, n, b_mn=1)).cpu().numpy()
         record(f"i8_b_mn_major_n{n}_k{k}_swapped", np.array_equal(got2, want), False)
     record(f"i8_b_mn_major_n{n}_k{k}", ok, True, {"maxerr": float(np.abs(got - want).max())})
     assert ok
@@ -85,7 +85,7 @@ def test_i8_b_mn_major(n, k, pad):
 
 def test_i8_issue_rate():
     """SM-clock cycles per kind::i8 MMA (M=128, K=32) for the N values the kernel may use."""
-    from skin_image_analysis_b200 import ops
+    from skin_image_analysis_b200 import debug_probes as probes
     out = {}
     for n in (96, 128, 192, 256):
         k = 256
@@ -95,8 +95,8 @@ def test_i8_issue_rate():
         ad = [desc(st * 256, 128, a_sbo, SW_NONE) for st in range(k // 32)]
         bd = [desc(b_base + st * 4 * b_lbo, b_lbo, b_sbo, SW_NONE) for st in range(k // 32)]
         img = torch.from_numpy(buf).cuda()
-        _, c1 = ops.umma_probe_i8(img, ad, bd, n, idesc_i8(128, n, b_mn=1), repeat=4, want_cycles=True)
-        _, c2 = ops.umma_probe_i8(img, ad, bd, n, idesc_i8(128, n, b_mn=1), repeat=36, want_cycles=True)
+        _, c1 = probes.umma_probe_i8(img, ad, bd, n, idesc_i8(128, n, b_mn=1), repeat=4, want_cycles=True)
+        _, c2 = probes.umma_probe_i8(img, ad, bd, n, idesc_i8(128, n, b_mn=1), repeat=36, want_cycles=True)
         out[f"n{n}"] = (c2 - c1) / (32 * len(ad))
     record("i8_cycles_per_mma_b_mn_major", True, False, out)
     print(out)

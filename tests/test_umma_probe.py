@@ -65,8 +65,8 @@ class Image:
 
 
 def run(img, a_descs, b_descs, n):
-    from skin_image_analysis_b200 import ops
-    return ops.umma_probe(img.tensor(), a_descs, b_descs, n).cpu().numpy()
+    from skin_image_analysis_b200 import debug_probes as probes
+    return probes.umma_probe(img.tensor(), a_descs, b_descs, n).cpu().numpy()
 
 
 REPORT = {}
@@ -220,7 +220,7 @@ def test_exploratory_row_shifts_inside_swizzle_atoms():
 
 def test_exploratory_issue_rate():
     """SM-clock cycles per UMMA (M=128, K=16) for the operand layouts in use -- recorded only."""
-    from skin_image_analysis_b200 import ops
+    from skin_image_analysis_b200 import debug_probes as probes
     rng = np.random.default_rng(6)
     out = {}
     for n in (32, 64, 128, 256):
@@ -230,7 +230,7 @@ def test_exploratory_issue_rate():
         img.put_rows_swizzled(16384, b, 128)
         ad = [desc(kk * 32, 0, 1024, SW_128) for kk in range(4)] * 8
         bd = [desc(16384 + kk * 32, 0, 1024, SW_128) for kk in range(4)] * 8
-        _, cyc = ops.umma_probe(img.tensor(), ad, bd, n, repeat=64, want_cycles=True)
+        _, cyc = probes.umma_probe(img.tensor(), ad, bd, n, repeat=64, want_cycles=True)
         out[f"sw128_n{n}_cycles_per_mma"] = cyc / (64 * 32)
     # 64-byte rows (conv 32->64) and the single-halo addressing (8-row groups one halo row apart)
     for name, rb, lay, n, shift, sbo in (("sw64_n64_aligned", 64, SW_64, 64, 0, 8 * 64),
@@ -246,7 +246,7 @@ def test_exploratory_issue_rate():
         img.put_rows_swizzled(a_bytes, b, rb)
         ad = [desc(shift * rb + kk * 32, 0, sbo, lay) for kk in range(k // 16)] * (32 // (k // 16))
         bd = [desc(a_bytes + kk * 32, 0, 8 * rb, lay) for kk in range(k // 16)] * (32 // (k // 16))
-        _, cyc = ops.umma_probe(img.tensor(), ad, bd, n, repeat=64, want_cycles=True)
+        _, cyc = probes.umma_probe(img.tensor(), ad, bd, n, repeat=64, want_cycles=True)
         out[name + "_cycles_per_mma"] = cyc / (64 * 32)
     patch, bmat = rand_int(rng, (38, 96)), rand_int(rng, (128, 256))
     img = Image(7424 + 65536)
@@ -254,7 +254,7 @@ def test_exploratory_issue_rate():
     img.put_core_matrices(7424, bmat, 128, 4096)
     ad = [desc(r * 192 + kk * 32, 16, 384, SW_NONE) for r in range(8) for kk in range(2)]
     bd = [desc(7424 + (r * 4 + kk * 2) * 128, 128, 4096, SW_NONE) for r in range(8) for kk in range(2)]
-    _, cyc = ops.umma_probe(img.tensor(), ad, bd, 128, repeat=128, want_cycles=True)
+    _, cyc = probes.umma_probe(img.tensor(), ad, bd, 128, repeat=128, want_cycles=True)
     out["conv1_nosw_n128_cycles_per_mma"] = cyc / (128 * 16)
     record("issue_rate", True, False, out)
 
@@ -286,10 +286,10 @@ def _bits(t):
 @pytest.mark.parametrize("coords", [(0, -1, -1, 0), (0, 8, 15, 1), (0, 3, 2, 1)])
 def test_tma_conv3x3_halo_box(cin, swz, coords):
     """box [C<=64, 8 x, 18 y, 1 n] of an NHWC tensor: 144 smem rows of one pixel, zero outside the image."""
-    from skin_image_analysis_b200 import ops
+    from skin_image_analysis_b200 import debug_probes as probes
     b, h, w = 2, 20, 16
     t = _coded((b, h, w, cin), 7)
-    got = ops.tma_probe(t, (cin, w, h, b), (cin * 2, w * cin * 2, h * w * cin * 2), (cin, 8, 18, 1), swz, coords)
+    got = probes.tma_probe(t, (cin, w, h, b), (cin * 2, w * cin * 2, h * w * cin * 2), (cin, 8, 18, 1), swz, coords)
     src = _bits(t)
     rows = np.zeros((144, cin), np.uint16)
     for yy in range(18):
@@ -308,11 +308,11 @@ def test_tma_conv1_patch_box(coords, rows=38):
     """box [24 px * 4 ch, 38 rows, 1] of the padded NHWC4 image seen as [B, H, (W+8)*4].  The innermost
     start must be a multiple of 8 elements (16 bytes) -- (x0-2)*4 with x0 % 16 == 0 -- an unaligned start
     raises an illegal-instruction fault (found on the first bring-up run)."""
-    from skin_image_analysis_b200 import ops
+    from skin_image_analysis_b200 import debug_probes as probes
     b, h, w = 2, 32, 56
     t = _coded((b, h, w * 4), 8)
     n_rows = rows
-    got = ops.tma_probe(t, (w * 4, h, b), (w * 8, h * w * 8), (96, n_rows, 1), 0, coords)
+    got = probes.tma_probe(t, (w * 4, h, b), (w * 8, h * w * 8), (96, n_rows, 1), 0, coords)
     src = _bits(t)
     rows = np.zeros((n_rows, 96), np.uint16)
     for yy in range(n_rows):
@@ -327,10 +327,10 @@ def test_tma_conv1_patch_box(coords, rows=38):
 
 
 def test_tma_linear_tile_box():
-    from skin_image_analysis_b200 import ops
+    from skin_image_analysis_b200 import debug_probes as probes
     m, k = 200, 256
     t = _coded((m, k), 9)
-    got = ops.tma_probe(t, (k, m), (k * 2,), (64, 128), 128, (64, 128))
+    got = probes.tma_probe(t, (k, m), (k * 2,), (64, 128), 128, (64, 128))
     src = _bits(t)
     rows = np.zeros((128, 64), np.uint16)
     rows[:72] = src[128:200, 64:128]
@@ -344,7 +344,7 @@ def test_exploratory_alu_rates():
     import ctypes
     from skin_image_analysis_b200 import _lib
     out = (ctypes.c_double * 8)()
-    _lib.check(_lib.load().sia_debug_alu_rates(out, 8))
+    _lib.check(_lib.load_debug().sia_debug_alu_rates(out, 8))
     names = ["FFMA", "PRMT", "I2F_U8_plus_IADD", "DP4A", "DP2A", "IMAD", "SHF", "FFMA2"]
     record("alu_rates_lane_ops_per_clk_per_sm", True, False, dict(zip(names, [round(v, 1) for v in out])))
 
@@ -377,7 +377,7 @@ def test_single_halo_copy_taps(row_bytes, layout):
 
 def test_exploratory_tma_box_throughput():
     """SM-clock cycles per TMA box (32 boxes in flight from one SM) for the shapes in use and candidates."""
-    from skin_image_analysis_b200 import ops
+    from skin_image_analysis_b200 import debug_probes as probes
     out = {}
     rep = 32
     # conv1 patch boxes on a [B, H, WP*4] view of the padded NHWC4 image
@@ -387,7 +387,7 @@ def test_exploratory_tma_box_throughput():
                                        ("conv1_128B_rows_pitch240_start_aligned128", 240, 16, 38, 0)):
         b, h = 4, 224
         t = _coded((b, h, wp * 4), 1)
-        _, cyc = ops.tma_probe(t, (wp * 4, h, b), (wp * 8, h * wp * 8), (box_px * 4, rows, 1), 0, (c0, 0, 0),
+        _, cyc = probes.tma_probe(t, (wp * 4, h, b), (wp * 8, h * wp * 8), (box_px * 4, rows, 1), 0, (c0, 0, 0),
                                repeat=rep, step_dim=1, step=4)
         out[name] = cyc / rep
     # conv3x3 halo boxes
@@ -395,12 +395,12 @@ def test_exploratory_tma_box_throughput():
                                 ("conv3_sw128_8x18", 64, 128, (64, 8, 18, 1)), ("conv3_sw128_16x12", 64, 128, (64, 16, 12, 1))):
         b, h, w = 2, 112, 112
         t = _coded((b, h, w, cin), 2)
-        _, cyc = ops.tma_probe(t, (cin, w, h, b), (cin * 2, w * cin * 2, h * w * cin * 2), box, swz, (0, 7, 3, 0),
+        _, cyc = probes.tma_probe(t, (cin, w, h, b), (cin * 2, w * cin * 2, h * w * cin * 2), box, swz, (0, 7, 3, 0),
                                repeat=rep, step_dim=2, step=2)
         out[name] = cyc / rep
     # plain 2-D GEMM tile
     t = _coded((1024, 4096), 3)
-    _, cyc = ops.tma_probe(t, (4096, 1024), (8192,), (64, 128), 128, (0, 0), repeat=rep, step_dim=0, step=64)
+    _, cyc = probes.tma_probe(t, (4096, 1024), (8192,), (64, 128), 128, (0, 0), repeat=rep, step_dim=0, step=64)
     out["linear_sw128_64x128"] = cyc / rep
     record("tma_cycles_per_box", True, False, {k: round(v, 1) for k, v in out.items()})
 
@@ -411,7 +411,7 @@ def test_exploratory_a_operand_in_tensor_memory():
     (high half), and one K = 16 instruction consumes 8 columns.  B = [I | 0] picks A's columns back out, so the
     accumulator reveals the K index the hardware assigns to every stored half-word; a random product then checks
     the arithmetic.  Exploratory: recorded in gpurun_out/probe_report.json."""
-    from skin_image_analysis_b200 import ops
+    from skin_image_analysis_b200 import debug_probes as probes
     k, n = 64, 64
     a = (np.arange(128)[:, None] * 0 + np.arange(k)[None, :]).astype(np.float32)          # A[m, kk] = kk
     a[:, 0] = np.arange(128) % 64                                                         # column 0 carries the row
@@ -420,7 +420,7 @@ def test_exploratory_a_operand_in_tensor_memory():
     img = Image(n * k * 2)
     img.put_core_matrices(0, np.eye(n, k, dtype=np.float32), 128, (k // 8) * 128)         # B[n, kk] = delta
     bd = [desc(kk * 256, 128, (k // 8) * 128, SW_NONE) for kk in range(k // 16)]
-    got = ops.umma_ts_probe(img.tensor(), torch.from_numpy(words.copy()).cuda(), 8, bd, n).cpu().numpy()
+    got = probes.umma_ts_probe(img.tensor(), torch.from_numpy(words.copy()).cuda(), 8, bd, n).cpu().numpy()
     ok_map = np.array_equal(got, a[:, :n])
     rng = np.random.default_rng(3)
     a2, b2 = rand_int(rng, (128, k)), rand_int(rng, (n, k))
@@ -428,7 +428,7 @@ def test_exploratory_a_operand_in_tensor_memory():
     words = (bits[:, 0::2] | (bits[:, 1::2] << 16)).astype(np.uint32).view(np.int32)
     img2 = Image(n * k * 2)
     img2.put_core_matrices(0, b2, 128, (k // 8) * 128)
-    got2 = ops.umma_ts_probe(img2.tensor(), torch.from_numpy(words.copy()).cuda(), 8, bd, n).cpu().numpy()
+    got2 = probes.umma_ts_probe(img2.tensor(), torch.from_numpy(words.copy()).cuda(), 8, bd, n).cpu().numpy()
     ok_rand = np.array_equal(got2, a2 @ b2.T)
     record("explore_a_in_tmem_f16", ok_map and ok_rand, False,
            {"mapping_ok": bool(ok_map), "random_ok": bool(ok_rand), "row0": got[0, :16].tolist(), "row5": got[5, :16].tolist(),

@@ -2,7 +2,7 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-from skin_image_analysis_b200 import ops
+from skin_image_analysis_b200 import debug_probes as probes
 from tests.test_umma_probe import desc
 from tests.test_umma_i8_probe import idesc_i8
 
@@ -10,13 +10,13 @@ SW_NONE, SW_128 = 0, 2
 img = torch.zeros(190 * 1024, dtype=torch.uint8, device="cuda")
 
 def cyc(kind, ad, bd, n, idesc):
-    f = ops.umma_probe_i8 if kind == 1 else None
+    f = probes.umma_probe_i8 if kind == 1 else None
     if kind == 1:
-        _, c1 = ops.umma_probe_i8(img, ad, bd, n, idesc, repeat=4, want_cycles=True)
-        _, c2 = ops.umma_probe_i8(img, ad, bd, n, idesc, repeat=36, want_cycles=True)
+        _, c1 = probes.umma_probe_i8(img, ad, bd, n, idesc, repeat=4, want_cycles=True)
+        _, c2 = probes.umma_probe_i8(img, ad, bd, n, idesc, repeat=36, want_cycles=True)
     else:
-        _, c1 = ops.umma_probe(img, ad, bd, n, repeat=4, want_cycles=True)
-        _, c2 = ops.umma_probe(img, ad, bd, n, repeat=36, want_cycles=True)
+        _, c1 = probes.umma_probe(img, ad, bd, n, repeat=4, want_cycles=True)
+        _, c2 = probes.umma_probe(img, ad, bd, n, repeat=36, want_cycles=True)
     return (c2 - c1) / (32 * len(ad))
 
 B0 = 64 * 1024
