@@ -21,6 +21,18 @@ def shard_range(n_items: int, rank: int, world_size: int) -> tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def shard_batches(n_images: int, batch: int, rank: int, world_size: int) -> tuple[int, int, int]:
+    """Sharding by WHOLE batches: the job's ceil(n_images / batch) global batches are dealt to the ranks in contiguous
+    balanced ranges -> (first batch, one past the last batch, number of global batches).  Every image then sits in the
+    same batch, at the same row, whatever the world size, so per-image results (and therefore the summed counts) are
+    bit-identical between a sharded run and a single-GPU run; only the last global batch can be ragged."""
+    if batch < 1:
+        raise ValueError("bad batch size")
+    n_batches = -(-n_images // batch)
+    lo, hi = shard_range(n_batches, rank, world_size)
+    return lo, hi, n_batches
+
+
 def init_from_env(backend: str | None = None) -> tuple[int, int, int]:
     """(rank, world_size, local_rank) from torchrun's environment; initialises the process group when
     WORLD_SIZE > 1."""

@@ -156,3 +156,12 @@ class EvalEngine:
     def read_counts(self) -> torch.Tensor:
         self.synchronize()
         return self.counts.cpu()
+
+    def allreduce_counts(self) -> torch.Tensor:
+        """The job's single collective (multi-GPU): sums the count tensor over all ranks ON THE ENGINE STREAM, i.e.
+        ordered after every batch queued so far -- ``torch.distributed.all_reduce`` only orders against the caller's
+        current stream, so calling it on ``eng.counts`` from the default stream could reduce a partial tensor."""
+        from . import distributed as D
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            D.allreduce_counts(self.counts)
+        return self.counts

@@ -76,3 +76,20 @@ def test_shard_range_partitions():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         shard_range(10, 2, 2)
+
+
+def test_shard_batches_cover_every_image_once():
+    """configs[2] sharding (bench.py --workload shard1m): whole batches, contiguous, balanced, ragged tail only in the
+    last global batch."""
+    from skin_image_analysis_b200.distributed import shard_batches
+    for n_images, batch in [(1_000_000, 256), (1000, 32), (5, 8), (512, 256)]:
+        for world in (1, 2, 3, 8):
+            seen = []
+            for r in range(world):
+                lo, hi, nb = shard_batches(n_images, batch, r, world)
+                assert nb == -(-n_images // batch) and 0 <= lo <= hi <= nb
+                seen += list(range(lo, hi))
+            assert seen == list(range(nb))
+            sizes = [shard_batches(n_images, batch, r, world)[1] - shard_batches(n_images, batch, r, world)[0]
+                     for r in range(world)]
+            assert max(sizes) - min(sizes) <= 1

