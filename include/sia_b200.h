@@ -121,6 +121,22 @@ int sia_preprocess_tc2_u8hwc(const uint8_t* src, int batch, int src_h, int src_w
                              int last_block_cols, int out_h, int out_w, const float* out_scale_host,
                              const float* out_bias_host, void* dst_nhwc4, void* stream);
 
+/* Warp-MMA variant of the same transform -- the DEFAULT for the padded NHWC4 bf16 layout (csrc/preprocess_mma.cu):
+ * both banded products of the resize run on mma.sync.m16n8k16 with the operands built in registers from the raw image
+ * bytes (the accumulators of the vertical product are the A fragments of the horizontal one), source rows streamed by
+ * one cp.async.bulk per 8-row octet into a shared-memory ring, whole-sector stores; pad columns are written as zeros.
+ * Replaces tone_bias_dataset.py:335, :411-427, :464-473 like sia_preprocess_u8hwc.  Tables:
+ * resize_weights.build_mma_tables (wy_frag [n_msteps][kv][32] x 16 B A fragments; r0 [n_msteps] window start rows,
+ * multiples of 8; wx_frag [n_tiles][2][2][32] x 8 B B fragments; wx_mask [n_tiles]; tile_begin [n_groups + 1]);
+ * q_stride / c_row4_host [4]: which row of a 16-row chunk the K slots read (resize_weights.MMA_ROW_MAPS);
+ * mul3_host [3] = 2^9 * scale / std_c, bias3_host [3] = -mean_c / std_c (host memory).  kv in {2, 3}.  Needs
+ * src_w % 8 == 0, even src_h, out_w % 8 == 0, 16-byte aligned src / dst; SIA_E_UNSUPPORTED otherwise. */
+int sia_preprocess_mma_u8hwc(const uint8_t* src, int batch, int src_h, int src_w, const void* wy_frag,
+                             const int32_t* r0, int n_msteps, int kv, const void* wx_frag, const uint32_t* wx_mask,
+                             const int32_t* tile_begin, int n_groups, int n_tiles, int q_stride,
+                             const int32_t* c_row4_host, const float* mul3_host, const float* bias3_host, int out_h,
+                             int out_w, void* dst, void* stream);
+
 /* SURVEY 8(f) row 2 -- the ToneClassifier test transform (notebooks/ToneClassifier/CNNTrialDataset.py:71-76:
  * v2.Resize((224,224)) on uint8 [bilinear, antialias] -> v2.ToDtype(float32, scale=True) -> v2.Normalize(mean, std))
  * for a batch of u8 HWC decode buffers.  torchvision's uint8 resize is ATen's fixed-point separable resampler

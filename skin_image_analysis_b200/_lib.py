@@ -33,6 +33,10 @@ SIGNATURES = {
                                         c_int, c_int, c_int, ctypes.POINTER(c_float), ctypes.POINTER(c_float), _P, _P]),
     "sia_preprocess_tc2_u8hwc": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, c_int, c_int, _P, _P, _P, c_int, c_int,
                                          c_int, c_int, ctypes.POINTER(c_float), ctypes.POINTER(c_float), _P, _P]),
+    "sia_preprocess_mma_u8hwc": (c_int, [_P, c_int, c_int, c_int, _P, _P, c_int, c_int, _P, _P, _P, c_int, c_int, c_int,
+                                         ctypes.POINTER(c_int32), ctypes.POINTER(c_float), ctypes.POINTER(c_float),
+                                         c_int, c_int, _P, _P]),
+    "sia_debug_set_mma_warps": (c_int, [c_int]),
     "sia_preprocess_tv_u8hwc": (c_int, [_P, c_int, c_int, c_int, _P, _P, c_int, c_int, _P, _P, c_int, c_int, _P, c_int,
                                         c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "sia_debug_tv_force_generic": (c_int, [c_int]),

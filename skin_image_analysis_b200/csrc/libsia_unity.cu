@@ -6,6 +6,7 @@
 #include "preprocess.cu"
 #include "preprocess_tc.cu"
 #include "preprocess_tc2.cu"
+#include "preprocess_mma.cu"
 #include "preprocess_tv.cu"
 #include "conv3x3.cu"
 #include "conv1.cu"

@@ -97,6 +97,28 @@ def _tc2_tables(device_index: int, src_h: int, src_w: int, out_h: int, out_w: in
     return _DeviceTc2Tables(t, torch.device("cuda", device_index))
 
 
+class _DeviceMmaTables:
+    def __init__(self, t: _rw.MmaTables, device):
+        self.host = t
+        self.wy_frag = torch.from_numpy(np.ascontiguousarray(t.wy_frag).view(np.int32)).to(device)
+        self.r0 = torch.from_numpy(np.ascontiguousarray(t.r0)).to(device)
+        self.wx_frag = torch.from_numpy(np.ascontiguousarray(t.wx_frag).view(np.int32)).to(device)
+        self.wx_mask = torch.from_numpy(np.ascontiguousarray(t.wx_mask).view(np.int32)).to(device)
+        self.tile_begin = torch.from_numpy(np.ascontiguousarray(t.tile_begin)).to(device)
+        qs, cs = _rw.MMA_ROW_MAPS[t.row_map]
+        self.q_stride, self.c_row = qs, (ctypes.c_int32 * 4)(*cs)
+
+
+@lru_cache(maxsize=64)
+def _mma_tables(device_index: int, src_h: int, src_w: int, out_h: int, out_w: int, antialias):
+    """Tables of the warp-MMA kernel, or None when the geometry does not fit it."""
+    try:
+        t = _rw.build_mma_tables(src_h, src_w, out_h, out_w, antialias=antialias)
+    except ValueError:
+        return None
+    return _DeviceMmaTables(t, torch.device("cuda", device_index))
+
+
 _LAYOUT_DTYPE = {LAYOUT_NCHW_F32: torch.float32, LAYOUT_NCHW_BF16: torch.bfloat16, LAYOUT_NHWC4_BF16: torch.bfloat16}
 
 
@@ -109,7 +131,9 @@ def preprocess_u8hwc(src: torch.Tensor, size, layout: int = LAYOUT_NCHW_F32, mea
     Defaults reproduce the reference transform exactly: ``float32(u8)/255`` (tone_bias_dataset.py:335),
     ``skimage.transform.resize`` (:425), no mean/std, CHW (:470).  ``fixed_point`` lets the bf16 layouts
     use the 15-bit integer-dot-product horizontal pass (<= 0.03 bf16 ulp from the fp32 pass); the fp32
-    layout always uses fp32 arithmetic.  ``impl``: "cuda_core" (csrc/preprocess.cu), "tensor_core"
+    layout always uses fp32 arithmetic.  ``impl``: "mma" (csrc/preprocess_mma.cu: both passes on mma.sync with
+    register-built operands; NHWC4 layout, src_w % 8 == 0, even src_h, out_w % 8 == 0 -- what "auto" picks first),
+    "cuda_core" (csrc/preprocess.cu), "tensor_core"
     (csrc/preprocess_tc.cu: vertical pass as a tcgen05 GEMM; NHWC4 layout, src_w % 8 == 0, <= 256 source rows
     per 128 output rows), "tensor_core2" (csrc/preprocess_tc2.cu: the horizontal pass is a second tcgen05 product
     too; additionally <= 4 + 13 + 4 output columns per 40-pixel block, out_w % 4 == 0) or "auto" = tensor_core2, else
@@ -131,8 +155,20 @@ def preprocess_u8hwc(src: torch.Tensor, size, layout: int = LAYOUT_NCHW_F32, mea
             raise ValueError(f"out must have shape {shape}")
     osc = (ctypes.c_float * 3)(*[1.0 / float(s) for s in std])
     obi = (ctypes.c_float * 3)(*[-float(m) / float(s) for m, s in zip(mean, std)])
-    if impl not in ("auto", "cuda_core", "tensor_core", "tensor_core2"):
-        raise ValueError("impl must be 'auto', 'cuda_core', 'tensor_core' or 'tensor_core2'")
+    if impl not in ("auto", "cuda_core", "tensor_core", "tensor_core2", "mma"):
+        raise ValueError("impl must be 'auto', 'mma', 'cuda_core', 'tensor_core' or 'tensor_core2'")
+    if impl == "mma" or (impl == "auto" and fixed_point and layout == LAYOUT_NHWC4_BF16):
+        tm = _mma_tables(src.device.index, sh, sw, oh, ow, antialias) if layout == LAYOUT_NHWC4_BF16 else None
+        if tm is not None and src.data_ptr() % 16 == 0 and out.data_ptr() % 16 == 0:
+            h = tm.host
+            mul = (ctypes.c_float * 3)(*[_rw.MMA_OUT_SCALE * float(scale) / float(s) for s in std])
+            check(_lib.load().sia_preprocess_mma_u8hwc(
+                ptr(src), b, sh, sw, ptr(tm.wy_frag), ptr(tm.r0), h.n_msteps, h.kv, ptr(tm.wx_frag), ptr(tm.wx_mask),
+                ptr(tm.tile_begin), h.n_groups, h.n_tiles, tm.q_stride, tm.c_row, mul, obi, oh, ow, ptr(out),
+                stream_ptr()), "sia_preprocess_mma_u8hwc")
+            return out
+        if impl == "mma":
+            raise SiaError("warp-MMA preprocess does not support this geometry / layout")
     auto_tc = impl == "auto" and fixed_point and layout == LAYOUT_NHWC4_BF16 and src.data_ptr() % 16 == 0
     t2 = None
     if (impl == "tensor_core2" or auto_tc) and layout == LAYOUT_NHWC4_BF16 and out.data_ptr() % 32 == 0:

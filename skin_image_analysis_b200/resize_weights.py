@@ -584,3 +584,171 @@ def tc2_emulate(u8: np.ndarray, t: Tc2Tables, out_h: int, out_w: int, scale: flo
                     o = d2[:lanes, 3 * sl: 3 * sl + 3] * (t.slot_scale[b, sl] * np.float32(scale))
                     out[tile * v.tile_rows: tile * v.tile_rows + lanes, j] = o
     return out
+
+
+# -------------------------------------------------------------------------------------------------
+# Tables of the warp-MMA kernel (csrc/preprocess_mma.cu)
+# -------------------------------------------------------------------------------------------------
+MMA_ROWS = 16             # output rows of one m-step = M of mma.sync.m16n8k16
+MMA_GROUP_PX = 32         # source pixels of one column group: 8 lane groups x 4 pixels (12 bytes) each
+MMA_WY_SHIFT = 15         # vertical weights are stored as fp16(w * 2^15); the image bytes enter as fp16 subnormals b * 2^-24
+MMA_OUT_SCALE = 2.0 ** (24 - MMA_WY_SHIFT)        # what the kernel multiplies its accumulators by (besides scale / std)
+# which row of a 16-row chunk lane quad-index q reads for the four K slots c = 0..3 (k = 2q, 2q+1, 2q+8, 2q+9):
+# "natural": 2q + (0, 1, 8, 9);  "spread": 4q + (0, 1, 2, 3) -- chosen per row pitch so that the 32 lanes of one
+# shared-memory load hit 32 different banks (600-pixel rows: 450 words = 2 (mod 32) -> "spread" is conflict free)
+MMA_ROW_MAPS = {"natural": (2, (0, 1, 8, 9)), "spread": (4, (0, 1, 2, 3))}
+
+
+def mma_row_map(row_bytes: int) -> str:
+    """The mapping with fewer shared-memory bank conflicts for rows of ``row_bytes`` bytes stored back to back."""
+    words = row_bytes // 4
+    best, best_cost = "natural", None
+    for name, (qs, cs) in MMA_ROW_MAPS.items():
+        cost = 0
+        for c in cs:
+            banks = [((qs * q + c) * words + 3 * g) % 32 for q in range(4) for g in range(8)]
+            cost += len(banks) - len(set(banks))
+        if best_cost is None or cost < best_cost:
+            best, best_cost = name, cost
+    return best
+
+
+@dataclass
+class MmaTables:
+    """Everything ``sia_preprocess_mma_u8hwc`` needs for one (source size, output size).
+
+    The resize is two banded products run on the warp-level tensor-core path (mma.sync.m16n8k16, fp16 in / fp32
+    accumulate), chained in registers:
+
+        V[i, k]    = sum_r Wy[i, r] S[r, k]        M = 16 output rows, N = 8 image-byte columns, K = 16*kv source rows
+        out[i, j]  = sum_x Wx[j, x] V[i, x, c]     M = the same 16 rows, N = 8 output pixels of channel c, K = 16 pixels
+
+    * one m-step = 16 output rows; it reads the source rows [r0[m], r0[m] + 16 kv), r0 a multiple of 8.
+    * the source row is cut into groups of 32 pixels (96 bytes); lane group g (= lane / 4) of a warp owns the 12 bytes
+      [96 grp + 12 g, +12): V n-tile b (0..11) holds byte b of every lane group, i.e. its 8 columns are the pixels
+      4 g + b / 3 of channel b % 3 -- which makes the accumulators of the first product, two n-tiles at a time,
+      exactly the A operand of the second one (K index k < 8: pixel 4 k + 2 X, k >= 8: pixel 4 (k - 8) + 2 X + 1 for
+      the K chunk X in {0, 1}); the de-interleaving of the channels costs nothing.
+    * output n-tile t = the padded columns [8 t, 8 t + 8) of the NHWC4 row (pixel j sits in column j + 1, pad columns
+      carry zero weights and come out as zeros).  A tile reads at most two adjacent groups; it is computed when its
+      LAST group has been processed, from the V fragments of that group ("cur") and of the one before ("prev"):
+      the tiles finished by group grp are [tile_begin[grp], tile_begin[grp + 1]).
+    * the weights are rounded to fp16 individually (every weight keeps 11 significant bits, so sparse / dark images
+      keep their relative accuracy); the row and column sums are then 1 +- 3e-4, which is NOT renormalised: a flat
+      image comes out within 6e-4 (relative) of flat before the bf16 rounding, i.e. within one bf16 ulp.  The only
+      scale left in the kernel is the constant ``MMA_OUT_SCALE``.
+    """
+    kv: int
+    n_msteps: int
+    n_groups: int
+    n_tiles: int
+    row_map: str
+    r0: np.ndarray            # int32 [n_msteps]
+    wy_frag: np.ndarray       # uint32 [n_msteps, kv, 32, 4]     A fragments of the vertical operator
+    wx_frag: np.ndarray       # uint32 [n_tiles, 2, 2, 32, 2]    B fragments of the horizontal operator [tile][prev/cur][X]
+    wx_mask: np.ndarray       # uint32 [n_tiles]                 bit (rel * 2 + X): that fragment has a non-zero weight
+    tile_begin: np.ndarray    # int32 [n_groups + 1]
+    wy16: np.ndarray          # float64 [n_msteps * 16, src_h]   fp16-rounded vertical weights (unshifted), for emulation
+    wx16: np.ndarray          # float64 [out_w + 8, src_w]       fp16-rounded horizontal weights per padded column
+
+
+def _f16_bits(x: np.ndarray) -> np.ndarray:
+    return np.asarray(x, np.float16).view(np.uint16).astype(np.uint32)
+
+
+def build_mma_tables(src_h: int, src_w: int, out_h: int, out_w: int, antialias: str | bool = "skimage") -> MmaTables:
+    """Raises ValueError when the geometry does not fit the kernel (the caller falls back to another kernel)."""
+    if src_w % 8 != 0 or src_h % 2 != 0:
+        raise ValueError("the warp-MMA kernel copies 16-byte aligned octets of rows: src_w % 8 and src_h % 2 must be 0")
+    if out_w % 8 != 0:
+        raise ValueError("the warp-MMA kernel writes n-tiles of 8 padded columns: out_w % 8 must be 0")
+    if antialias == "skimage":
+        aa = out_h < src_h or out_w < src_w
+    else:
+        aa = bool(antialias)
+    rows_y = axis_operator_rows(src_h, out_h, aa)
+    rows_x = axis_operator_rows(src_w, out_w, aa)
+    # ---------------- vertical operator: windows and A fragments ------------------------------------------------------
+    n_msteps = -(-out_h // MMA_ROWS)
+    r0 = np.zeros(n_msteps, np.int32)
+    span = 0
+    for m in range(n_msteps):
+        rs = rows_y[m * MMA_ROWS: (m + 1) * MMA_ROWS]
+        first, last = min(min(r) for r in rs), max(max(r) for r in rs)
+        r0[m] = first // 8 * 8
+        span = max(span, last - r0[m] + 1)
+    kv = -(-span // 16)
+    if kv > 3:
+        raise ValueError(f"16 output rows read {span} source rows: more than the 48-row window of the warp-MMA kernel")
+    kv = max(kv, 2)
+    if np.any(np.diff(r0) < 0):
+        raise ValueError("vertical windows are not monotonic")
+    wy16 = np.zeros((n_msteps * MMA_ROWS, src_h), np.float64)
+    a_dense = np.zeros((n_msteps, MMA_ROWS, 16 * kv), np.float64)           # fp16(w * 2^15), window-relative columns
+    for i, r in enumerate(rows_y):
+        m = i // MMA_ROWS
+        if max(r.values()) * 2.0 ** MMA_WY_SHIFT > 65504.0:
+            raise ValueError("vertical weight overflows fp16")
+        q = {c: float(np.float16(v * 2.0 ** MMA_WY_SHIFT)) for c, v in r.items()}     # round to nearest: every weight
+        for c, v in q.items():                                                      # keeps 11 significant bits
+            a_dense[m, i % MMA_ROWS, c - r0[m]] = v
+            wy16[i, c] = v * 2.0 ** -MMA_WY_SHIFT
+    row_map = mma_row_map(3 * src_w)
+    qs, cs = MMA_ROW_MAPS[row_map]
+    lane = np.arange(32)
+    g, q4 = lane // 4, lane % 4
+    wy_frag = np.zeros((n_msteps, kv, 32, 4), np.uint32)
+    for kc in range(kv):
+        blk = a_dense[:, :, 16 * kc: 16 * kc + 16]                             # [m, row, chunk row]
+        # A fragment register reg holds (row, logical k) = a0 (g, 2q / 2q+1), a1 (g+8, same), a2 (g, 2q+8 / 2q+9), a3;
+        # logical k = 2q + (c & 1) + 8 (c >> 1) reads chunk row qs * q + cs[c]
+        for reg, (rr, c_lo) in enumerate(((g, 0), (g + 8, 0), (g, 2), (g + 8, 2))):
+            lo = _f16_bits(blk[:, rr, qs * q4 + cs[c_lo]])
+            hi = _f16_bits(blk[:, rr, qs * q4 + cs[c_lo + 1]])
+            wy_frag[:, kc, :, reg] = lo | (hi << np.uint32(16))
+    # ---------------- horizontal operator: n-tiles and B fragments ----------------------------------------------------
+    n_groups = -(-src_w // MMA_GROUP_PX)
+    n_tiles = (out_w + NHWC4_PAD) // 8
+    wx16 = np.zeros((out_w + NHWC4_PAD, src_w), np.float64)
+    for j, r in enumerate(rows_x):
+        for c, v in r.items():
+            wx16[j + 1, c] = float(np.float16(v))
+    tile_first, tile_last = np.zeros(n_tiles, np.int32), np.zeros(n_tiles, np.int32)
+    for t in range(n_tiles):
+        cols = np.nonzero(wx16[8 * t: 8 * t + 8].any(0))[0]
+        if len(cols) == 0:
+            raise ValueError("an output n-tile without any real pixel")
+        tile_first[t], tile_last[t] = int(cols.min()) // MMA_GROUP_PX, int(cols.max()) // MMA_GROUP_PX
+    if np.any(tile_last - tile_first > 1):
+        raise ValueError("an output n-tile reads more than two column groups")
+    if np.any(np.diff(tile_last) < 0):
+        raise ValueError("horizontal windows are not monotonic")
+    tile_begin = np.array([int(np.searchsorted(tile_last, grp, side="left")) for grp in range(n_groups + 1)], np.int32)
+    wx_frag = np.zeros((n_tiles, 2, 2, 32, 2), np.uint32)
+    wx_mask = np.zeros(n_tiles, np.uint32)
+    k_idx = np.stack([2 * q4, 2 * q4 + 1, 2 * q4 + 8, 2 * q4 + 9], 1)         # [lane, 4] logical k of b0.lo, b0.hi, b1.lo, b1.hi
+    for t in range(n_tiles):
+        pc = 8 * t + g                                                        # padded column of n = g
+        for rel in range(2):
+            grp = int(tile_last[t]) - 1 + rel
+            if grp < 0:
+                continue
+            for x_chunk in range(2):
+                px = 32 * grp + 4 * (k_idx % 8) + 2 * x_chunk + (k_idx // 8)     # source pixel of logical k
+                w = np.where(px < src_w, wx16[pc[:, None], np.minimum(px, src_w - 1)], 0.0)
+                if np.any(w != 0.0):
+                    wx_mask[t] |= np.uint32(1 << (rel * 2 + x_chunk))
+                bits = _f16_bits(w)
+                wx_frag[t, rel, x_chunk, :, 0] = bits[:, 0] | (bits[:, 1] << np.uint32(16))
+                wx_frag[t, rel, x_chunk, :, 1] = bits[:, 2] | (bits[:, 3] << np.uint32(16))
+    return MmaTables(kv, n_msteps, n_groups, n_tiles, row_map, r0, wy_frag, wx_frag, wx_mask, tile_begin, wy16, wx16)
+
+
+def mma_emulate(u8: np.ndarray, t: MmaTables, out_h: int, out_w: int, scale: float = 1.0 / 255.0) -> np.ndarray:
+    """numpy model of the warp-MMA kernel's arithmetic (fp16 weights, fp32 accumulate, V rounded once to fp16) -> [out_h, out_w, 3] float32, before mean / std and the bf16 rounding."""
+    src_h, src_w, _ = u8.shape
+    s = u8.reshape(src_h, src_w * 3).astype(np.float64)
+    v = (t.wy16[:out_h] * 2.0 ** MMA_WY_SHIFT) @ (s * 2.0 ** -24)              # what the first product accumulates
+    v16 = v.astype(np.float32).astype(np.float16).astype(np.float64).reshape(out_h, src_w, 3)
+    h = np.einsum("jx,ixc->ijc", t.wx16[1: out_w + 1], v16).astype(np.float32)
+    return h * (np.float32(MMA_OUT_SCALE) * np.float32(scale))

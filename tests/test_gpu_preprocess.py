@@ -214,9 +214,9 @@ def test_two_product_pass_large_batches_and_flat_images():
 
 
 def test_auto_falls_back_when_the_tensor_core_kernels_do_not_fit():
-    """impl="auto" on the NHWC4 layout: a geometry neither tensor-core kernel takes (131-pixel rows are not a multiple
-    of 8 bytes) goes to the CUDA-core kernel, a 512 x 512 output (too many columns per block for the two-product
-    kernel) to the one-product kernel; asking for a kernel explicitly still refuses loudly."""
+    """impl="auto" on the NHWC4 layout: a geometry no tensor-core kernel takes (131-pixel rows are not a multiple
+    of 8 bytes) goes to the CUDA-core kernel, a 512 x 512 output to the warp-MMA kernel (the two-product tcgen05 kernel
+    refuses it: too many columns per block); asking for a kernel explicitly still refuses loudly."""
     from skin_image_analysis_b200 import _lib, ops
     odd = helpers.synthetic_u8_image(97, 131, 8, "noise")
     auto = _gpu([odd], (64, 64), ops.LAYOUT_NHWC4_BF16)
@@ -225,4 +225,6 @@ def test_auto_falls_back_when_the_tensor_core_kernels_do_not_fit():
         _gpu([odd], (64, 64), ops.LAYOUT_NHWC4_BF16, impl="tensor_core")
     big = helpers.synthetic_u8_image(450, 600, 9, "smooth")
     auto = _gpu([big], (512, 512), ops.LAYOUT_NHWC4_BF16)
-    assert torch.equal(auto, _gpu([big], (512, 512), ops.LAYOUT_NHWC4_BF16, impl="tensor_core"))
+    assert torch.equal(auto, _gpu([big], (512, 512), ops.LAYOUT_NHWC4_BF16, impl="mma"))
+    with pytest.raises(_lib.SiaError):
+        _gpu([big], (512, 512), ops.LAYOUT_NHWC4_BF16, impl="tensor_core2")

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
     product = {n for n, _ in _declared("sia_b200.h")}
     debug = {n for n, _ in _declared("sia_b200_debug.h")}
     assert product and debug and not (product & debug)
-    switches = {"sia_debug_tv_force_generic", "sia_debug_set_trace", "sia_debug_set_stats"}
+    switches = {"sia_debug_tv_force_generic", "sia_debug_set_trace", "sia_debug_set_stats", "sia_debug_set_mma_warps"}
     assert not any(n.startswith("sia_debug") for n in product)
     for name in sorted(product | switches):
         assert hasattr(lib, name), f"{name} declared but not exported by libsia_b200.so"
@@ -268,3 +268,75 @@ def test_two_product_tables_reject_unsupported_geometry():
     for shape in [(450, 600, 512, 512), (300, 400, 224, 224)]:
         with pytest.raises(ValueError):
             rw.build_tc2_tables(*shape)
+
+
+@pytest.mark.parametrize("shape", [(450, 600, 224, 224), (450, 600, 512, 512), (300, 400, 224, 224), (96, 128, 64, 88),
+                                   (480, 640, 224, 224), (200, 200, 224, 224)])
+def test_warp_mma_tables_reproduce_the_oracle_operator(shape):
+    """resize_weights.build_mma_tables: the fp16 weights are the exact operator rounded to nearest (row / column sums
+    within 5e-4 of one), the fragment tables hold exactly the dense fp16 operators (through the row permutation and the
+    K order of the second product), and the numpy model of the kernel's arithmetic is within 8e-4 of full scale of
+    the oracle and within one bf16 ulp of it after rounding -- also on the sparse 0 / 255 pattern."""
+    from skin_image_analysis_b200 import resize_weights as rw
+    h, w, oh, ow = shape
+    t = rw.build_mma_tables(h, w, oh, ow)
+    assert t.kv in (2, 3) and t.n_tiles == (ow + 8) // 8 and t.n_groups == -(-w // 32)
+    assert np.abs(t.wy16[:oh].sum(1) - 1.0).max() <= 5e-4 and np.abs(t.wx16[1:ow + 1].sum(1) - 1.0).max() <= 5e-4
+    assert np.all(t.wx16[0] == 0) and np.all(t.wx16[ow + 1:] == 0)
+    lane = np.arange(32)
+    g, q = lane // 4, lane % 4
+    qs, cs = rw.MMA_ROW_MAPS[t.row_map]
+    rows_read = sorted({qs * qq + c for qq in range(4) for c in cs})
+    assert rows_read == list(range(16))                    # the permutation covers the 16 rows of a chunk exactly once
+    if w == 600:
+        assert t.row_map == "spread"                       # 450-word rows: conflict-free only with the spread map
+    # A fragments -> dense Wy: register (a0, a1, a2, a3) = rows (g, g+8, g, g+8), K slots (0/1, 0/1, 2/3, 2/3)
+    for m in (0, t.n_msteps // 2, t.n_msteps - 1):
+        dense = np.zeros((16, 16 * t.kv))
+        for kc in range(t.kv):
+            for reg, (rr, c_lo) in enumerate(((g, 0), (g + 8, 0), (g, 2), (g + 8, 2))):
+                word = t.wy_frag[m, kc, :, reg]
+                dense[rr, 16 * kc + qs * q + cs[c_lo]] = (word & 0xFFFF).astype(np.uint16).view(np.float16)
+                dense[rr, 16 * kc + qs * q + cs[c_lo + 1]] = (word >> 16).astype(np.uint16).view(np.float16)
+        rows = np.arange(16 * m, min(16 * m + 16, oh))
+        cols = np.arange(t.r0[m], min(t.r0[m] + 16 * t.kv, h))
+        assert np.array_equal(dense[:len(rows), :len(cols)] * 2.0 ** -15, t.wy16[rows][:, cols])
+        assert t.r0[m] % 8 == 0 and not t.wy16[rows][:, :t.r0[m]].any() and not t.wy16[rows][:, t.r0[m] + 16 * t.kv:].any()
+    # B fragments -> dense Wx: every non-zero weight appears exactly once, in the fragment of its source group
+    seen = np.zeros_like(t.wx16)
+    tile_last = np.searchsorted(t.tile_begin, np.arange(t.n_tiles), side="right") - 1
+    assert t.tile_begin[0] == 0 and t.tile_begin[-1] == t.n_tiles and np.all(np.diff(t.tile_begin) >= 0)
+    for tile in range(t.n_tiles):
+        for rel in range(2):
+            grp = int(tile_last[tile]) - 1 + rel
+            for x in range(2):
+                frag = t.wx_frag[tile, rel, x]
+                assert bool(frag.any()) == bool((t.wx_mask[tile] >> (rel * 2 + x)) & 1)
+                if grp < 0:
+                    assert not frag.any()
+                    continue
+                for reg in range(2):
+                    for half in range(2):
+                        k = 2 * q + half + 8 * reg
+                        px = 32 * grp + 4 * (k % 8) + 2 * x + k // 8
+                        val = ((frag[:, reg] >> (16 * half)) & 0xFFFF).astype(np.uint16).view(np.float16).astype(np.float64)
+                        ok = px < w
+                        np.add.at(seen, ((8 * tile + g)[ok], px[ok]), val[ok])
+                        assert not val[~ok].any()
+    assert np.array_equal(seen, t.wx16)
+    for kind in ("noise", "extremes", "smooth"):
+        u8 = helpers.synthetic_u8_image(h, w, 77, kind)
+        got = rw.mma_emulate(u8, t, oh, ow)
+        want = R.transform_u8(u8, (oh, ow)).transpose(1, 2, 0)
+        assert np.abs(got - want).max() <= 8e-4
+        got_bf, want_bf = (torch.from_numpy(np.ascontiguousarray(a)).to(torch.bfloat16).float().numpy() for a in (got, want))
+        assert np.all(np.abs(got_bf - want_bf) <= np.maximum(np.abs(want_bf), 2.0 ** -126) * 2.0 ** -7), kind
+    flat = np.full((h, w, 3), 200, np.uint8)
+    assert np.abs(rw.mma_emulate(flat, t, oh, ow) / (200.0 / 255.0) - 1.0).max() <= 1e-3
+
+
+def test_warp_mma_tables_reject_unsupported_geometry():
+    from skin_image_analysis_b200 import resize_weights as rw
+    for shape in [(97, 131, 64, 64), (450, 600, 112, 112), (450, 600, 224, 220), (451, 600, 224, 224)]:
+        with pytest.raises(ValueError):
+            rw.build_mma_tables(*shape)
