@@ -25,8 +25,10 @@
 //     fragments and the previous group's (kept in registers), scaled, rounded to bf16 and stored as whole 32-byte
 //     sectors (a lane quad writes 64 contiguous bytes).  Pad columns of the NHWC4 row have zero weights: the kernel
 //     writes them as zeros itself.
-//   * the compute warps of a CTA split the groups of a row; each also runs the first product of the last group of
-//     its left neighbour (halo) so that every n-tile is finished by exactly one warp without any exchange.
+//   * the compute warps of a CTA split the groups of a row.  A tile that straddles two warps' ranges is finished by the
+//     LEFT warp: the right warp publishes the V fragments of its first group in shared memory as soon as it has them
+//     (early in its sweep), the left warp picks them up at the end of its own sweep (mbarrier handshake, one 3 KB
+//     buffer per boundary) -- no group is computed twice and nobody waits in steady state.
 //   * one more warp streams the source rows into a ring of 8-row octets, ONE cp.async.bulk per octet (14 400 bytes at
 //     the bench shape: the copy engine retires a request every ~190 clocks whatever its size, so per-row copies cap
 //     the kernel at 2.7 TB/s).  Rows sit back to back; which chunk row a lane reads for which K slot is a per-geometry
@@ -46,6 +48,7 @@
 namespace sia {
 
 constexpr int PM_GROUP_BYTES = 96;               // 32 pixels
+constexpr int PM_PUB_WORDS = 24 * 32;            // one published set of A fragments: 24 registers x 32 lanes
 
 struct PreMmaParams {
   const uint8_t* src;
@@ -73,6 +76,81 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
 }
 // pack_f16x2 / pack_bf16x2 (lo, hi) -> one 32-bit register: preprocess_tc2.cu / sia_ptx.cuh
 
+// mbarrier wait that backs off between polls (the copy lane shares its scheduler with two compute warps)
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t site) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(64);
+    if (++spins > (SIA_WATCHDOG_SPINS >> 2)) {
+      if (g_watchdog_word != nullptr) {
+        *g_watchdog_word = 0x80000000u | (site << 16) | (blockIdx.x & 0xffffu);
+        __threadfence_system();
+      }
+      __trap();
+    }
+  }
+}
+
+// One output n-tile: second product from the previous / current group's A fragments, scale, bf16, two 16-byte stores.
+struct PmOut {
+  uint8_t* row0;
+  uint8_t* row1;
+  bool ok0, ok1;
+  float mul0, mul1, mul2, bias0, bias1, bias2;
+  int has_bias, out_w, q;
+};
+__device__ __forceinline__ void pm_tile(const PmOut& o, int t, uint32_t mask, const uint2* wxt,
+                                        const uint32_t (&prev)[3][2][4], const uint32_t (&cur)[3][2][4]) {
+  float hp[3][4], hc[3][4];                       // two independent accumulation chains per channel
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) hp[c][e] = hc[c][e] = 0.f;
+#pragma unroll
+  for (int x = 0; x < 2; ++x) {
+    if ((mask >> x) & 1u) {
+      const uint2 bf = wxt[x * 32];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) mma16816(hp[c], prev[c][x], bf.x, bf.y);
+    }
+    if ((mask >> (2 + x)) & 1u) {
+      const uint2 bf = wxt[(2 + x) * 32];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) mma16816(hc[c], cur[c][x], bf.x, bf.y);
+    }
+  }
+  const int pc0 = t * 8 + 2 * o.q;
+  float b00 = 0.f, b01 = 0.f, b02 = 0.f, b10 = 0.f, b11 = 0.f, b12 = 0.f;
+  if (o.has_bias) {                                     // pad columns stay zero whatever the bias
+    if (pc0 >= 1 && pc0 <= o.out_w) { b00 = o.bias0; b01 = o.bias1; b02 = o.bias2; }
+    if (pc0 + 1 <= o.out_w) { b10 = o.bias0; b11 = o.bias1; b12 = o.bias2; }
+  }
+  if (o.ok0) {
+    uint4 v;
+    v.x = pack_bf16x2(fmaf(hp[0][0] + hc[0][0], o.mul0, b00), fmaf(hp[1][0] + hc[1][0], o.mul1, b01));
+    v.y = pack_bf16x2(fmaf(hp[2][0] + hc[2][0], o.mul2, b02), 0.f);
+    v.z = pack_bf16x2(fmaf(hp[0][1] + hc[0][1], o.mul0, b10), fmaf(hp[1][1] + hc[1][1], o.mul1, b11));
+    v.w = pack_bf16x2(fmaf(hp[2][1] + hc[2][1], o.mul2, b12), 0.f);
+#ifndef SIA_PM_NO_STORE
+    *reinterpret_cast<uint4*>(o.row0 + (size_t)pc0 * 8) = v;
+#else
+    if (v.x == 0x12345678u) *reinterpret_cast<uint4*>(o.row0 + (size_t)pc0 * 8) = v;
+#endif
+  }
+  if (o.ok1) {
+    uint4 v;
+    v.x = pack_bf16x2(fmaf(hp[0][2] + hc[0][2], o.mul0, b00), fmaf(hp[1][2] + hc[1][2], o.mul1, b01));
+    v.y = pack_bf16x2(fmaf(hp[2][2] + hc[2][2], o.mul2, b02), 0.f);
+    v.z = pack_bf16x2(fmaf(hp[0][3] + hc[0][3], o.mul0, b10), fmaf(hp[1][3] + hc[1][3], o.mul1, b11));
+    v.w = pack_bf16x2(fmaf(hp[2][3] + hc[2][3], o.mul2, b12), 0.f);
+#ifndef SIA_PM_NO_STORE
+    *reinterpret_cast<uint4*>(o.row1 + (size_t)pc0 * 8) = v;
+#else
+    if (v.x == 0x12345678u) *reinterpret_cast<uint4*>(o.row1 + (size_t)pc0 * 8) = v;
+#endif
+  }
+}
+
 template <int KV, int NW>
 __global__ void __launch_bounds__((NW + 1) * 32, 1) preprocess_mma_kernel(const PreMmaParams p) {
   extern __shared__ __align__(128) uint8_t pm_smem[];
@@ -83,10 +161,10 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) preprocess_mma_kernel(const 
   // ---- shared-memory carve-up -------------------------------------------------------------------------------------
   uint8_t* ring = pm_smem;
   size_t off = (size_t)R * octet_bytes;
-  uint4* wy_s = reinterpret_cast<uint4*>(pm_smem + off);
-  off += (size_t)p.n_msteps * KV * 32 * sizeof(uint4);
   uint2* wx_s = reinterpret_cast<uint2*>(pm_smem + off);
   off += (size_t)p.n_tiles * 4 * 32 * sizeof(uint2);
+  uint32_t* pub_s = reinterpret_cast<uint32_t*>(pm_smem + off);           // [NW][24][32]; slot 0 unused
+  off += (size_t)NW * PM_PUB_WORDS * sizeof(uint32_t);
   int* r0_s = reinterpret_cast<int*>(pm_smem + off);
   off += (size_t)p.n_msteps * sizeof(int);
   int* tbeg_s = reinterpret_cast<int*>(pm_smem + off);
@@ -96,12 +174,20 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) preprocess_mma_kernel(const 
   off = (off + 7) & ~(size_t)7;
   uint64_t* full = reinterpret_cast<uint64_t*>(pm_smem + off);
   uint64_t* empty = full + R;
+  uint64_t* pub_full = empty + R;        // [NW]
+  uint64_t* pub_empty = pub_full + NW;   // [NW]
+  uint64_t* tab_bar = pub_empty + NW;    // the B-fragment table has landed
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < R; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], NW);
     }
+    for (int i = 0; i < NW; ++i) {
+      mbar_init(&pub_full[i], 1);
+      mbar_init(&pub_empty[i], 1);
+    }
+    mbar_init(tab_bar, 1);
     fence_mbar_init();
   }
   __syncthreads();
@@ -114,20 +200,25 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) preprocess_mma_kernel(const 
   const size_t image_bytes = (size_t)p.src_h * p.row_bytes;
 
   if (warp == NW) {
-    // =============================== copy warp: one lane streams the source octets =================================
+    // =============================== copy warp: one lane streams the table and the source octets =====================
     if (lane == 0) {
-      int seq = 0;
+      const uint32_t tab_bytes = (uint32_t)(p.n_tiles * 4 * 32 * sizeof(uint2));
+      mbar_arrive_expect_tx(tab_bar, tab_bytes);
+      bulk_load_1d(wx_s, p.wx_frag, tab_bytes, tab_bar);
+      int slot = 0;
+      uint32_t phase = 0;                 // parity of the ring pass `slot` belongs to
+      bool wrapped = false;
       int u = u_lo;
       while (u < u_hi) {
         const int img = u / p.n_msteps;
         const int pass_end = min(u_hi, (img + 1) * p.n_msteps);
         const uint8_t* image = p.src + (size_t)img * image_bytes;
-        int o_next = __ldg(&p.r0[u % p.n_msteps]) >> 3;
-        for (int uu = u; uu < pass_end; ++uu) {
-          const int o_end = min((__ldg(&p.r0[uu % p.n_msteps]) >> 3) + 2 * KV, n_oct_img);
-          for (int o = o_next; o < o_end; ++o, ++seq) {
-            const int slot = seq % R;
-            if (seq >= R) mbar_wait(&empty[slot], ((seq / R) & 1) ^ 1, 61);
+        int m = u - img * p.n_msteps;
+        int o_next = __ldg(&p.r0[m]) >> 3;
+        for (int uu = u; uu < pass_end; ++uu, ++m) {
+          const int o_end = min((__ldg(&p.r0[m]) >> 3) + 2 * KV, n_oct_img);
+          for (int o = o_next; o < o_end; ++o) {
+            if (wrapped) mbar_wait_backoff(&empty[slot], phase ^ 1u, 61);
             const uint32_t bytes = (uint32_t)(min(8, p.src_h - o * 8) * p.row_bytes);
 #ifdef SIA_PM_NO_COPY            // timing variant: no source traffic at all, the barriers still cycle
             mbar_arrive(&full[slot]);
@@ -135,6 +226,11 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) preprocess_mma_kernel(const 
             mbar_arrive_expect_tx(&full[slot], bytes);
             bulk_load_1d(ring + (size_t)slot * octet_bytes, image + (size_t)o * octet_bytes, bytes, &full[slot]);
 #endif
+            if (++slot == R) {
+              slot = 0;
+              phase ^= 1u;
+              wrapped = true;
+            }
           }
           o_next = max(o_next, o_end);
         }
@@ -145,21 +241,21 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) preprocess_mma_kernel(const 
   }
 
   // ================================== compute warps ================================================================
-  // tables -> shared memory (the copy warp is already fetching the first octets)
   {
     const int tid = threadIdx.x, nt = NW * 32;
-    for (int i = tid; i < p.n_msteps * KV * 32; i += nt) wy_s[i] = __ldg(&p.wy_frag[i]);
-    for (int i = tid; i < p.n_tiles * 4 * 32; i += nt) wx_s[i] = __ldg(&p.wx_frag[i]);
     for (int i = tid; i < p.n_msteps; i += nt) r0_s[i] = __ldg(&p.r0[i]);
     for (int i = tid; i <= p.n_groups; i += nt) tbeg_s[i] = __ldg(&p.tile_begin[i]);
     for (int i = tid; i < p.n_tiles; i += nt) mask_s[i] = __ldg(&p.wx_mask[i]);
     asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
+    mbar_wait(tab_bar, 0, 60);
   }
 
-  // column groups of this warp: [g_first, g_end) are its own, one halo group (first product only) before them
-  const int g_first = (p.n_groups * warp + NW - 1) / NW;
-  const int g_end = (p.n_groups * (warp + 1) + NW - 1) / NW;
-  const int g_start = max(g_first - 1, 0);
+  // Column groups of this warp for m-step number `step` of this CTA: [g_first, g_end) with boundaries
+  // floor((n_groups * w + rot) / NW), rot rotating with the step -- 19 groups over 8 warps is 3,3,3,2,2,2,2,2 for any
+  // fixed split, and the ring lets warps drift by an m-step, so rotating WHO gets the third group evens the load out.
+  // (The host guarantees n_groups >= NW: every warp owns at least one group.)
+  const bool publish = warp > 0;                   // my first group's fragments go to the left neighbour
+  const bool adopt = warp + 1 < NW;                // I finish the tiles that straddle my right boundary
   // the two row pairs this lane reads in every 16-row chunk: chunk rows rowA, rowA + 1 (K slots 0, 1) and rowB, rowB + 1
   const int row_a = p.q_stride * q + p.c_row[0], row_b = p.q_stride * q + p.c_row[2];
   const int oct_a = row_a >> 3, oct_b = row_b >> 3;                              // 0 or 1: which octet of the chunk
@@ -168,42 +264,57 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) preprocess_mma_kernel(const 
   const uint32_t next_row = (uint32_t)p.row_bytes;
   const uint32_t ring_u32 = smem_u32(ring);
   const int out_pitch_px = p.out_w + SIA_NHWC4_PAD;
-  const float mul0 = p.mul[0], mul1 = p.mul[1], mul2 = p.mul[2];
+  uint32_t* my_pub = pub_s + (size_t)warp * PM_PUB_WORDS + lane;
+  const uint32_t* right_pub = pub_s + (size_t)(warp + 1) * PM_PUB_WORDS + lane;
 
-  int seq_base = 0;       // sequence number of the first octet of the current pass
+  PmOut out;
+  out.mul0 = p.mul[0]; out.mul1 = p.mul[1]; out.mul2 = p.mul[2];
+  out.bias0 = p.bias[0]; out.bias1 = p.bias[1]; out.bias2 = p.bias[2];
+  out.has_bias = p.has_bias; out.out_w = p.out_w; out.q = q;
+
+  // ring bookkeeping without divisions: slot / parity of the next octet to wait for, to release, and of the window start
+  int w_slot = 0, r_slot = 0, base_slot = 0;
+  uint32_t w_phase = 0;
+  uint32_t step = 0;                                // m-steps done by this CTA: parity of the fragment hand-over
   int u = u_lo;
   while (u < u_hi) {
     const int img = u / p.n_msteps;
     const int pass_end = min(u_hi, (img + 1) * p.n_msteps);
-    const int o_start = r0_s[u % p.n_msteps] >> 3;
-    int o_waited = o_start, o_released = o_start, o_issued_end = o_start;
-    for (int uu = u; uu < pass_end; ++uu) {
-      const int m = uu % p.n_msteps;
+    int m = u - img * p.n_msteps;
+    const int o_start = r0_s[m] >> 3;
+    int o_waited = o_start, o_released = o_start, o_base = o_start;      // octet numbers matching w_slot / r_slot / base_slot
+    for (int uu = u; uu < pass_end; ++uu, ++m, ++step) {
+      const int rot = (int)((step * 3u) & (uint32_t)(NW - 1));
+      const int g_first = (p.n_groups * warp + rot) / NW, g_end = (p.n_groups * (warp + 1) + rot) / NW;
       const int o0 = r0_s[m] >> 3;
       const int o_win_end = min(o0 + 2 * KV, n_oct_img);
-      o_issued_end = max(o_issued_end, o_win_end);
       for (; o_waited < o_win_end; ++o_waited) {
-        const int s = seq_base + (o_waited - o_start);
-        mbar_wait(&full[s % R], (s / R) & 1, 62);
+        mbar_wait(&full[w_slot], w_phase, 62);
+        if (++w_slot == R) { w_slot = 0; w_phase ^= 1u; }
       }
+      base_slot += o0 - o_base;                     // (windows advance by less than a ring)
+      if (base_slot >= R) base_slot -= R;
+      o_base = o0;
 
-#ifdef SIA_PM_NO_COMPUTE          // timing variant: the compute warps only wait for and release the octets
-      if (false) {
-#else
-      if (g_end > g_first) {
-#endif
+#ifndef SIA_PM_NO_COMPUTE          // (timing variant without: the compute warps only wait for and release the octets)
+      {
         const int row0 = m * 16 + g, row1 = row0 + 8;
-        uint8_t* out_row0 = p.dst + ((size_t)img * p.out_h + row0) * out_pitch_px * 8;
-        uint8_t* out_row1 = out_row0 + (size_t)8 * out_pitch_px * 8;
-        const bool ok0 = row0 < p.out_h, ok1 = row1 < p.out_h;
+        out.row0 = p.dst + ((size_t)img * p.out_h + row0) * out_pitch_px * 8;
+        out.row1 = out.row0 + (size_t)8 * out_pitch_px * 8;
+        out.ok0 = row0 < p.out_h;
+        out.ok1 = row1 < p.out_h;
 
         // shared-memory addresses of this lane's two row pairs in each 16-row chunk of the window
         uint32_t pa[KV], pb[KV];
+        uint4 wy[KV];                               // A fragments of the vertical operator for this m-step
 #pragma unroll
         for (int kc = 0; kc < KV; ++kc) {
-          const int sa = seq_base + (o0 + 2 * kc + oct_a - o_start), sb = seq_base + (o0 + 2 * kc + oct_b - o_start);
-          pa[kc] = ring_u32 + (uint32_t)((sa % R) * octet_bytes) + off_a;
-          pb[kc] = ring_u32 + (uint32_t)((sb % R) * octet_bytes) + off_b;
+          int sa = base_slot + 2 * kc + oct_a, sb = base_slot + 2 * kc + oct_b;
+          if (sa >= R) sa -= R;
+          if (sb >= R) sb -= R;
+          pa[kc] = ring_u32 + (uint32_t)(sa * octet_bytes) + off_a;
+          pb[kc] = ring_u32 + (uint32_t)(sb * octet_bytes) + off_b;
+          wy[kc] = __ldg(&p.wy_frag[(m * KV + kc) * 32 + lane]);
         }
 
         uint32_t prev[3][2][4];                                    // A fragments of the previous group
@@ -214,7 +325,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) preprocess_mma_kernel(const 
 #pragma unroll
             for (int e = 0; e < 4; ++e) prev[c][x][e] = 0u;
 
-        for (int grp = g_start; grp < g_end; ++grp) {
+        for (int grp = g_first; grp < g_end; ++grp) {
           // ---------------- first product: V[16 rows x 96 bytes] of this group --------------------------------------
           float vacc[12][4];
 #pragma unroll
@@ -233,8 +344,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) preprocess_mma_kernel(const 
               asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wc[w]) : "r"(qb + 4 * w));
               asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wd[w]) : "r"(qb + next_row + 4 * w));
             }
-            const uint4 af4 = wy_s[(m * KV + kc) * 32 + lane];
-            const uint32_t af[4] = {af4.x, af4.y, af4.z, af4.w};
+            const uint32_t af[4] = {wy[kc].x, wy[kc].y, wy[kc].z, wy[kc].w};
 #pragma unroll
             for (int w = 0; w < 3; ++w) {
               const uint32_t t01 = __byte_perm(wa[w], wb[w], 0x5140), t23 = __byte_perm(wa[w], wb[w], 0x7362);
@@ -257,61 +367,25 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) preprocess_mma_kernel(const 
               cur[c][x][2] = pack_f16x2(vacc[tb][0], vacc[tb][1]);
               cur[c][x][3] = pack_f16x2(vacc[tb][2], vacc[tb][3]);
             }
+          const bool first_group = grp == g_first;
+          if (first_group && publish) {
+            // hand this group's fragments to the left neighbour (it finishes the tiles that straddle the boundary)
+            if (step > 0) mbar_wait(&pub_empty[warp], (step - 1) & 1u, 64);
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+              for (int x = 0; x < 2; ++x)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) my_pub[((c * 2 + x) * 4 + e) * 32] = cur[c][x][e];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&pub_full[warp]);
+          }
           // ---------------- second product + store for every output tile whose last group this is --------------------
-          if (grp >= g_first) {
-            const int t_end = tbeg_s[grp + 1];
-            for (int t = tbeg_s[grp]; t < t_end; ++t) {
-              float hacc[3][4];
-#pragma unroll
-              for (int c = 0; c < 3; ++c)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) hacc[c][e] = 0.f;
-              const uint32_t mask = mask_s[t];
-              const uint2* wxt = wx_s + (size_t)t * 4 * 32 + lane;
-#pragma unroll
-              for (int x = 0; x < 2; ++x) {
-                if ((mask >> x) & 1u) {
-                  const uint2 bf = wxt[x * 32];
-#pragma unroll
-                  for (int c = 0; c < 3; ++c) mma16816(hacc[c], prev[c][x], bf.x, bf.y);
-                }
-                if ((mask >> (2 + x)) & 1u) {
-                  const uint2 bf = wxt[(2 + x) * 32];
-#pragma unroll
-                  for (int c = 0; c < 3; ++c) mma16816(hacc[c], cur[c][x], bf.x, bf.y);
-                }
-              }
-              const int pc0 = t * 8 + 2 * q;
-              float b00 = 0.f, b01 = 0.f, b02 = 0.f, b10 = 0.f, b11 = 0.f, b12 = 0.f;
-              if (p.has_bias) {                                     // pad columns stay zero whatever the bias
-                if (pc0 >= 1 && pc0 <= p.out_w) { b00 = p.bias[0]; b01 = p.bias[1]; b02 = p.bias[2]; }
-                if (pc0 + 1 <= p.out_w) { b10 = p.bias[0]; b11 = p.bias[1]; b12 = p.bias[2]; }
-              }
-              if (ok0) {
-                uint4 v;
-                v.x = pack_bf16x2(fmaf(hacc[0][0], mul0, b00), fmaf(hacc[1][0], mul1, b01));
-                v.y = pack_bf16x2(fmaf(hacc[2][0], mul2, b02), 0.f);
-                v.z = pack_bf16x2(fmaf(hacc[0][1], mul0, b10), fmaf(hacc[1][1], mul1, b11));
-                v.w = pack_bf16x2(fmaf(hacc[2][1], mul2, b12), 0.f);
-#ifndef SIA_PM_NO_STORE
-                *reinterpret_cast<uint4*>(out_row0 + (size_t)pc0 * 8) = v;
-#else
-                if (v.x == 0x12345678u) *reinterpret_cast<uint4*>(out_row0 + (size_t)pc0 * 8) = v;
-#endif
-              }
-              if (ok1) {
-                uint4 v;
-                v.x = pack_bf16x2(fmaf(hacc[0][2], mul0, b00), fmaf(hacc[1][2], mul1, b01));
-                v.y = pack_bf16x2(fmaf(hacc[2][2], mul2, b02), 0.f);
-                v.z = pack_bf16x2(fmaf(hacc[0][3], mul0, b10), fmaf(hacc[1][3], mul1, b11));
-                v.w = pack_bf16x2(fmaf(hacc[2][3], mul2, b12), 0.f);
-#ifndef SIA_PM_NO_STORE
-                *reinterpret_cast<uint4*>(out_row1 + (size_t)pc0 * 8) = v;
-#else
-                if (v.x == 0x12345678u) *reinterpret_cast<uint4*>(out_row1 + (size_t)pc0 * 8) = v;
-#endif
-              }
-            }
+          const int t_end = tbeg_s[grp + 1];
+          for (int t = tbeg_s[grp]; t < t_end; ++t) {
+            const uint32_t mask = mask_s[t];
+            if (first_group && publish && (mask & 3u)) continue;          // straddles my left boundary: not mine
+            pm_tile(out, t, mask, wx_s + (size_t)t * 4 * 32 + lane, prev, cur);
           }
 #pragma unroll
           for (int c = 0; c < 3; ++c)
@@ -320,32 +394,50 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) preprocess_mma_kernel(const 
 #pragma unroll
               for (int e = 0; e < 4; ++e) prev[c][x][e] = cur[c][x][e];
         }
-      }
-
-      // ---------------- release the octets no later m-step of this pass reads ------------------------------------------
-      const int o_rel_end = (uu + 1 < pass_end) ? min(r0_s[(uu + 1) % p.n_msteps] >> 3, n_oct_img) : o_issued_end;
-      for (; o_waited < o_rel_end; ++o_waited) {            // (only if windows ever leave a gap)
-        const int s = seq_base + (o_waited - o_start);
-        mbar_wait(&full[s % R], (s / R) & 1, 63);
-      }
-      __syncwarp();
-      if (lane == 0) {
-        for (int o = o_released; o < o_rel_end; ++o) {
-          const int s = seq_base + (o - o_start);
-          mbar_arrive(&empty[s % R]);
+        if (adopt) {
+          // tiles whose last group is the right neighbour's first one and that also read my last group
+          mbar_wait(&pub_full[warp + 1], step & 1u, 65);
+          uint32_t nxt[3][2][4];
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int x = 0; x < 2; ++x)
+#pragma unroll
+              for (int e = 0; e < 4; ++e) nxt[c][x][e] = right_pub[((c * 2 + x) * 4 + e) * 32];
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&pub_empty[warp + 1]);
+          const int t_end = tbeg_s[g_end + 1];
+          for (int t = tbeg_s[g_end]; t < t_end; ++t) {
+            const uint32_t mask = mask_s[t];
+            if (mask & 3u) pm_tile(out, t, mask, wx_s + (size_t)t * 4 * 32 + lane, prev, nxt);
+          }
         }
       }
-      o_released = max(o_released, o_rel_end);
+#endif
+
+      // ---------------- release the octets no later m-step of this pass reads ------------------------------------------
+      const int o_rel_end = (uu + 1 < pass_end) ? min(r0_s[m + 1] >> 3, n_oct_img) : o_win_end;
+      for (; o_waited < o_rel_end; ++o_waited) {            // (only if windows ever leave a gap)
+        mbar_wait(&full[w_slot], w_phase, 63);
+        if (++w_slot == R) { w_slot = 0; w_phase ^= 1u; }
+      }
+      __syncwarp();
+      for (; o_released < o_rel_end; ++o_released) {
+        if (lane == 0) mbar_arrive(&empty[r_slot]);
+        if (++r_slot == R) r_slot = 0;
+      }
     }
-    seq_base += o_issued_end - o_start;
+    // the next pass starts at the slot after the last octet of this one
+    base_slot = w_slot;
     u = pass_end;
   }
 }
 
 template <int KV, int NW>
-static int launch_pre_mma(const PreMmaParams& p, size_t smem, cudaStream_t st) {
+static int launch_pre_mma(const PreMmaParams& p, size_t smem_without_pub, cudaStream_t st) {
   auto kern = preprocess_mma_kernel<KV, NW>;
   static SmemSlots configured = {};
+  const size_t smem = smem_without_pub + (size_t)NW * PM_PUB_WORDS * 4 + (size_t)(2 * NW + 1) * 8;
   if (int rc = ensure_dynamic_smem(kern, (int)smem, &configured)) return rc;
   const long long total = (long long)p.batch * p.n_msteps;
   const int grid = (int)(total < sm_count() ? total : sm_count());
@@ -371,10 +463,12 @@ extern "C" int sia_preprocess_mma_u8hwc(const uint8_t* src, int batch, int src_h
   using namespace sia;
   SIA_REQUIRE(src && wy_frag && r0 && wx_frag && wx_mask && tile_begin && c_row4_host && mul3_host && bias3_host && dst);
   SIA_REQUIRE(batch >= 1 && src_h >= 2 && src_w >= 8 && out_h >= 1 && out_w >= 8);
-  SIA_REQUIRE(aligned(src, 16) && aligned(dst, 16) && aligned(wy_frag, 16) && aligned(wx_frag, 8));
+  SIA_REQUIRE(aligned(src, 16) && aligned(dst, 16) && aligned(wy_frag, 16) && aligned(wx_frag, 16));
   if (src_w % 8 != 0 || src_h % 2 != 0 || out_w % 8 != 0) return SIA_E_UNSUPPORTED;
   if (n_msteps != (out_h + 15) / 16 || n_groups != (src_w + 31) / 32 || n_tiles != (out_w + SIA_NHWC4_PAD) / 8)
     return SIA_E_INVALID;
+  const int warps = n_groups >= 8 ? g_pm_warps : 4;
+  if (n_groups < warps) return SIA_E_UNSUPPORTED;            // every compute warp owns at least one column group
   if (int rc = ensure_watchdog()) return rc;
   PreMmaParams p;
   p.src = src;
@@ -406,19 +500,20 @@ extern "C" int sia_preprocess_mma_u8hwc(const uint8_t* src, int batch, int src_h
       const int r = q_stride * q + c_row4_host[c];
       if (r < 0 || r > 14 || c_row4_host[c + 1] != c_row4_host[c] + 1 || (r & 7) == 7) return SIA_E_INVALID;
     }
-  const size_t tables = (size_t)n_msteps * kv * 32 * 16 + (size_t)n_tiles * 4 * 32 * 8 + (size_t)n_msteps * 4 +
-                        (size_t)(n_groups + 1) * 4 + (size_t)n_tiles * 4 + 8;
-  // the ring: the 2*kv octets of a window + as many octets of prefetch as fit (at least 2)
+  const size_t tables = (size_t)n_tiles * 4 * 32 * 8 + (size_t)n_msteps * 4 + (size_t)(n_groups + 1) * 4 +
+                        (size_t)n_tiles * 4 + 8;
+  const size_t pub = (size_t)warps * PM_PUB_WORDS * 4 + (size_t)(2 * warps + 1) * 8;
+  // the ring: the 2*kv octets of a window + as many octets of prefetch as fit (at least 2).  (The last group's loads may
+  // run past the last slot's end, into the tables behind the ring: read-only garbage that meets zero weights.)
   const size_t octet = (size_t)8 * p.row_bytes;
-  const size_t budget = 227 * 1024 - tables - 64;     // (the last group's loads may run past the last slot's end, into
-                                                       // the tables behind the ring: read-only garbage, zero weights)
-  int ring = (int)(budget / octet);
+  const size_t budget = 227 * 1024 - tables - pub - 64;
+  int ring = (int)(budget / (octet + 16));
   if (ring > 24) ring = 24;
   if (ring < 2 * kv + 2) return SIA_E_UNSUPPORTED;
   p.ring_octets = ring;
   const size_t smem = (size_t)ring * octet + tables + (size_t)2 * ring * 8;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (g_pm_warps == 4) {
+  if (warps == 4) {
     if (kv == 3) return launch_pre_mma<3, 4>(p, smem, st);
     if (kv == 2) return launch_pre_mma<2, 4>(p, smem, st);
   } else {
