@@ -332,7 +332,7 @@ def tensor_peak(peaks, clocks):
 def stage_breakdown(eng, batch, peaks, tensor_tflops, iters=12):
     """Average duration of every kernel of the step, measured INSIDE whole steps: the kernels are launched
     one after the other on the engine stream (no graph) with a CUDA event between consecutive launches,
-    input slots rotating as in the timed region.  Roofline fractions use the measured peaks: HBM copy for the
+    input slots rotating as in the timed region, all iterations queued ahead of the GPU.  Roofline fractions use the measured peaks: HBM copy for the
     preprocess kernel and for fc1 (a 103 MB weight stream per launch), ``tensor_tflops`` for the conv kernels."""
     from skin_image_analysis_b200 import ops
     plan, ws = eng.plan, eng.plan.workspace(batch)
@@ -357,15 +357,18 @@ def stage_breakdown(eng, batch, peaks, tensor_tflops, iters=12):
         plan.tail(ws["partial"], logp=ws["logp"], pred=ws["pred"])
         ev[k].record(eng.stream)
 
+    # All iterations are queued back to back and read after ONE synchronize: with a synchronize per iteration the GPU
+    # idles before every first launch, and the first stage (preprocess) absorbs the host's launch latency (~17 us).
     total = dict.fromkeys(names, 0.0)
+    warm = 3
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)] for _ in range(iters + warm)]
     with torch.cuda.stream(eng.stream):
-        for it in range(iters + 3):
-            ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
-            launch_all(it % eng.n_slots, ev)
-            eng.stream.synchronize()
-            if it >= 3:
-                for j, nm in enumerate(names):
-                    total[nm] += ev[j].elapsed_time(ev[j + 1]) * 1e-3 / iters
+        for it in range(iters + warm):
+            launch_all(it % eng.n_slots, evs[it])
+        eng.stream.synchronize()
+    for it in range(warm, iters + warm):
+        for j, nm in enumerate(names):
+            total[nm] += evs[it][j].elapsed_time(evs[it][j + 1]) * 1e-3 / iters
     out = {}
     t = total["preprocess"]
     gbs = pre_bytes_per_image(size) * batch / t / 1e9

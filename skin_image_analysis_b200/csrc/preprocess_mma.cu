@@ -80,7 +80,7 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t site) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(64);
+    __nanosleep(256);
     if (++spins > (SIA_WATCHDOG_SPINS >> 2)) {
       if (g_watchdog_word != nullptr) {
         *g_watchdog_word = 0x80000000u | (site << 16) | (blockIdx.x & 0xffffu);
@@ -272,6 +272,12 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) preprocess_mma_kernel(const 
   out.bias0 = p.bias[0]; out.bias1 = p.bias[1]; out.bias2 = p.bias[2];
   out.has_bias = p.has_bias; out.out_w = p.out_w; out.q = q;
 
+  uint4 wy_next[KV];                                // A fragments of the vertical operator, fetched one m-step ahead
+  {
+    const int m0 = u_lo % p.n_msteps;
+#pragma unroll
+    for (int kc = 0; kc < KV; ++kc) wy_next[kc] = __ldg(&p.wy_frag[(m0 * KV + kc) * 32 + lane]);
+  }
   // ring bookkeeping without divisions: slot / parity of the next octet to wait for, to release, and of the window start
   int w_slot = 0, r_slot = 0, base_slot = 0;
   uint32_t w_phase = 0;
@@ -284,7 +290,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) preprocess_mma_kernel(const 
     const int o_start = r0_s[m] >> 3;
     int o_waited = o_start, o_released = o_start, o_base = o_start;      // octet numbers matching w_slot / r_slot / base_slot
     for (int uu = u; uu < pass_end; ++uu, ++m, ++step) {
-      const int rot = (int)((step * 3u) & (uint32_t)(NW - 1));
+      const int rot = (int)((step * 5u) % (uint32_t)NW);          // 5 is coprime with 4, 8, 12, 16
       const int g_first = (p.n_groups * warp + rot) / NW, g_end = (p.n_groups * (warp + 1) + rot) / NW;
       const int o0 = r0_s[m] >> 3;
       const int o_win_end = min(o0 + 2 * KV, n_oct_img);
@@ -307,6 +313,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) preprocess_mma_kernel(const 
         // shared-memory addresses of this lane's two row pairs in each 16-row chunk of the window
         uint32_t pa[KV], pb[KV];
         uint4 wy[KV];                               // A fragments of the vertical operator for this m-step
+        const int m_next = (m + 1 < p.n_msteps) ? m + 1 : 0;
 #pragma unroll
         for (int kc = 0; kc < KV; ++kc) {
           int sa = base_slot + 2 * kc + oct_a, sb = base_slot + 2 * kc + oct_b;
@@ -314,7 +321,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) preprocess_mma_kernel(const 
           if (sb >= R) sb -= R;
           pa[kc] = ring_u32 + (uint32_t)(sa * octet_bytes) + off_a;
           pb[kc] = ring_u32 + (uint32_t)(sb * octet_bytes) + off_b;
-          wy[kc] = __ldg(&p.wy_frag[(m * KV + kc) * 32 + lane]);
+          wy[kc] = wy_next[kc];
+          wy_next[kc] = __ldg(&p.wy_frag[(m_next * KV + kc) * 32 + lane]);     // (L2 latency hidden behind this m-step)
         }
 
         uint32_t prev[3][2][4];                                    // A fragments of the previous group
@@ -445,12 +453,12 @@ static int launch_pre_mma(const PreMmaParams& p, size_t smem_without_pub, cudaSt
   return launch_status();
 }
 
-static int g_pm_warps = 8;      // compute warps per CTA (sia_debug_set_mma_warps: 4 or 8; A/B timing only)
+static int g_pm_warps = 8;      // compute warps per CTA (sia_debug_set_mma_warps: 4, 8 or 12; A/B timing only)
 
 }  // namespace sia
 
 extern "C" int sia_debug_set_mma_warps(int warps) {
-  if (warps != 4 && warps != 8) return SIA_E_INVALID;
+  if (warps != 4 && warps != 8 && warps != 12) return SIA_E_INVALID;
   sia::g_pm_warps = warps;
   return 0;
 }
@@ -467,7 +475,7 @@ extern "C" int sia_preprocess_mma_u8hwc(const uint8_t* src, int batch, int src_h
   if (src_w % 8 != 0 || src_h % 2 != 0 || out_w % 8 != 0) return SIA_E_UNSUPPORTED;
   if (n_msteps != (out_h + 15) / 16 || n_groups != (src_w + 31) / 32 || n_tiles != (out_w + SIA_NHWC4_PAD) / 8)
     return SIA_E_INVALID;
-  const int warps = n_groups >= 8 ? g_pm_warps : 4;
+  const int warps = n_groups >= g_pm_warps ? g_pm_warps : 4;
   if (n_groups < warps) return SIA_E_UNSUPPORTED;            // every compute warp owns at least one column group
   if (int rc = ensure_watchdog()) return rc;
   PreMmaParams p;
@@ -516,6 +524,9 @@ extern "C" int sia_preprocess_mma_u8hwc(const uint8_t* src, int batch, int src_h
   if (warps == 4) {
     if (kv == 3) return launch_pre_mma<3, 4>(p, smem, st);
     if (kv == 2) return launch_pre_mma<2, 4>(p, smem, st);
+  } else if (warps == 12) {
+    if (kv == 3) return launch_pre_mma<3, 12>(p, smem, st);
+    if (kv == 2) return launch_pre_mma<2, 12>(p, smem, st);
   } else {
     if (kv == 3) return launch_pre_mma<3, 8>(p, smem, st);
     if (kv == 2) return launch_pre_mma<2, 8>(p, smem, st);
