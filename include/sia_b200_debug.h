@@ -3,7 +3,7 @@
  * Two groups:
  *   (1) switches exported by the product library libsia_b200.so itself, because they toggle instrumentation or
  *       A/B paths inside the product kernels: sia_debug_tv_force_generic, sia_debug_set_trace, sia_debug_set_stats,
- *       sia_debug_set_mma_warps;
+ *       sia_debug_set_mma_warps, sia_debug_set_programmatic_launch;
  *   (2) hardware probes (tcgen05 / TMA / TMEM / ALU micro-benchmarks used by tests/test_umma_probe.py to pin the
  *       descriptor conventions the kernels rely on), built into a SEPARATE library libsia_b200_debug.so
  *       (csrc/libsia_debug_unity.cu): the product library carries none of them.
@@ -34,6 +34,11 @@ int sia_debug_set_trace(long long* device_buffer_or_null);
  * producer wait-for-stage, MMA wait-for-accumulator, MMA wait-for-operands, MMA loop, epilogue
  * wait-for-accumulator, epilogue loop, tiles); NULL switches the instrumentation off (default). */
 int sia_debug_set_stats(unsigned long long* device_buffer_or_null);
+
+/* Debug / A-B (timing): programmatic dependent launch of the hot-path kernels (default on; SIA_PDL=0 in the
+ * environment switches it off as well).  With it, every kernel of the step lets the next one start its prologue
+ * (barrier init, tensor-memory allocation, resident weights) under its own tail wave. */
+int sia_debug_set_programmatic_launch(int on);
 
 /* Debug / A-B (timing): compute warps per CTA of sia_preprocess_mma_u8hwc: 4, 8 or 12 (default 8). */
 int sia_debug_set_mma_warps(int warps);

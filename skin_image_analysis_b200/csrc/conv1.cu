@@ -136,6 +136,10 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
   tc_fence_after_sync();
   const uint32_t tmem_base = bcast0(*tmem_slot);
   const float* smem_bias = reinterpret_cast<const float*>(smem_biasop);
+  // Programmatic dependent launch: everything above (and the resident weights below) overlaps the previous kernel's
+  // tail; nothing that kernel wrote is read, and nothing it reads is written, before pdl_wait().
+  pdl_launch_dependents();
+  if (!(warp == 0 && lane == 0)) pdl_wait();
 
 #ifdef SIA_C1_RAW_ISSUE
   // timing experiment: only the MMA warp runs, issuing every tile's UMMAs back to back without any barrier traffic
@@ -191,6 +195,7 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
     if (lane == 0) {
       mbar_arrive_expect_tx(wload_bar, C1_B_BYTES);
       for (int off = 0; off < C1_B_BYTES; off += 16384) bulk_load_1d(smem_b + off, w_packed + off, 16384, wload_bar);
+      pdl_wait();                       // the input tiles below are the previous kernel's output
       int stage = 0;
       uint32_t phase = 0;
       TileWalker1 t(blockIdx.x, gridDim.x, tiles_x, tiles_y);
@@ -417,7 +422,7 @@ extern "C" int sia_conv7x7_c3_relu_pool2_strided(const void* in_nhwc4, int batch
   static SmemSlots configured = {};
   if (int rc2 = ensure_dynamic_smem(conv1_kernel, smem, &configured)) return rc2;
   const int grid = total < sm_count() ? total : sm_count();
-  conv1_kernel<<<grid, C1_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
+  return launch_kernel(conv1_kernel, dim3(grid), dim3(C1_THREADS), smem, static_cast<cudaStream_t>(stream), true,
       tmap, static_cast<const uint8_t*>(w_packed), bias, static_cast<__nv_bfloat16*>(out_nhwc) + c_offset, h, w, tiles_y,
       tiles_x, total, c_stride);
   return launch_status();

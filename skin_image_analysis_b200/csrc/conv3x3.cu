@@ -154,6 +154,10 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = bcast0(*tmem_slot);
+  // programmatic dependent launch (see sia_ptx.cuh): the prologue above and the resident weights overlap the previous
+  // kernel's tail; the producer lane waits after it has issued the weight copies
+  pdl_launch_dependents();
+  if (!(warp == 0 && lane == 0)) pdl_wait();
 
   if (warp == 0) {
     // ================================ TMA producer ==========================================
@@ -165,6 +169,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
         const int n = C::B_BYTES - off < PIECE ? C::B_BYTES - off : PIECE;
         bulk_load_1d(smem_b + off, w_packed + off, n, wload_bar);
       }
+      pdl_wait();                       // the input tiles below are the previous kernel's output
       int stage = 0;
       uint32_t phase = 0;
       TileWalker t(blockIdx.x, gridDim.x, tiles_x, tiles_y);
@@ -400,6 +405,8 @@ conv3x3_stream_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = bcast0(*tmem_slot);
+  pdl_launch_dependents();          // programmatic dependent launch: the prologue above overlaps the previous kernel
+  pdl_wait();
   const int tiles_per_img = tiles_x * tiles_y;
 
   if (warp == 0) {
@@ -618,12 +625,17 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* 
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = bcast0(*tmem_slot);
+  // programmatic dependent launch (see sia_ptx.cuh): the prologue above and the resident weights overlap the previous
+  // kernel's tail; the producer lane waits after it has issued the weight copies
+  pdl_launch_dependents();
+  if (!(warp == 0 && lane == 0)) pdl_wait();
 
   if (warp == 0) {
     // ================================ TMA producer ==========================================
     if (lane == 0) {
       mbar_arrive_expect_tx(wload_bar, CP_B_BYTES);
       for (int off = 0; off < CP_B_BYTES; off += 16384) bulk_load_1d(smem_b + off, w_packed + off, 16384, wload_bar);
+      pdl_wait();                       // the input tiles below are the previous kernel's output
       int stage = 0;
       uint32_t phase = 0;
       TileWalker t(blockIdx.x, gridDim.x, tiles_x, tiles_y);
@@ -771,7 +783,7 @@ static int launch_conv3x3_pair(const void* in, int batch, int h, int w, const vo
   static SmemSlots configured = {};
   if (int rc2 = ensure_dynamic_smem(conv3x3_pair_kernel, smem, &configured)) return rc2;
   const int grid = total < sm_count() ? total : sm_count();
-  conv3x3_pair_kernel<<<grid, CV_THREADS, smem, st>>>(tmap, static_cast<const uint8_t*>(w_packed), bias,
+  return launch_kernel(conv3x3_pair_kernel, dim3(grid), dim3(CV_THREADS), smem, st, true, tmap, static_cast<const uint8_t*>(w_packed), bias,
                                                       static_cast<__nv_bfloat16*>(out), h, w, tiles_y, tiles_x, total);
   return launch_status();
 }
@@ -822,7 +834,7 @@ static int launch_conv3x3(const void* in, int batch, int h, int w, const void* w
   static SmemSlots configured = {};
   if (int rc2 = ensure_dynamic_smem(kern, smem, &configured)) return rc2;
   const int grid = total < sm_count() ? total : sm_count();
-  kern<<<grid, CV_THREADS, smem, st>>>(tmap, static_cast<const uint8_t*>(w_packed), bias,
+  return launch_kernel(kern, dim3(grid), dim3(CV_THREADS), smem, st, true, tmap, static_cast<const uint8_t*>(w_packed), bias,
                                        static_cast<__nv_bfloat16*>(out), h, w, tiles_y, tiles_x, total);
   return launch_status();
 }
@@ -841,7 +853,7 @@ static int launch_conv3x3_stream_t(const CUtensorMap& tmap, int nchunk, int batc
   static SmemSlots configured = {};
   if (int rc2 = ensure_dynamic_smem(kern, smem, &configured)) return rc2;
   const int grid = passes < sm_count() ? passes : sm_count();
-  kern<<<grid, CV_THREADS, smem, st>>>(tmap, static_cast<const uint8_t*>(w_packed), bias,
+  return launch_kernel(kern, dim3(grid), dim3(CV_THREADS), smem, st, true, tmap, static_cast<const uint8_t*>(w_packed), bias,
                                        static_cast<__nv_bfloat16*>(out), h, w, tiles_y, tiles_x, total, nchunk);
   return launch_status();
 }

@@ -1,4 +1,6 @@
 // Library-wide state and the small informational entry points of the C ABI.
+#include <stdlib.h>
+
 #include "sia_host.cuh"
 #include "sia_ptx.cuh"
 #include "../../include/sia_b200_debug.h"
@@ -48,9 +50,25 @@ __global__ void pad_nhwc_kernel(const uint4* __restrict__ in, uint4* __restrict_
   }
 }
 
+static int g_pdl = -1;      // -1: not decided yet (reads SIA_PDL on first use)
+
+bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* env = getenv("SIA_PDL");
+    g_pdl = (env != nullptr && env[0] == '0') ? 0 : 1;
+  }
+  return g_pdl != 0;
+}
+void set_pdl_enabled(bool on) { g_pdl = on ? 1 : 0; }
+
 }  // namespace sia
 
 #ifndef SIA_DEBUG_LIB
+extern "C" int sia_debug_set_programmatic_launch(int on) {
+  sia::set_pdl_enabled(on != 0);
+  return 0;
+}
+
 extern "C" int sia_debug_set_trace(long long* device_buffer_or_null) {
 #ifndef SIA_INSTRUMENT
   if (device_buffer_or_null != nullptr) return SIA_E_UNSUPPORTED;   // needs a -DSIA_INSTRUMENT build

@@ -55,6 +55,8 @@ linear_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = bcast0(*tmem_slot);
+  pdl_launch_dependents();          // programmatic dependent launch: the prologue above overlaps the previous kernel
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -137,6 +139,11 @@ head_tail_kernel(const float* __restrict__ partial, int splits, int M, int n1, i
   __shared__ __align__(16) float h2p[TAIL_KPARTS][TAIL_IMGS][TAIL_MAX_N2];   // partial sums of fc2 over the K parts
   __shared__ float z[TAIL_IMGS][2];
   const int m0 = blockIdx.x * TAIL_IMGS;
+  // Programmatic dependent launch: this kernel may be resident before the split-K GEMM has finished; its partial sums
+  // (and the labels / group ids another stream operation wrote) are read with ld.global.cg, i.e. from L2, never
+  // through an L1 line left over from the previous batch.
+  pdl_launch_dependents();
+  pdl_wait();
 
   // h1 = relu(b1 + sum over splits, in split order): the loads of one element are independent
   for (int i = threadIdx.x; i < TAIL_IMGS * n1; i += blockDim.x) {
@@ -151,16 +158,16 @@ head_tail_kernel(const float* __restrict__ partial, int splits, int M, int n1, i
       for (; sp + 16 <= splits; sp += 16) {
         float v[16];
 #pragma unroll
-        for (int u = 0; u < 16; ++u) v[u] = __ldg(src + (size_t)(sp + u) * step);
+        for (int u = 0; u < 16; ++u) v[u] = __ldcg(src + (size_t)(sp + u) * step);
 #pragma unroll
         for (int u = 0; u < 16; ++u) s += v[u];
       }
       for (; sp + 4 <= splits; sp += 4) {
-        const float a = __ldg(src + (size_t)sp * step), b = __ldg(src + (size_t)(sp + 1) * step);
-        const float c = __ldg(src + (size_t)(sp + 2) * step), d = __ldg(src + (size_t)(sp + 3) * step);
+        const float a = __ldcg(src + (size_t)sp * step), b = __ldcg(src + (size_t)(sp + 1) * step);
+        const float c = __ldcg(src + (size_t)(sp + 2) * step), d = __ldcg(src + (size_t)(sp + 3) * step);
         s = (((s + a) + b) + c) + d;
       }
-      for (; sp < splits; ++sp) s += __ldg(src + (size_t)sp * step);
+      for (; sp < splits; ++sp) s += __ldcg(src + (size_t)sp * step);
       s = fmaxf(s + b1[k], 0.f);
     }
     h1[k * TAIL_IMGS + img] = s;
@@ -274,9 +281,9 @@ head_tail_kernel(const float* __restrict__ partial, int splits, int M, int n1, i
     const int pr = (z1 > z0) ? 1 : 0;   // torch.max: first maximal index on ties
     pred[m] = (uint8_t)pr;
     if (counts != nullptr) {
-      const int cell = ((label[m] != 0) ? 2 : 0) | pr;
+      const int cell = ((__ldcg(label + m) != 0) ? 2 : 0) | pr;
       for (int a = 0; a < n_attr; ++a) {
-        const int g = groups[(size_t)a * groups_stride + m];
+        const int g = __ldcg(groups + (size_t)a * groups_stride + m);
         if (g < n_groups) atomicAdd(&counts[(a * n_groups + g) * 4 + cell], 1ull);
       }
     }
@@ -357,7 +364,7 @@ extern "C" int sia_linear_splitk(const void* a_bf16, const void* w_bf16, int m, 
   static SmemSlots configured = {};
   if (int rc2 = ensure_dynamic_smem(linear_splitk_kernel, smem, &configured)) return rc2;
   dim3 grid((m + LN_BM - 1) / LN_BM, n / LN_BN, splits);
-  linear_splitk_kernel<<<grid, LN_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(ta, tw, partial, m, n,
+  return launch_kernel(linear_splitk_kernel, grid, dim3(LN_THREADS), smem, static_cast<cudaStream_t>(stream), true, ta, tw, partial, m, n,
                                                                                      k / LN_BK, splits);
   return launch_status();
 }
@@ -372,7 +379,7 @@ extern "C" int sia_head_tail(const float* partial, int splits, int m, int n1, in
   if (counts != nullptr) {
     SIA_REQUIRE(label && groups && n_attr >= 1 && n_groups >= 1 && groups_stride >= m);
   }
-  head_tail_kernel<<<(m + TAIL_IMGS - 1) / TAIL_IMGS, TAIL_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+  return launch_kernel(head_tail_kernel, dim3((m + TAIL_IMGS - 1) / TAIL_IMGS), dim3(TAIL_THREADS), 0, static_cast<cudaStream_t>(stream), true,
       partial, splits, m, n1, n2, b1, w2t, b2, w3, b3, logp, pred, label, groups, groups_stride, n_attr, n_groups,
       reinterpret_cast<unsigned long long*>(counts));
   return launch_status();

@@ -178,6 +178,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) preprocess_mma_kernel(const 
   uint64_t* pub_empty = pub_full + NW;   // [NW]
   uint64_t* tab_bar = pub_empty + NW;    // the B-fragment table has landed
 
+  pdl_launch_dependents();          // the next kernel (conv1) may start its prologue under this kernel's tail
   if (threadIdx.x == 0) {
     for (int i = 0; i < R; ++i) {
       mbar_init(&full[i], 1);
@@ -191,6 +192,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) preprocess_mma_kernel(const 
     fence_mbar_init();
   }
   __syncthreads();
+  pdl_wait();                       // (no-op unless launched as a programmatic dependent: the output buffer is shared)
 
   // ---- this CTA's contiguous range of m-steps ------------------------------------------------------------------------
   const long long total = (long long)p.batch * p.n_msteps;
@@ -449,8 +451,7 @@ static int launch_pre_mma(const PreMmaParams& p, size_t smem_without_pub, cudaSt
   if (int rc = ensure_dynamic_smem(kern, (int)smem, &configured)) return rc;
   const long long total = (long long)p.batch * p.n_msteps;
   const int grid = (int)(total < sm_count() ? total : sm_count());
-  kern<<<grid, (NW + 1) * 32, smem, st>>>(p);
-  return launch_status();
+  return launch_kernel(kern, dim3(grid), dim3((NW + 1) * 32), smem, st, true, p);
 }
 
 static int g_pm_warps = 8;      // compute warps per CTA (sia_debug_set_mma_warps: 4, 8 or 12; A/B timing only)

@@ -65,6 +65,31 @@ inline int ensure_dynamic_smem(Kernel kern, int bytes, SmemSlots* configured) {
   return 0;
 }
 
+// Whether the hot-path kernels are launched with programmatic dependent launch (default on; SIA_PDL=0 in the
+// environment or sia_debug_set_programmatic_launch(0) switches it off for A/B timing).
+bool pdl_enabled();
+void set_pdl_enabled(bool on);
+
+// Launch with (pdl = true) or without the programmatic-stream-serialization attribute.  A kernel launched with it MUST
+// execute pdl_wait() before it reads anything an earlier kernel wrote or writes anything an earlier kernel reads.
+template <typename... KArgs, typename... Args>
+inline int launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                         Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+  if (e != cudaSuccess) return (int)e;
+  return launch_status();
+}
+
 // rank <= 5.  dims / box in elements (innermost first); strides in BYTES for dims 1..rank-1.
 int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle);

@@ -124,6 +124,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32
   }
 }
 
+// ---------------------------------- programmatic dependent launch ---------------------------
+// A kernel launched with the programmatic-stream-serialization attribute may start while its predecessor in the
+// stream is still running: everything before pdl_wait() (barrier init, TMEM allocation, tensor-map prefetch, loads of
+// weights that no kernel writes) overlaps the predecessor's tail; pdl_wait() returns once the predecessor grid has
+// completed and its memory is visible.  pdl_launch_dependents() lets the NEXT kernel's CTAs be scheduled as soon as
+// every CTA of this grid has executed it (or exited).  Both are no-ops for a normally launched kernel.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------- fences ---------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async_smem() {
   // generic-proxy writes to shared memory -> visible to the async proxy (TMA / UMMA operand reads)
