@@ -475,9 +475,13 @@ def run_ours(args):
         eng.step_resident(slot)
 
     def barrier():
+        # Local GPU work first, THEN the collective: an NCCL kernel that spin-waits for a slower peer must not share
+        # the GPU with seconds of queued evaluation kernels (observed at N >= 2 with a 2 s region: a conv1 CTA made no
+        # progress while the barrier kernel of an early rank was resident, until its mbarrier watchdog fired).
+        torch.cuda.synchronize()
         if world > 1:
             torch.distributed.barrier()
-        torch.cuda.synchronize()
+            torch.cuda.synchronize()
 
     # ------------------------------------ value: inputs resident in HBM ------------------------------
     for s in range(warmup):
@@ -648,8 +652,18 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
-    else:
+        return
+    try:
         run_ours(args)
+    except Exception:
+        try:        # a kernel watchdog (mbarrier wait timed out -> trap) leaves its site in pinned host memory
+            from skin_image_analysis_b200 import _lib
+            wd = _lib.load().sia_watchdog_status(0)
+            print(f"[bench] sia watchdog word 0x{wd:08x} (site {(wd >> 16) & 0x7fff}, block {wd & 0xffff})",
+                  file=sys.stderr, flush=True)
+        except Exception:
+            pass
+        raise
 
 
 if __name__ == "__main__":

@@ -6,6 +6,7 @@ launches on the current torch stream.  PyTorch is used for allocation and stream
 from __future__ import annotations
 
 import ctypes
+import os
 from functools import lru_cache
 
 import numpy as np
@@ -155,6 +156,8 @@ def preprocess_u8hwc(src: torch.Tensor, size, layout: int = LAYOUT_NCHW_F32, mea
             raise ValueError(f"out must have shape {shape}")
     osc = (ctypes.c_float * 3)(*[1.0 / float(s) for s in std])
     obi = (ctypes.c_float * 3)(*[-float(m) / float(s) for m, s in zip(mean, std)])
+    if impl == "auto" and os.environ.get("SIA_PREPROCESS_IMPL"):      # A/B switch for whole-pipeline timing runs
+        impl = os.environ["SIA_PREPROCESS_IMPL"]
     if impl not in ("auto", "cuda_core", "tensor_core", "tensor_core2", "mma"):
         raise ValueError("impl must be 'auto', 'mma', 'cuda_core', 'tensor_core' or 'tensor_core2'")
     if impl == "mma" or (impl == "auto" and fixed_point and layout == LAYOUT_NHWC4_BF16):
