@@ -26,7 +26,7 @@ def main():
     # the ToneClassifier transform variant on the same decode buffers (one launch)
     from skin_image_analysis_b200 import ops
     ops.preprocess_tv_u8hwc(eng.u8[0], (OUT, OUT), ops.LAYOUT_NHWC4_BF16, out=eng.x4)
-    # the opt-in two-product tensor-core preprocess, one launch
+    # the round-1 default, the two-product tcgen05 preprocess, one launch for comparison
     ops.preprocess_u8hwc(eng.u8[0], (OUT, OUT), ops.LAYOUT_NHWC4_BF16, out=eng.x4, impl="tensor_core2")
     torch.cuda.synchronize()
     print("counted", int(eng.read_counts()[0].sum()))
