@@ -40,7 +40,7 @@ int sia_debug_set_stats(unsigned long long* device_buffer_or_null);
  * (barrier init, tensor-memory allocation, resident weights) under its own tail wave. */
 int sia_debug_set_programmatic_launch(int on);
 
-/* Debug / A-B (timing): compute warps per CTA of sia_preprocess_mma_u8hwc: 4, 8 or 12 (default 8). */
+/* Debug / A-B (timing): compute warps per CTA of sia_preprocess_mma_u8hwc: 4 or 8 (default 8). */
 int sia_debug_set_mma_warps(int warps);
 
 /* ---- (2) exported by libsia_b200_debug.so ------------------------------------------------------------ */

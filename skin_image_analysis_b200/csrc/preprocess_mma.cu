@@ -48,6 +48,11 @@
 namespace sia {
 
 constexpr int PM_GROUP_BYTES = 96;               // 32 pixels
+#ifdef SIA_PM_NO_V                               // timing variant: no first product (the fragments are zeros)
+#define PM_KV_RUN(kv) 0
+#else
+#define PM_KV_RUN(kv) (kv)
+#endif
 constexpr int PM_PUB_WORDS = 24 * 32;            // one published set of A fragments: 24 registers x 32 lanes
 
 struct PreMmaParams {
@@ -80,7 +85,7 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t site) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(256);
+    __nanosleep(64);
     if (++spins > (SIA_WATCHDOG_SPINS >> 2)) {
       if (g_watchdog_word != nullptr) {
         *g_watchdog_word = 0x80000000u | (site << 16) | (blockIdx.x & 0xffffu);
@@ -101,6 +106,9 @@ struct PmOut {
 };
 __device__ __forceinline__ void pm_tile(const PmOut& o, int t, uint32_t mask, const uint2* wxt,
                                         const uint32_t (&prev)[3][2][4], const uint32_t (&cur)[3][2][4]) {
+#ifdef SIA_PM_NO_TILES            // timing variant: no second product, no stores
+  if (mask != 0xdeadbeefu) return;
+#endif
   float hp[3][4], hc[3][4];                       // two independent accumulation chains per channel
 #pragma unroll
   for (int c = 0; c < 3; ++c)
@@ -344,7 +352,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) preprocess_mma_kernel(const 
             for (int e = 0; e < 4; ++e) vacc[b][e] = 0.f;
           const uint32_t goff = (uint32_t)(grp * PM_GROUP_BYTES);
 #pragma unroll
-          for (int kc = 0; kc < KV; ++kc) {
+          for (int kc = 0; kc < PM_KV_RUN(KV); ++kc) {
             const uint32_t qa = pa[kc] + goff, qb = pb[kc] + goff;
             uint32_t wa[3], wb[3], wc[3], wd[3];
 #pragma unroll
@@ -454,12 +462,12 @@ static int launch_pre_mma(const PreMmaParams& p, size_t smem_without_pub, cudaSt
   return launch_kernel(kern, dim3(grid), dim3((NW + 1) * 32), smem, st, true, p);
 }
 
-static int g_pm_warps = 8;      // compute warps per CTA (sia_debug_set_mma_warps: 4, 8 or 12; A/B timing only)
+static int g_pm_warps = 8;      // compute warps per CTA (sia_debug_set_mma_warps: 4 or 8; A/B timing only)
 
 }  // namespace sia
 
 extern "C" int sia_debug_set_mma_warps(int warps) {
-  if (warps != 4 && warps != 8 && warps != 12) return SIA_E_INVALID;
+  if (warps != 4 && warps != 8) return SIA_E_INVALID;
   sia::g_pm_warps = warps;
   return 0;
 }
@@ -525,9 +533,6 @@ extern "C" int sia_preprocess_mma_u8hwc(const uint8_t* src, int batch, int src_h
   if (warps == 4) {
     if (kv == 3) return launch_pre_mma<3, 4>(p, smem, st);
     if (kv == 2) return launch_pre_mma<2, 4>(p, smem, st);
-  } else if (warps == 12) {
-    if (kv == 3) return launch_pre_mma<3, 12>(p, smem, st);
-    if (kv == 2) return launch_pre_mma<2, 12>(p, smem, st);
   } else {
     if (kv == 3) return launch_pre_mma<3, 8>(p, smem, st);
     if (kv == 2) return launch_pre_mma<2, 8>(p, smem, st);
