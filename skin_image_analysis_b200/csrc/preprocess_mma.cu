@@ -54,6 +54,7 @@ constexpr int PM_GROUP_BYTES = 96;               // 32 pixels
 #define PM_KV_RUN(kv) (kv)
 #endif
 constexpr int PM_PUB_WORDS = 24 * 32;            // one published set of A fragments: 24 registers x 32 lanes
+constexpr int PM_WIN_BARS = 8;                   // "the new octets of unit k have landed": one mbarrier per unit, ring of 8
 
 struct PreMmaParams {
   const uint8_t* src;
@@ -180,18 +181,16 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) preprocess_mma_kernel(const 
   uint32_t* mask_s = reinterpret_cast<uint32_t*>(pm_smem + off);
   off += (size_t)p.n_tiles * sizeof(uint32_t);
   off = (off + 7) & ~(size_t)7;
-  uint64_t* full = reinterpret_cast<uint64_t*>(pm_smem + off);
-  uint64_t* empty = full + R;
+  uint64_t* win = reinterpret_cast<uint64_t*>(pm_smem + off);      // [PM_WIN_BARS]: all new octets of a unit have landed
+  uint64_t* empty = win + PM_WIN_BARS;                              // [R]: every compute warp has released the slot
   uint64_t* pub_full = empty + R;        // [NW]
   uint64_t* pub_empty = pub_full + NW;   // [NW]
   uint64_t* tab_bar = pub_empty + NW;    // the B-fragment table has landed
 
   pdl_launch_dependents();          // the next kernel (conv1) may start its prologue under this kernel's tail
   if (threadIdx.x == 0) {
-    for (int i = 0; i < R; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], NW);
-    }
+    for (int i = 0; i < PM_WIN_BARS; ++i) mbar_init(&win[i], 1);
+    for (int i = 0; i < R; ++i) mbar_init(&empty[i], NW);
     for (int i = 0; i < NW; ++i) {
       mbar_init(&pub_full[i], 1);
       mbar_init(&pub_empty[i], 1);
@@ -215,7 +214,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) preprocess_mma_kernel(const 
       const uint32_t tab_bytes = (uint32_t)(p.n_tiles * 4 * 32 * sizeof(uint2));
       mbar_arrive_expect_tx(tab_bar, tab_bytes);
       bulk_load_1d(wx_s, p.wx_frag, tab_bytes, tab_bar);
-      int slot = 0;
+      int slot = 0, wb = 0;
       uint32_t phase = 0;                 // parity of the ring pass `slot` belongs to
       bool wrapped = false;
       int u = u_lo;
@@ -226,15 +225,21 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) preprocess_mma_kernel(const 
         int m = u - img * p.n_msteps;
         int o_next = __ldg(&p.r0[m]) >> 3;
         for (int uu = u; uu < pass_end; ++uu, ++m) {
+          // one mbarrier per unit covers all the octets the unit adds to the ring (a wait on a completed mbarrier
+          // still costs the waiting warp ~130 clocks: one wait per unit instead of one per octet)
           const int o_end = min((__ldg(&p.r0[m]) >> 3) + 2 * KV, n_oct_img);
+          uint32_t total = 0;
+          for (int o = o_next; o < o_end; ++o) total += (uint32_t)(min(8, p.src_h - o * 8) * p.row_bytes);
+#ifdef SIA_PM_NO_COPY            // timing variant: no source traffic at all, the barriers still cycle
+          total = 0;
+#endif
+          if (total > 0) mbar_arrive_expect_tx(&win[wb], total);
+          else mbar_arrive(&win[wb]);
           for (int o = o_next; o < o_end; ++o) {
             if (wrapped) mbar_wait_backoff(&empty[slot], phase ^ 1u, 61);
+#ifndef SIA_PM_NO_COPY
             const uint32_t bytes = (uint32_t)(min(8, p.src_h - o * 8) * p.row_bytes);
-#ifdef SIA_PM_NO_COPY            // timing variant: no source traffic at all, the barriers still cycle
-            mbar_arrive(&full[slot]);
-#else
-            mbar_arrive_expect_tx(&full[slot], bytes);
-            bulk_load_1d(ring + (size_t)slot * octet_bytes, image + (size_t)o * octet_bytes, bytes, &full[slot]);
+            bulk_load_1d(ring + (size_t)slot * octet_bytes, image + (size_t)o * octet_bytes, bytes, &win[wb]);
 #endif
             if (++slot == R) {
               slot = 0;
@@ -242,6 +247,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) preprocess_mma_kernel(const 
               wrapped = true;
             }
           }
+          if (++wb == PM_WIN_BARS) wb = 0;
           o_next = max(o_next, o_end);
         }
         u = pass_end;
@@ -289,8 +295,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) preprocess_mma_kernel(const 
     for (int kc = 0; kc < KV; ++kc) wy_next[kc] = __ldg(&p.wy_frag[(m0 * KV + kc) * 32 + lane]);
   }
   // ring bookkeeping without divisions: slot / parity of the next octet to wait for, to release, and of the window start
-  int w_slot = 0, r_slot = 0, base_slot = 0;
-  uint32_t w_phase = 0;
+  int w_slot = 0, r_slot = 0, base_slot = 0, wb = 0;
+  uint32_t wb_phase = 0;
   uint32_t step = 0;                                // m-steps done by this CTA: parity of the fragment hand-over
   int u = u_lo;
   while (u < u_hi) {
@@ -304,9 +310,12 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) preprocess_mma_kernel(const 
       const int g_first = (p.n_groups * warp + rot) / NW, g_end = (p.n_groups * (warp + 1) + rot) / NW;
       const int o0 = r0_s[m] >> 3;
       const int o_win_end = min(o0 + 2 * KV, n_oct_img);
-      for (; o_waited < o_win_end; ++o_waited) {
-        mbar_wait(&full[w_slot], w_phase, 62);
-        if (++w_slot == R) { w_slot = 0; w_phase ^= 1u; }
+      mbar_wait(&win[wb], wb_phase, 62);            // every octet this unit adds to the ring has landed
+      if (++wb == PM_WIN_BARS) { wb = 0; wb_phase ^= 1u; }
+      if (o_win_end > o_waited) {
+        w_slot += o_win_end - o_waited;             // (slot of the next octet nobody has waited for yet)
+        if (w_slot >= R) w_slot -= R;
+        o_waited = o_win_end;
       }
       base_slot += o0 - o_base;                     // (windows advance by less than a ring)
       if (base_slot >= R) base_slot -= R;
@@ -433,12 +442,9 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) preprocess_mma_kernel(const 
       }
 #endif
 
-      // ---------------- release the octets no later m-step of this pass reads ------------------------------------------
-      const int o_rel_end = (uu + 1 < pass_end) ? min(r0_s[m + 1] >> 3, n_oct_img) : o_win_end;
-      for (; o_waited < o_rel_end; ++o_waited) {            // (only if windows ever leave a gap)
-        mbar_wait(&full[w_slot], w_phase, 63);
-        if (++w_slot == R) { w_slot = 0; w_phase ^= 1u; }
-      }
+      // ---------------- release the octets no later unit of this pass reads (a gap between two windows, if a geometry
+      //                  ever has one, lands with the next unit and is released after it) -------------------------------
+      const int o_rel_end = (uu + 1 < pass_end) ? min(r0_s[m + 1] >> 3, o_waited) : o_waited;
       __syncwarp();
       for (; o_released < o_rel_end; ++o_released) {
         if (lane == 0) mbar_arrive(&empty[r_slot]);
@@ -524,11 +530,11 @@ extern "C" int sia_preprocess_mma_u8hwc(const uint8_t* src, int batch, int src_h
   // run past the last slot's end, into the tables behind the ring: read-only garbage that meets zero weights.)
   const size_t octet = (size_t)8 * p.row_bytes;
   const size_t budget = 227 * 1024 - tables - pub - 64;
-  int ring = (int)(budget / (octet + 16));
+  int ring = (int)((budget - PM_WIN_BARS * 8) / (octet + 8));
   if (ring > 24) ring = 24;
   if (ring < 2 * kv + 2) return SIA_E_UNSUPPORTED;
   p.ring_octets = ring;
-  const size_t smem = (size_t)ring * octet + tables + (size_t)2 * ring * 8;
+  const size_t smem = (size_t)ring * octet + tables + (size_t)(ring + PM_WIN_BARS) * 8;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (warps == 4) {
     if (kv == 3) return launch_pre_mma<3, 4>(p, smem, st);
