@@ -182,19 +182,20 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) preprocess_mma_kernel(const 
   off += (size_t)p.n_tiles * sizeof(uint32_t);
   off = (off + 7) & ~(size_t)7;
   uint64_t* win = reinterpret_cast<uint64_t*>(pm_smem + off);      // [PM_WIN_BARS]: all new octets of a unit have landed
-  uint64_t* empty = win + PM_WIN_BARS;                              // [R]: every compute warp has released the slot
-  uint64_t* pub_full = empty + R;        // [NW]
-  uint64_t* pub_empty = pub_full + NW;   // [NW]
-  uint64_t* tab_bar = pub_empty + NW;    // the B-fragment table has landed
+  uint64_t* rel = win + PM_WIN_BARS;                                // [PM_WIN_BARS]: every compute warp is done with a unit
+  uint64_t* tab_bar = rel + PM_WIN_BARS;                            // the B-fragment table has landed
+  // fragment hand-over between neighbouring warps: plain shared-memory flags (unit numbers), polled with volatile loads
+  // (a shared-memory load costs ~30 clocks, an mbarrier wait ~130 even when complete)
+  volatile uint32_t* pub_flag = reinterpret_cast<volatile uint32_t*>(tab_bar + 1);    // [NW]: units published by warp w
+  volatile uint32_t* pub_ack = pub_flag + NW;                                           // [NW]: units of warp w adopted
 
   pdl_launch_dependents();          // the next kernel (conv1) may start its prologue under this kernel's tail
   if (threadIdx.x == 0) {
-    for (int i = 0; i < PM_WIN_BARS; ++i) mbar_init(&win[i], 1);
-    for (int i = 0; i < R; ++i) mbar_init(&empty[i], NW);
-    for (int i = 0; i < NW; ++i) {
-      mbar_init(&pub_full[i], 1);
-      mbar_init(&pub_empty[i], 1);
+    for (int i = 0; i < PM_WIN_BARS; ++i) {
+      mbar_init(&win[i], 1);
+      mbar_init(&rel[i], NW);
     }
+    for (int i = 0; i < NW; ++i) pub_flag[i] = pub_ack[i] = 0u;
     mbar_init(tab_bar, 1);
     fence_mbar_init();
   }
@@ -215,8 +216,11 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) preprocess_mma_kernel(const 
       mbar_arrive_expect_tx(tab_bar, tab_bytes);
       bulk_load_1d(wx_s, p.wx_frag, tab_bytes, tab_bar);
       int slot = 0, wb = 0;
-      uint32_t phase = 0;                 // parity of the ring pass `slot` belongs to
-      bool wrapped = false;
+      // release side: the compute warps arrive once per unit on rel[]; how many octets a unit retires follows from the
+      // r0 table (everything below the next window's start; everything at the end of a pass), so the copy lane keeps a
+      // second cursor over the units and a running count of retired octets
+      int issued = 0, retired = 0, ru = u_lo, rb = 0, r_prev_end = 0;
+      uint32_t rb_phase = 0;
       int u = u_lo;
       while (u < u_hi) {
         const int img = u / p.n_msteps;
@@ -236,16 +240,24 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) preprocess_mma_kernel(const 
           if (total > 0) mbar_arrive_expect_tx(&win[wb], total);
           else mbar_arrive(&win[wb]);
           for (int o = o_next; o < o_end; ++o) {
-            if (wrapped) mbar_wait_backoff(&empty[slot], phase ^ 1u, 61);
+            while (issued - retired >= R) {          // the slot still holds an octet some warp may read
+              mbar_wait_backoff(&rel[rb], rb_phase, 61);
+              if (++rb == PM_WIN_BARS) { rb = 0; rb_phase ^= 1u; }
+              const int img_r = ru / p.n_msteps, m_r = ru - img_r * p.n_msteps;
+              const int pass_lo = max(u_lo, img_r * p.n_msteps), pass_hi = min(u_hi, (img_r + 1) * p.n_msteps);
+              if (ru == pass_lo) r_prev_end = __ldg(&p.r0[m_r]) >> 3;
+              const int waited = min((__ldg(&p.r0[m_r]) >> 3) + 2 * KV, n_oct_img);
+              const int r_end = (ru + 1 < pass_hi) ? min(__ldg(&p.r0[m_r + 1]) >> 3, waited) : waited;
+              retired += max(r_end - r_prev_end, 0);
+              r_prev_end = max(r_prev_end, r_end);
+              ++ru;
+            }
+            ++issued;
 #ifndef SIA_PM_NO_COPY
             const uint32_t bytes = (uint32_t)(min(8, p.src_h - o * 8) * p.row_bytes);
             bulk_load_1d(ring + (size_t)slot * octet_bytes, image + (size_t)o * octet_bytes, bytes, &win[wb]);
 #endif
-            if (++slot == R) {
-              slot = 0;
-              phase ^= 1u;
-              wrapped = true;
-            }
+            if (++slot == R) slot = 0;
           }
           if (++wb == PM_WIN_BARS) wb = 0;
           o_next = max(o_next, o_end);
@@ -295,7 +307,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) preprocess_mma_kernel(const 
     for (int kc = 0; kc < KV; ++kc) wy_next[kc] = __ldg(&p.wy_frag[(m0 * KV + kc) * 32 + lane]);
   }
   // ring bookkeeping without divisions: slot / parity of the next octet to wait for, to release, and of the window start
-  int w_slot = 0, r_slot = 0, base_slot = 0, wb = 0;
+  int w_slot = 0, base_slot = 0, wb = 0;
   uint32_t wb_phase = 0;
   uint32_t step = 0;                                // m-steps done by this CTA: parity of the fragment hand-over
   int u = u_lo;
@@ -304,13 +316,14 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) preprocess_mma_kernel(const 
     const int pass_end = min(u_hi, (img + 1) * p.n_msteps);
     int m = u - img * p.n_msteps;
     const int o_start = r0_s[m] >> 3;
-    int o_waited = o_start, o_released = o_start, o_base = o_start;      // octet numbers matching w_slot / r_slot / base_slot
+    int o_waited = o_start, o_base = o_start;      // octet numbers matching w_slot / base_slot
     for (int uu = u; uu < pass_end; ++uu, ++m, ++step) {
       const int rot = (int)((step * 5u) % (uint32_t)NW);          // 5 is coprime with 4, 8, 12, 16
       const int g_first = (p.n_groups * warp + rot) / NW, g_end = (p.n_groups * (warp + 1) + rot) / NW;
       const int o0 = r0_s[m] >> 3;
       const int o_win_end = min(o0 + 2 * KV, n_oct_img);
       mbar_wait(&win[wb], wb_phase, 62);            // every octet this unit adds to the ring has landed
+      const int my_bar = wb;
       if (++wb == PM_WIN_BARS) { wb = 0; wb_phase ^= 1u; }
       if (o_win_end > o_waited) {
         w_slot += o_win_end - o_waited;             // (slot of the next octet nobody has waited for yet)
@@ -397,7 +410,15 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) preprocess_mma_kernel(const 
           const bool first_group = grp == g_first;
           if (first_group && publish) {
             // hand this group's fragments to the left neighbour (it finishes the tiles that straddle the boundary)
-            if (step > 0) mbar_wait(&pub_empty[warp], (step - 1) & 1u, 64);
+            {                                         // the left neighbour has picked up my previous unit's fragments
+              uint32_t spins = 0;
+              while (pub_ack[warp] < step) {
+                if (++spins > SIA_WATCHDOG_SPINS) {
+                  if (g_watchdog_word != nullptr) *g_watchdog_word = 0x80000000u | (64u << 16) | (blockIdx.x & 0xffffu);
+                  __trap();
+                }
+              }
+            }
 #pragma unroll
             for (int c = 0; c < 3; ++c)
 #pragma unroll
@@ -405,7 +426,10 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) preprocess_mma_kernel(const 
 #pragma unroll
                 for (int e = 0; e < 4; ++e) my_pub[((c * 2 + x) * 4 + e) * 32] = cur[c][x][e];
             __syncwarp();
-            if (lane == 0) mbar_arrive(&pub_full[warp]);
+            if (lane == 0) {
+              __threadfence_block();
+              pub_flag[warp] = step + 1u;
+            }
           }
           // ---------------- second product + store for every output tile whose last group this is --------------------
           const int t_end = tbeg_s[grp + 1];
@@ -423,7 +447,16 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) preprocess_mma_kernel(const 
         }
         if (adopt) {
           // tiles whose last group is the right neighbour's first one and that also read my last group
-          mbar_wait(&pub_full[warp + 1], step & 1u, 65);
+          {
+            uint32_t spins = 0;
+            while (pub_flag[warp + 1] < step + 1u) {
+              if (++spins > SIA_WATCHDOG_SPINS) {
+                if (g_watchdog_word != nullptr) *g_watchdog_word = 0x80000000u | (65u << 16) | (blockIdx.x & 0xffffu);
+                __trap();
+              }
+            }
+            __threadfence_block();
+          }
           uint32_t nxt[3][2][4];
 #pragma unroll
           for (int c = 0; c < 3; ++c)
@@ -432,7 +465,10 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) preprocess_mma_kernel(const 
 #pragma unroll
               for (int e = 0; e < 4; ++e) nxt[c][x][e] = right_pub[((c * 2 + x) * 4 + e) * 32];
           __syncwarp();
-          if (lane == 0) mbar_arrive(&pub_empty[warp + 1]);
+          if (lane == 0) {
+            __threadfence_block();
+            pub_ack[warp + 1] = step + 1u;
+          }
           const int t_end = tbeg_s[g_end + 1];
           for (int t = tbeg_s[g_end]; t < t_end; ++t) {
             const uint32_t mask = mask_s[t];
@@ -442,14 +478,10 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) preprocess_mma_kernel(const 
       }
 #endif
 
-      // ---------------- release the octets no later unit of this pass reads (a gap between two windows, if a geometry
-      //                  ever has one, lands with the next unit and is released after it) -------------------------------
-      const int o_rel_end = (uu + 1 < pass_end) ? min(r0_s[m + 1] >> 3, o_waited) : o_waited;
+      // ---------------- done with the unit: the copy lane works out from the r0 table which octets that retires (those
+      //                  below the next window's start; all of them at the end of a pass) ------------------------------
       __syncwarp();
-      for (; o_released < o_rel_end; ++o_released) {
-        if (lane == 0) mbar_arrive(&empty[r_slot]);
-        if (++r_slot == R) r_slot = 0;
-      }
+      if (lane == 0) mbar_arrive(&rel[my_bar]);
     }
     // the next pass starts at the slot after the last octet of this one
     base_slot = w_slot;
@@ -461,7 +493,7 @@ template <int KV, int NW>
 static int launch_pre_mma(const PreMmaParams& p, size_t smem_without_pub, cudaStream_t st) {
   auto kern = preprocess_mma_kernel<KV, NW>;
   static SmemSlots configured = {};
-  const size_t smem = smem_without_pub + (size_t)NW * PM_PUB_WORDS * 4 + (size_t)(2 * NW + 1) * 8;
+  const size_t smem = smem_without_pub + (size_t)NW * PM_PUB_WORDS * 4 + 8 + (size_t)2 * NW * 4 + 8;
   if (int rc = ensure_dynamic_smem(kern, (int)smem, &configured)) return rc;
   const long long total = (long long)p.batch * p.n_msteps;
   const int grid = (int)(total < sm_count() ? total : sm_count());
@@ -525,16 +557,16 @@ extern "C" int sia_preprocess_mma_u8hwc(const uint8_t* src, int batch, int src_h
     }
   const size_t tables = (size_t)n_tiles * 4 * 32 * 8 + (size_t)n_msteps * 4 + (size_t)(n_groups + 1) * 4 +
                         (size_t)n_tiles * 4 + 8;
-  const size_t pub = (size_t)warps * PM_PUB_WORDS * 4 + (size_t)(2 * warps + 1) * 8;
+  const size_t pub = (size_t)warps * PM_PUB_WORDS * 4 + 8 + (size_t)2 * warps * 4 + 8;
   // the ring: the 2*kv octets of a window + as many octets of prefetch as fit (at least 2).  (The last group's loads may
   // run past the last slot's end, into the tables behind the ring: read-only garbage that meets zero weights.)
   const size_t octet = (size_t)8 * p.row_bytes;
   const size_t budget = 227 * 1024 - tables - pub - 64;
-  int ring = (int)((budget - PM_WIN_BARS * 8) / (octet + 8));
+  int ring = (int)((budget - 2 * PM_WIN_BARS * 8) / octet);
   if (ring > 24) ring = 24;
   if (ring < 2 * kv + 2) return SIA_E_UNSUPPORTED;
   p.ring_octets = ring;
-  const size_t smem = (size_t)ring * octet + tables + (size_t)(ring + PM_WIN_BARS) * 8;
+  const size_t smem = (size_t)ring * octet + tables + (size_t)2 * PM_WIN_BARS * 8;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (warps == 4) {
     if (kv == 3) return launch_pre_mma<3, 4>(p, smem, st);
