@@ -159,6 +159,11 @@ int sia_preprocess_tv_u8hwc(const uint8_t* src, int batch, int src_h, int src_w,
  * src/tone_bias_test.py:190-196) -> padded NHWC4 bf16 [B,h,w+8,4] (SIA_LAYOUT_NHWC4_BF16). */
 int sia_nchw_f32_to_nhwc4_bf16(const float* src, int batch, int h, int w, void* dst, void* stream);
 
+/* SURVEY 8(f) row 4, the decode side: a GPU JPEG decoder (nvJPEG, e.g. torchvision.io.decode_jpeg(device="cuda"))
+ * emits planar [B,3,H,W] uint8; the transform kernels read the interleaved decode buffer [B,H,W,3] that
+ * skimage.io.imread produces on the reference path (src/tone_bias_dataset.py:326).  w % 4 == 0. */
+int sia_chw_u8_to_hwc_u8(const uint8_t* src_chw, int batch, int h, int w, uint8_t* dst_hwc, void* stream);
+
 /* Floor pooling on odd sizes (tone_bias_optuna.define_isic_model with n_conv_layers >= 4: 14 -> 7 -> 3 -> 1,
  * src/tone_bias_optuna.py:143-152; nn.MaxPool2d drops the last row / column): the conv kernels take even sizes, so
  * an odd-sized activation [B,h,w,C] bf16 is copied into an even-sized buffer [B,out_h,out_w,C] whose cells outside

@@ -42,6 +42,7 @@ SIGNATURES = {
                                         c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "sia_debug_tv_force_generic": (c_int, [c_int]),
     "sia_nchw_f32_to_nhwc4_bf16": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
+    "sia_chw_u8_to_hwc_u8": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
     "sia_pad_nhwc_bf16": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P]),
     "sia_pack_conv7x7_c3": (c_int, [_P, _P, _P]),
     "sia_pack_conv7x7_c3_bytes": (c_size_t, []),

@@ -50,6 +50,29 @@ __global__ void pad_nhwc_kernel(const uint4* __restrict__ in, uint4* __restrict_
   }
 }
 
+// [B,3,H,W] u8 (what a GPU JPEG decoder emits) -> [B,H,W,3] u8 (the decode-buffer layout of the transform kernels).
+// Thread = 4 pixels of one row: three 32-bit plane loads, three 32-bit stores of 12 interleaved bytes.
+__global__ void chw_to_hwc_u8_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int h, int w,
+                                     long long quads_total) {
+  const int wq = w >> 2;
+  const size_t plane = (size_t)h * w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < quads_total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int xq = (int)(i % wq);
+    const long long row = i / wq;                       // b * h + y
+    const long long b = row / h;
+    const size_t in = (size_t)b * 3 * plane + (size_t)(row - b * h) * w + (size_t)xq * 4;
+    const uint32_t r = *reinterpret_cast<const uint32_t*>(src + in);
+    const uint32_t g = *reinterpret_cast<const uint32_t*>(src + in + plane);
+    const uint32_t bl = *reinterpret_cast<const uint32_t*>(src + in + 2 * plane);
+    uint32_t* out = reinterpret_cast<uint32_t*>(dst + ((size_t)row * w + (size_t)xq * 4) * 3);
+    const uint32_t rg0 = __byte_perm(r, g, 0x5140), rg1 = __byte_perm(r, g, 0x7362);     // r0 g0 r1 g1 | r2 g2 r3 g3
+    out[0] = __byte_perm(rg0, bl, 0x2410);                                   // r0 g0 b0 r1
+    out[1] = __byte_perm(__byte_perm(rg0, bl, 0x0053), rg1, 0x5410);         // g1 b1 r2 g2
+    out[2] = __byte_perm(rg1, bl, 0x7326);                                   // b2 r3 g3 b3
+  }
+}
+
 static int g_pdl = -1;      // -1: not decided yet (reads SIA_PDL on first use)
 
 bool pdl_enabled() {
@@ -122,6 +145,17 @@ int sia_pad_nhwc_bf16(const void* in_nhwc, int batch, int h, int w, int channels
   pad_nhwc_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(in_nhwc), static_cast<uint4*>(out_nhwc), h, w, out_h, out_w, valid_h, valid_w, c8,
       total);
+  return launch_status();
+}
+
+int sia_chw_u8_to_hwc_u8(const uint8_t* src_chw, int batch, int h, int w, uint8_t* dst_hwc, void* stream) {
+  using namespace sia;
+  SIA_REQUIRE(src_chw && dst_hwc && batch >= 1 && h >= 1 && w >= 4);
+  if (w % 4 != 0) return SIA_E_UNSUPPORTED;
+  SIA_REQUIRE(aligned(src_chw, 4) && aligned(dst_hwc, 4));
+  const long long quads = (long long)batch * h * (w / 4);
+  const int blocks = (int)((quads + 255) / 256 < 8192 ? (quads + 255) / 256 : 8192);
+  chw_to_hwc_u8_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(src_chw, dst_hwc, h, w, quads);
   return launch_status();
 }
 

@@ -20,7 +20,7 @@ from ._lib import (LAYOUT_NCHW_BF16, LAYOUT_NCHW_F32, LAYOUT_NHWC4_BF16, NHWC4_P
 __all__ = [
     "preprocess_u8hwc", "nchw_f32_to_nhwc4", "pack_conv7x7_c3", "pack_conv3x3", "pack_linear_chw_to_hwc",
     "conv7x7_c3_relu_pool2", "conv3x3_relu_pool2", "linear_splitk", "head_tail", "head_tail_chain", "confusion_counts",
-    "pad_nhwc", "LAYOUT_NCHW_F32", "LAYOUT_NCHW_BF16", "LAYOUT_NHWC4_BF16", "NHWC4_PAD",
+    "pad_nhwc", "chw_to_hwc_u8", "LAYOUT_NCHW_F32", "LAYOUT_NCHW_BF16", "LAYOUT_NHWC4_BF16", "NHWC4_PAD",
 ]
 
 
@@ -337,6 +337,20 @@ def conv3x3_relu_pool2(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tens
         out = torch.empty((b, h // 2, w // 2, cout), dtype=torch.bfloat16, device=x.device)
     check(_lib.load().sia_conv3x3_relu_pool2(ptr(x), b, h, w, cin, cout, ptr(w_packed), ptr(bias), ptr(out),
                                              stream_ptr()), "sia_conv3x3_relu_pool2")
+    return out
+
+
+def chw_to_hwc_u8(x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """[B,3,H,W] uint8 (a GPU JPEG decoder's planar output) -> [B,H,W,3] uint8 decode buffers for the transform kernels."""
+    _need(x, torch.uint8, "x")
+    if x.dim() != 4 or x.shape[1] != 3:
+        raise ValueError("x must be [B,3,H,W] uint8")
+    b, _, h, w = x.shape
+    if out is None:
+        out = torch.empty((b, h, w, 3), dtype=torch.uint8, device=x.device)
+    else:
+        _need(out, torch.uint8, "out")
+    check(_lib.load().sia_chw_u8_to_hwc_u8(ptr(x), b, h, w, ptr(out), stream_ptr()), "sia_chw_u8_to_hwc_u8")
     return out
 
 

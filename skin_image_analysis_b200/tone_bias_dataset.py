@@ -32,7 +32,7 @@ from ._lib import SiaError
 from .resize_weights import rescale_size
 
 __all__ = ["HibaDataset", "Rescale", "RandomCrop", "ToTensor", "GpuBatchTransform", "convert_type2tone",
-           "DeferredImage", "DeferredBatch"]
+           "DeferredImage", "DeferredBatch", "decode_jpeg_batch"]
 
 
 def convert_type2tone(row):
@@ -179,6 +179,31 @@ _register_collate()
 def _in_loader_worker() -> bool:
     from torch.utils.data import get_worker_info
     return get_worker_info() is not None
+
+
+def decode_jpeg_batch(files, device="cuda") -> torch.Tensor:
+    """SURVEY 8(f) row 4 -- JPEG decode in front of the transform kernel, on the GPU: ``files`` = paths or encoded byte
+    buffers of same-sized JPEGs -> [B,H,W,3] uint8 decode buffers on ``device`` (what ``GpuBatchTransform`` /
+    ``EvalEngine.step`` take).  The decode itself is nvJPEG through ``torchvision.io.decode_jpeg(device=...)`` (a library
+    call: a decoder is outside the hand-written path); its planar output is interleaved by ``sia_chw_u8_to_hwc_u8``.
+    nvJPEG and libjpeg (the reference reads with ``skimage.io.imread``, tone_bias_dataset.py:326) differ by a few grey
+    levels in chroma up-sampling, so this front end is NOT the bit-exact parity path -- ``HibaDataset`` (PIL decode in
+    the DataLoader workers) is."""
+    import torchvision
+    datas = []
+    for f in files:
+        if isinstance(f, (str, os.PathLike)):
+            datas.append(torchvision.io.read_file(str(f)))
+        else:
+            datas.append(torch.frombuffer(bytearray(f), dtype=torch.uint8))
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise SiaError("decode_jpeg_batch decodes on a CUDA device")
+    planes = torchvision.io.decode_jpeg(datas, device=device, mode=torchvision.io.ImageReadMode.RGB)
+    if len({tuple(p.shape) for p in planes}) != 1:
+        raise ValueError("decode_jpeg_batch needs same-sized images (batch them by size)")
+    with torch.cuda.device(device):
+        return ops.chw_to_hwc_u8(torch.stack(planes).contiguous())
 
 
 class Rescale(object):

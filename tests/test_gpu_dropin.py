@@ -279,3 +279,31 @@ def test_full_size_bench_config_vs_cpu_oracle():
     # xavier-random weights give nearly constant logits, so the margin band holds most images; the
     # images outside it must still be a real sample
     assert int(safe.sum()) >= 32
+
+
+def test_gpu_jpeg_decode_front_end(tmp_path):
+    """nvJPEG decode (torchvision, a library call) -> sia_chw_u8_to_hwc_u8 -> fused transform.  The
+    interleave kernel is exact; the decoded pixels differ from libjpeg's (the reference's decoder) by a few grey levels
+    on smooth images, so after the 2x down-sampling resize the transform agrees with the oracle on the PIL-decoded bytes
+    to 2 % of full scale -- a front end for throughput, not the bit-exact parity path (that is HibaDataset)."""
+    import io
+    from PIL import Image
+    from skin_image_analysis_b200 import ops
+    from skin_image_analysis_b200.tone_bias_dataset import decode_jpeg_batch
+    g = torch.Generator(device="cuda").manual_seed(2)
+    planar = torch.randint(0, 256, (3, 3, 20, 28), dtype=torch.uint8, device="cuda", generator=g)
+    assert torch.equal(ops.chw_to_hwc_u8(planar), planar.permute(0, 2, 3, 1).contiguous())
+    files, pil = [], []
+    for i in range(3):
+        u8 = helpers.synthetic_u8_image(450, 600, 800 + i, "smooth")
+        path = tmp_path / f"img{i}.jpg"
+        Image.fromarray(u8, "RGB").save(path, format="JPEG", quality=95, subsampling=0)
+        files.append(str(path) if i else path.read_bytes())                # a path or an encoded buffer
+        pil.append(np.array(Image.open(path).convert("RGB")))
+    batch = decode_jpeg_batch(files)
+    assert batch.shape == (3, 450, 600, 3) and batch.dtype == torch.uint8 and batch.is_cuda
+    diff = (batch.cpu().numpy().astype(np.int32) - np.stack(pil).astype(np.int32))
+    assert np.abs(diff).mean() <= 1.0 and np.abs(diff).max() <= 16        # decoder-dependent, a few grey levels
+    got = ops.preprocess_u8hwc(batch, (224, 224), ops.LAYOUT_NCHW_F32).cpu().numpy()
+    want = np.stack([R.transform_u8(im, (224, 224)) for im in pil])
+    assert np.abs(got - want).max() <= 0.02
