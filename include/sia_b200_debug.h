@@ -3,7 +3,7 @@
  * Two groups:
  *   (1) switches exported by the product library libsia_b200.so itself, because they toggle instrumentation or
  *       A/B paths inside the product kernels: sia_debug_tv_force_generic, sia_debug_set_trace, sia_debug_set_stats,
- *       sia_debug_set_mma_warps, sia_debug_set_programmatic_launch;
+ *       sia_debug_set_mma_warps, sia_debug_set_programmatic_launch, sia_debug_set_tail_impl;
  *   (2) hardware probes (tcgen05 / TMA / TMEM / ALU micro-benchmarks used by tests/test_umma_probe.py to pin the
  *       descriptor conventions the kernels rely on), built into a SEPARATE library libsia_b200_debug.so
  *       (csrc/libsia_debug_unity.cu): the product library carries none of them.
@@ -42,6 +42,10 @@ int sia_debug_set_programmatic_launch(int on);
 
 /* Debug / A-B (timing): compute warps per CTA of sia_preprocess_mma_u8hwc: 4 or 8 (default 8). */
 int sia_debug_set_mma_warps(int warps);
+
+/* Debug / A-B (timing, parity): which kernel sia_head_tail launches for the 512 -> 256 -> 2 head: 0 = the
+ * eight-CTA cluster kernel (default), 1 = the one-CTA-per-four-images kernel every other head uses. */
+int sia_debug_set_tail_impl(int impl);
 
 /* ---- (2) exported by libsia_b200_debug.so ------------------------------------------------------------ */
 

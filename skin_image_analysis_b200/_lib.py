@@ -37,6 +37,7 @@ SIGNATURES = {
                                          ctypes.POINTER(c_int32), ctypes.POINTER(c_float), ctypes.POINTER(c_float),
                                          c_int, c_int, _P, _P]),
     "sia_debug_set_mma_warps": (c_int, [c_int]),
+    "sia_debug_set_tail_impl": (c_int, [c_int]),
     "sia_debug_set_programmatic_launch": (c_int, [c_int]),
     "sia_preprocess_tv_u8hwc": (c_int, [_P, c_int, c_int, c_int, _P, _P, c_int, c_int, _P, _P, c_int, c_int, _P, c_int,
                                         c_int, c_int, c_int, c_int, c_int, _P, _P]),

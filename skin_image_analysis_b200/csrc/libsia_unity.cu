@@ -10,4 +10,5 @@
 #include "preprocess_tv.cu"
 #include "conv3x3.cu"
 #include "conv1.cu"
+#include "tail_cluster.cu"
 #include "linear.cu"

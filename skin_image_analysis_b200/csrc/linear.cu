@@ -379,6 +379,12 @@ extern "C" int sia_head_tail(const float* partial, int splits, int m, int n1, in
   if (counts != nullptr) {
     SIA_REQUIRE(label && groups && n_attr >= 1 && n_groups >= 1 && groups_stride >= m);
   }
+  // the reference's head (512 -> 256 -> 2) runs on eight-CTA clusters (tail_cluster.cu); any other head here
+  int crc = 0;
+  if (launch_head_tail_cluster(&crc, partial, splits, m, n1, n2, b1, w2t, b2, w3, b3, logp, pred, label, groups,
+                               groups_stride, n_attr, n_groups, reinterpret_cast<unsigned long long*>(counts),
+                               static_cast<cudaStream_t>(stream)))
+    return crc;
   return launch_kernel(head_tail_kernel, dim3((m + TAIL_IMGS - 1) / TAIL_IMGS), dim3(TAIL_THREADS), 0, static_cast<cudaStream_t>(stream), true,
       partial, splits, m, n1, n2, b1, w2t, b2, w3, b3, logp, pred, label, groups, groups_stride, n_attr, n_groups,
       reinterpret_cast<unsigned long long*>(counts));

@@ -294,6 +294,73 @@ __host__ __device__ constexpr uint32_t make_idesc_i8(uint32_t m, uint32_t n, uin
          ((m >> 4) << 24);
 }
 
+// ---------------------------------- clusters / distributed shared memory ---------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// Address of the same shared-memory location in CTA `rank` of this cluster (shared::cluster window).
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t cta_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_v2(uint32_t cluster_addr, float a, float b) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(cluster_addr), "f"(a), "f"(b) : "memory");
+}
+// Asynchronous remote store: 16 / 8 bytes into another CTA's shared memory, completing `bytes` on an mbarrier of THAT
+// CTA (both addresses in the shared::cluster window of the same CTA).  The receiver waits on its own barrier with
+// mbar_wait_cluster: no fence, no cluster-wide barrier on the data path.
+__device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, uint32_t cluster_bar, float a, float b, float c,
+                                            float d) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(cluster_addr), "f"(a), "f"(b), "f"(c), "f"(d), "r"(cluster_bar)
+               : "memory");
+}
+__device__ __forceinline__ void st_async_v2(uint32_t cluster_addr, uint32_t cluster_bar, float a, float b) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
+               ::"r"(cluster_addr), "f"(a), "f"(b), "r"(cluster_bar)
+               : "memory");
+}
+// mbar_wait for a barrier completed by other CTAs of the cluster (acquire at cluster scope).
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, uint32_t site) {
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (++spins > SIA_WATCHDOG_SPINS) {
+      if (g_watchdog_word != nullptr) {
+        *g_watchdog_word = 0x80000000u | (site << 16) | (blockIdx.x & 0xffffu);
+        __threadfence_system();
+      }
+      __trap();
+    }
+  }
+}
+// The two halves of barrier.cluster: every thread of every CTA of the cluster arrives, then waits.  The release /
+// acquire pair orders the distributed-shared-memory stores before the arrive ahead of the loads after the wait.
+__device__ __forceinline__ void cluster_arrive_release() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait_acquire() {
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// ---------------------------------- cp.async (LDGSTS) ----------------------------------------
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
 // ---------------------------------- small math helpers ---------------------------------------
 // One 256-bit global store (sm_100: STG.256): a whole 32-byte sector per lane in ONE request, instead of two 16-byte
 // halves that reach L2 as partial-sector writes.  p must be 32-byte aligned.

@@ -88,10 +88,14 @@ def test_pack_linear_permutes_chw_to_hwc():
     assert torch.equal(p.view(4, 5, 3), w.view(4, 3, 5).permute(0, 2, 1))
 
 
-def test_head_tail_matches_torch():
-    from skin_image_analysis_b200 import ops
-    g = torch.Generator(device="cuda").manual_seed(5)
-    m, s = 37, 6
+@pytest.mark.parametrize("m,s", [(37, 6), (1, 1), (16, 18), (17, 21), (256, 18), (300, 45)])
+@pytest.mark.parametrize("impl", [0, 1])
+def test_head_tail_matches_torch(m, s, impl):
+    """Both kernels behind sia_head_tail for the 512 -> 256 -> 2 head: the eight-CTA cluster kernel (impl 0, the
+    default) and the four-images-per-CTA kernel (impl 1), against float64 torch; ragged last cluster, more split-K
+    slices than one load batch, one image."""
+    from skin_image_analysis_b200 import _lib, ops
+    g = torch.Generator(device="cuda").manual_seed(5 + m)
     part = torch.randn(s, m, 512, device="cuda", generator=g)
     b1 = torch.randn(512, device="cuda", generator=g)
     w2 = torch.randn(256, 512, device="cuda", generator=g) * 0.05
@@ -101,8 +105,16 @@ def test_head_tail_matches_torch():
     label = torch.randint(0, 2, (m,), device="cuda", dtype=torch.uint8)
     groups = torch.randint(0, 7, (3, m), device="cuda", dtype=torch.uint8)
     counts = torch.zeros((3, 6, 2, 2), dtype=torch.int64, device="cuda")
-    logp, pred = ops.head_tail(part, b1, w2.t().contiguous(), b2, w3, b3, label=label, groups=groups, n_groups=6,
-                               counts=counts)
+    lib = _lib.load()
+    assert lib.sia_debug_set_tail_impl(impl) == 0
+    try:
+        logp, pred = ops.head_tail(part, b1, w2.t().contiguous(), b2, w3, b3, label=label, groups=groups, n_groups=6,
+                                   counts=counts)
+        again, pred_again = ops.head_tail(part, b1, w2.t().contiguous(), b2, w3, b3)
+        torch.cuda.synchronize()
+    finally:
+        assert lib.sia_debug_set_tail_impl(0) == 0
+    assert lib.sia_debug_set_tail_impl(2) != 0
     h1 = F.relu(part.double().sum(0) + b1.double())
     h2 = F.relu(h1 @ w2.double().t() + b2.double())
     z = h2 @ w3.double().t() + b3.double()
@@ -111,6 +123,8 @@ def test_head_tail_matches_torch():
     safe = (z[:, 1] - z[:, 0]).abs() > 1e-3
     assert torch.equal(pred[safe].long(), torch.max(want, 1)[1][safe])
     assert torch.equal(counts, ops.confusion_counts(pred, label, groups, 6))
+    assert int(counts[0].sum()) == int((groups[0] < 6).sum())
+    assert torch.equal(logp, again) and torch.equal(pred, pred_again)      # fixed summation order: bit-reproducible
 
 
 @pytest.mark.parametrize("kind", [om.LIST_MODEL, om.FOUR_CONV_MODEL])

@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol():
     debug = {n for n, _ in _declared("sia_b200_debug.h")}
     assert product and debug and not (product & debug)
     switches = {"sia_debug_tv_force_generic", "sia_debug_set_trace", "sia_debug_set_stats", "sia_debug_set_mma_warps",
-                "sia_debug_set_programmatic_launch"}
+                "sia_debug_set_programmatic_launch", "sia_debug_set_tail_impl"}
     assert not any(n.startswith("sia_debug") for n in product)
     for name in sorted(product | switches):
         assert hasattr(lib, name), f"{name} declared but not exported by libsia_b200.so"
