@@ -215,6 +215,14 @@ int sia_conv7x7_c3_relu_pool2_strided(const void* in_nhwc4, int batch, int h, in
  * ------------------------------------------------------------------------------------------ */
 int sia_linear_splitk(const void* a_bf16, const void* w_bf16, int m, int n, int k, int splits, float* partial,
                       void* stream);
+/* The same product with the weights stored tile by tile (sia_retile_linear_w, once at model load): every 128 x 64
+ * weight tile is one contiguous 16 KB block in HBM, already in the shared-memory order the tensor cores read, so a
+ * pipeline stage fetches it with ONE bulk copy instead of 128 strided 128-byte rows.  Bit-identical results. */
+int sia_linear_splitk_tiled(const void* a_bf16, const void* w_tiles_bf16, int m, int n, int k, int splits,
+                            float* partial, void* stream);
+/* w : bf16 [n,k] row-major  ->  w_tiles : bf16, n*k elements, tiles [n/128][k/64] of 128 rows x 128 bytes with the
+ * 16-byte chunks of row r XOR-swizzled by (r & 7).  n % 128 == 0, k % 64 == 0; not in place. */
+int sia_retile_linear_w(const void* w_bf16, int n, int k, void* w_tiles_bf16, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K6 (+K7)  tail:  h1 = relu(sum_s partial + b1); h2 = relu(W2 h1 + b2); z = W3 h2 + b3;

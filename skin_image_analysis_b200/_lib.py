@@ -58,6 +58,8 @@ SIGNATURES = {
     "sia_conv7x7_c3_relu_pool2": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, _P]),
     "sia_conv3x3_relu_pool2": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P]),
     "sia_linear_splitk": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P]),
+    "sia_linear_splitk_tiled": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P]),
+    "sia_retile_linear_w": (c_int, [_P, c_int, c_int, _P, _P]),
     "sia_head_tail": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int,
                               c_int, _P, _P]),
     "sia_confusion_counts": (c_int, [_P, _P, _P, c_longlong, c_longlong, c_int, c_int, _P, _P]),

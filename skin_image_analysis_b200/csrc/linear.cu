@@ -20,11 +20,17 @@ namespace sia {
 constexpr int LN_BM = 128, LN_BN = 128, LN_BK = 64;
 constexpr int LN_STAGE_BYTES = (LN_BM + LN_BN) * LN_BK * 2;  // 32 KB
 constexpr int LN_NSTAGE = 6;
+constexpr int LN_OUT_PITCH = LN_BN * 4 + 16;   // epilogue staging: rows 4 words apart modulo the 32 banks
 constexpr int LN_THREADS = 192;  // warp0 TMA, warp1 MMA (+TMEM alloc), warps2-5 epilogue
 
+// W_TILED: the weights are stored tile by tile, each 128 x 64 tile as the 16 KB shared-memory image the MMA reads
+// (128-byte rows, 16-byte chunks XOR-swizzled by the row; sia_retile_linear_w), so a stage's weight tile is ONE
+// contiguous bulk copy instead of 128 strided 128-byte rows.
+template <bool W_TILED>
 __global__ void __launch_bounds__(LN_THREADS, 1)
 linear_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                     float* __restrict__ partial, int M, int N, int kblocks_total, int splits) {
+                     const uint8_t* __restrict__ w_tiles, float* __restrict__ partial, int M, int N, int kblocks_total,
+                     int splits) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + LN_NSTAGE * LN_STAGE_BYTES);
@@ -56,23 +62,40 @@ linear_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   tc_fence_after_sync();
   const uint32_t tmem_base = bcast0(*tmem_slot);
   pdl_launch_dependents();          // programmatic dependent launch: the prologue above overlaps the previous kernel
-  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
+      auto load_w = [&](int stage, int kb) {
+        uint8_t* sw = smem + stage * LN_STAGE_BYTES + LN_BM * LN_BK * 2;
+        if constexpr (W_TILED) {
+          bulk_load_1d(sw, w_tiles + ((size_t)n_blk * kblocks_total + kb) * (LN_BN * LN_BK * 2), LN_BN * LN_BK * 2,
+                       &full_bar[stage]);
+        } else {
+          tma_load_2d(sw, &tmap_w, &full_bar[stage], kb * LN_BK, n_blk * LN_BN);
+        }
+      };
+      // the weights are not the predecessor's output: the weight tiles of the first stages are requested before
+      // griddepcontrol.wait, the activations after it
+      const int pre = min(LN_NSTAGE, kb_hi - kb_lo);
+      for (int i = 0; i < pre; ++i) {
+        mbar_arrive_expect_tx(&full_bar[i], LN_STAGE_BYTES);
+        load_w(i, kb_lo + i);
+      }
+      pdl_wait();
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = kb_lo; kb < kb_hi; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1, 40);
-        uint8_t* sa = smem + stage * LN_STAGE_BYTES;
-        uint8_t* sw = sa + LN_BM * LN_BK * 2;
-        mbar_arrive_expect_tx(&full_bar[stage], LN_STAGE_BYTES);
-        tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * LN_BK, m_blk * LN_BM);
-        tma_load_2d(sw, &tmap_w, &full_bar[stage], kb * LN_BK, n_blk * LN_BN);
+        if (kb - kb_lo >= pre) {
+          mbar_wait(&empty_bar[stage], phase ^ 1, 40);
+          mbar_arrive_expect_tx(&full_bar[stage], LN_STAGE_BYTES);
+          load_w(stage, kb);
+        }
+        tma_load_2d(smem + stage * LN_STAGE_BYTES, &tmap_a, &full_bar[stage], kb * LN_BK, m_blk * LN_BM);
         if (++stage == LN_NSTAGE) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
+    pdl_wait();
     constexpr uint32_t idesc = make_idesc_bf16(LN_BM, LN_BN);
     constexpr uint32_t hi = desc_hi(1024, SW_128B);
     const uint32_t lo0 = desc_lo(smem_u32(smem), 0);
@@ -95,25 +118,30 @@ linear_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       if (++stage == LN_NSTAGE) { stage = 0; phase ^= 1; }
     }
   } else {
-    // epilogue: warp w may only touch TMEM lanes 32*(w%4) ..
+    // epilogue: warp w may only touch TMEM lanes 32*(w%4) ..  Each lane owns one output row (512 bytes of this tile):
+    // it stages the row in the pipeline memory (idle once done_bar has completed) and sends it with ONE bulk copy,
+    // instead of 16-byte pieces scattered over 32 rows per store instruction.
     const int e = warp & 3;
     const int row = m_blk * LN_BM + e * 32 + lane;
+    float* mine = reinterpret_cast<float*>(smem + (e * 32 + lane) * LN_OUT_PITCH);
+    pdl_wait();
     mbar_wait(done_bar, 0, 42);
     tc_fence_after_sync();
-    float* dst = partial + ((size_t)split * M + row) * N + n_blk * LN_BN;
 #pragma unroll 1
     for (int cb = 0; cb < LN_BN; cb += 32) {
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(32 * e) << 16) + cb, v);
       tmem_ld_wait();
-      if (row < M) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          *reinterpret_cast<float4*>(dst + cb + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                                 __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-        }
+      for (int j = 0; j < 32; j += 4) {
+        *reinterpret_cast<float4*>(mine + cb + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
       }
     }
+    fence_proxy_async_smem();        // the generic-proxy stores above -> visible to the bulk copy engine
+    if (row < M) bulk_store_1d(partial + ((size_t)split * M + row) * N + n_blk * LN_BN, mine, LN_BN * 4);
+    bulk_commit_group();
+    bulk_wait_group0();
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -338,9 +366,25 @@ extern "C" int sia_pack_linear_chw_to_hwc(const float* w, int n, int c, int hw, 
   return launch_status();
 }
 
-extern "C" int sia_linear_splitk(const void* a_bf16, const void* w_bf16, int m, int n, int k, int splits,
-                                 float* partial, void* stream) {
-  using namespace sia;
+namespace sia {
+// [n][k] bf16 (k contiguous) -> tiles [n/128][k/64][128 rows][8 chunks of 16 bytes], chunk c of row r at position
+// c ^ (r & 7): the K-major SWIZZLE_128B image of the tile
+__global__ void retile_linear_kernel(const uint4* __restrict__ src, int n, int k, uint4* __restrict__ dst) {
+  const int kb_total = k / LN_BK;
+  const size_t chunks = (size_t)n * k / 8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < chunks; i += (size_t)gridDim.x * blockDim.x) {
+    const int p = (int)(i & 7);
+    const int r = (int)((i >> 3) & (LN_BN - 1));
+    const size_t tile = i >> 10;
+    const int kb = (int)(tile % kb_total);
+    const size_t nb = tile / kb_total;
+    const int c = p ^ (r & 7);
+    dst[i] = src[((nb * LN_BN + r) * (size_t)k + (size_t)kb * LN_BK) / 8 + c];
+  }
+}
+
+static int linear_splitk_launch(const void* a_bf16, const void* w_bf16, bool tiled, int m, int n, int k, int splits,
+                                float* partial, void* stream) {
   SIA_REQUIRE(a_bf16 && w_bf16 && partial && m >= 1 && n >= 1 && k >= 1 && splits >= 1);
   SIA_REQUIRE(aligned(a_bf16, 16) && aligned(w_bf16, 16) && aligned(partial, 16));
   if (n % LN_BN != 0 || k % LN_BK != 0 || splits > k / LN_BK || splits > 65535) return SIA_E_UNSUPPORTED;
@@ -353,19 +397,48 @@ extern "C" int sia_linear_splitk(const void* a_bf16, const void* w_bf16, int m, 
     int rc = encode_tmap_bf16(&ta, a_bf16, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != 0) return rc;
   }
-  {
+  if (!tiled) {
     const uint64_t dims[2] = {(uint64_t)k, (uint64_t)n};
     const uint64_t strides[1] = {(uint64_t)k * 2};
     const uint32_t box[2] = {LN_BK, LN_BN};
     int rc = encode_tmap_bf16(&tw, w_bf16, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != 0) return rc;
+  } else {
+    tw = ta;      // not read by the tiled kernel
   }
   const int smem = 1024 + LN_NSTAGE * LN_STAGE_BYTES + (2 * LN_NSTAGE + 2) * 8;
-  static SmemSlots configured = {};
-  if (int rc2 = ensure_dynamic_smem(linear_splitk_kernel, smem, &configured)) return rc2;
   dim3 grid((m + LN_BM - 1) / LN_BM, n / LN_BN, splits);
-  return launch_kernel(linear_splitk_kernel, grid, dim3(LN_THREADS), smem, static_cast<cudaStream_t>(stream), true, ta, tw, partial, m, n,
-                                                                                     k / LN_BK, splits);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (tiled) {
+    static SmemSlots configured = {};
+    if (int rc2 = ensure_dynamic_smem(linear_splitk_kernel<true>, smem, &configured)) return rc2;
+    return launch_kernel(linear_splitk_kernel<true>, grid, dim3(LN_THREADS), smem, st, true, ta, tw,
+                         static_cast<const uint8_t*>(w_bf16), partial, m, n, k / LN_BK, splits);
+  }
+  static SmemSlots configured = {};
+  if (int rc2 = ensure_dynamic_smem(linear_splitk_kernel<false>, smem, &configured)) return rc2;
+  return launch_kernel(linear_splitk_kernel<false>, grid, dim3(LN_THREADS), smem, st, true, ta, tw,
+                       static_cast<const uint8_t*>(nullptr), partial, m, n, k / LN_BK, splits);
+}
+}  // namespace sia
+
+extern "C" int sia_linear_splitk(const void* a_bf16, const void* w_bf16, int m, int n, int k, int splits,
+                                 float* partial, void* stream) {
+  return sia::linear_splitk_launch(a_bf16, w_bf16, false, m, n, k, splits, partial, stream);
+}
+
+extern "C" int sia_linear_splitk_tiled(const void* a_bf16, const void* w_tiles_bf16, int m, int n, int k, int splits,
+                                       float* partial, void* stream) {
+  return sia::linear_splitk_launch(a_bf16, w_tiles_bf16, true, m, n, k, splits, partial, stream);
+}
+
+extern "C" int sia_retile_linear_w(const void* w_bf16, int n, int k, void* w_tiles_bf16, void* stream) {
+  using namespace sia;
+  SIA_REQUIRE(w_bf16 && w_tiles_bf16 && w_bf16 != w_tiles_bf16 && n >= 1 && k >= 1);
+  SIA_REQUIRE(aligned(w_bf16, 16) && aligned(w_tiles_bf16, 16));
+  if (n % LN_BN != 0 || k % LN_BK != 0) return SIA_E_UNSUPPORTED;
+  retile_linear_kernel<<<sm_count() * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(w_bf16), n, k, static_cast<uint4*>(w_tiles_bf16));
   return launch_status();
 }
 

@@ -178,6 +178,17 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
       : "memory");
 }
 
+// 1-D bulk copy shared -> global (bulk async-group).  Both 16-byte aligned; bytes a multiple of 16.  The issuing
+// thread commits the group and waits: `read` = the shared-memory source may be overwritten; `all` = complete.
+__device__ __forceinline__ void bulk_store_1d(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               ::"l"(reinterpret_cast<uint64_t>(gdst)), "r"(smem_u32(ssrc)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ---------------------------------- TMEM -----------------------------------------------------
 // ncols: power of two in [32, 512].  Must be executed by one full warp; the same warp frees.
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot_in_smem, uint32_t ncols) {

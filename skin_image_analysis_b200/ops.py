@@ -19,7 +19,7 @@ from ._lib import (LAYOUT_NCHW_BF16, LAYOUT_NCHW_F32, LAYOUT_NHWC4_BF16, NHWC4_P
 
 __all__ = [
     "preprocess_u8hwc", "nchw_f32_to_nhwc4", "pack_conv7x7_c3", "pack_conv3x3", "pack_linear_chw_to_hwc",
-    "conv7x7_c3_relu_pool2", "conv3x3_relu_pool2", "linear_splitk", "head_tail", "head_tail_chain", "confusion_counts",
+    "conv7x7_c3_relu_pool2", "conv3x3_relu_pool2", "linear_splitk", "retile_linear_w", "TiledLinearWeight", "head_tail", "head_tail_chain", "confusion_counts",
     "pad_nhwc", "chw_to_hwc_u8", "LAYOUT_NCHW_F32", "LAYOUT_NCHW_BF16", "LAYOUT_NHWC4_BF16", "NHWC4_PAD",
 ]
 
@@ -371,16 +371,41 @@ def pad_nhwc(x: torch.Tensor, valid_hw, out_hw, out: torch.Tensor | None = None)
 # -------------------------------------------------------------------------------------------------
 # K5 / K6 linear part
 # -------------------------------------------------------------------------------------------------
-def linear_splitk(a: torch.Tensor, w: torch.Tensor, splits: int, out: torch.Tensor | None = None) -> torch.Tensor:
-    _need(a, torch.bfloat16, "a")
+class TiledLinearWeight:
+    """fc1 weights re-laid tile by tile (``sia_retile_linear_w``): ``tiles`` is a flat bf16 tensor of n*k elements."""
+
+    def __init__(self, tiles: torch.Tensor, n: int, k: int):
+        self.tiles, self.n, self.k = tiles, n, k
+        self.shape = (n, k)
+        self.device = tiles.device
+
+
+def retile_linear_w(w: torch.Tensor) -> TiledLinearWeight:
+    """bf16 [n, k] row-major -> TiledLinearWeight (every 128 x 64 tile contiguous, pre-swizzled)."""
     _need(w, torch.bfloat16, "w")
+    n, k = w.shape
+    tiles = torch.empty(n * k, dtype=torch.bfloat16, device=w.device)
+    check(_lib.load().sia_retile_linear_w(ptr(w), n, k, ptr(tiles), stream_ptr()), "sia_retile_linear_w")
+    return TiledLinearWeight(tiles, n, k)
+
+
+def linear_splitk(a: torch.Tensor, w, splits: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    """``w``: bf16 [n, k] tensor, or a TiledLinearWeight (one bulk copy per weight tile)."""
+    _need(a, torch.bfloat16, "a")
+    tiled = isinstance(w, TiledLinearWeight)
+    _need(w.tiles if tiled else w, torch.bfloat16, "w")
     m, k = a.shape
     n, k2 = w.shape
     if k != k2:
         raise ValueError("inner dimensions differ")
     if out is None:
         out = torch.empty((splits, m, n), dtype=torch.float32, device=a.device)
-    check(_lib.load().sia_linear_splitk(ptr(a), ptr(w), m, n, k, splits, ptr(out), stream_ptr()), "sia_linear_splitk")
+    if tiled:
+        check(_lib.load().sia_linear_splitk_tiled(ptr(a), ptr(w.tiles), m, n, k, splits, ptr(out), stream_ptr()),
+              "sia_linear_splitk_tiled")
+    else:
+        check(_lib.load().sia_linear_splitk(ptr(a), ptr(w), m, n, k, splits, ptr(out), stream_ptr()),
+              "sia_linear_splitk")
     return out
 
 

@@ -11,6 +11,8 @@ accumulation.  There is no CPU or eager fallback: a CPU tensor, training mode, o
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -162,6 +164,9 @@ class CnnPlan:
         self.w1 = ops.pack_linear_chw_to_hwc(w1.contiguous(), c_last, raw * raw, self.n1_pad, c_last_pad)
         self.b1 = b1.detach().float().contiguous()
         self.feat = self.w1.shape[1]
+        # tile-major copy for the GEMM (every 128 x 64 weight tile one contiguous 16 KB block); the row-major one is freed
+        if os.environ.get("SIA_FC1_TILED", "1") != "0":          # A/B switch for timing
+            self.w1 = ops.retile_linear_w(self.w1)
         rest = [(w.detach().float(), b.detach().float().contiguous()) for w, b in fc_params[1:]]
         self.fused_tail = (len(rest) == 2 and self.n1 == self.n1_pad and self.n1 <= 512 and rest[0][0].shape[0] <= 256)
         if self.fused_tail:

@@ -81,6 +81,26 @@ def test_linear_splitk(m, n, k, splits):
     assert torch.allclose(got.double(), want, rtol=1e-4, atol=1e-2 * (k ** 0.5) * 0.05)
 
 
+@pytest.mark.parametrize("m,n,k,splits", [(256, 512, 6400, 9), (37, 128, 640, 10), (130, 256, 1024, 3)])
+def test_linear_splitk_tiled_weights_bit_identical(m, n, k, splits):
+    """sia_retile_linear_w + sia_linear_splitk_tiled (one bulk copy per weight tile) == the row-major kernel, bit for
+    bit; the tile image is checked against its definition (row r's 16-byte chunk c at position c ^ (r & 7))."""
+    from skin_image_analysis_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = torch.randn(m, k, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(n, k, device="cuda", generator=g) * 0.05).bfloat16()
+    wt = ops.retile_linear_w(w)
+    tiles = wt.tiles.view(n // 128, k // 64, 128, 8, 8)
+    src = w.view(n // 128, 128, k // 64, 8, 8).permute(0, 2, 1, 3, 4)          # [nb][kb][r][c][e]
+    r = torch.arange(128, device="cuda").view(128, 1)
+    pos = torch.arange(8, device="cuda").view(1, 8)
+    c_of_pos = (pos ^ (r & 7)).view(1, 1, 128, 8, 1).expand(n // 128, k // 64, 128, 8, 8)
+    assert torch.equal(tiles, torch.gather(src, 3, c_of_pos))
+    want = ops.linear_splitk(a, w, splits)
+    got = ops.linear_splitk(a, wt, splits)
+    assert torch.equal(got, want)
+
+
 def test_pack_linear_permutes_chw_to_hwc():
     from skin_image_analysis_b200 import ops
     w = torch.arange(4 * 3 * 5, dtype=torch.float32, device="cuda").view(4, 15)
