@@ -54,7 +54,7 @@ if [[ " $WHAT " == *" profile "* ]]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
       --log-file $OUT/launches_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_launches_bench.log 2>&1
   timeout 1200 ncu --set full --clock-control none --import-source on \
-      -k "regex:^(preprocess_mma_kernel|preprocess_tc_kernel|preprocess_tc2_kernel|preprocess_kernel|preprocess_tv_fast_kernel|conv1_kernel|conv3x3_pair_kernel|conv3x3_kernel|conv3x3_stream_kernel|linear_splitk_kernel|head_tail_kernel)$" -c 8 \
+      -k "regex:^(preprocess_mma_kernel|preprocess_tc_kernel|preprocess_tc2_kernel|preprocess_kernel|preprocess_tv_fast_kernel|conv1_kernel|conv3x3_pair_kernel|conv3x3_kernel|conv3x3_stream_kernel|linear_splitk_kernel|head_tail_cluster_kernel|head_tail_kernel)$" -c 9 \
       -f -o $OUT/prof python tools/profile_target.py 256 1 > $OUT/ncu_full.log 2>&1
   echo "profile rc=$?"; tail -3 $OUT/profile_plain.log
 fi
