@@ -238,13 +238,13 @@ static int launch_tail_cluster_j(int clusters, cudaStream_t st, const float* par
 }
 
 // Clusters of eight of these CTAs the device holds at once (one CTA per SM by shared memory; the CTAs of a cluster
-// share a GPC).  Asked once per device.
+// share a GPC).  Asked once per device; -1 = none.
 static int max_resident_tail_clusters() {
   static int cached[kMaxDevices] = {};
   int& have = cached[current_device()];
   if (have == 0) {
     static SmemSlots configured = {};
-    if (ensure_dynamic_smem(head_tail_cluster_kernel<1>, (int)sizeof(TclSmem), &configured) != 0) return 1;
+    if (ensure_dynamic_smem(head_tail_cluster_kernel<1>, (int)sizeof(TclSmem), &configured) != 0) return -1;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(TCL_CLUSTER * 64);
     cfg.blockDim = dim3(TCL_THREADS);
@@ -252,7 +252,7 @@ static int max_resident_tail_clusters() {
     int n = 0;
     if (cudaOccupancyMaxActiveClusters(&n, head_tail_cluster_kernel<1>, &cfg) != cudaSuccess || n < 1) {
       cudaGetLastError();
-      n = 1;
+      n = -1;                       // no room for a cluster of eight (a partitioned GPU): head_tail_kernel runs instead
     }
     have = n;
   }
@@ -270,6 +270,7 @@ inline bool launch_head_tail_cluster(int* rc, const float* partial, int splits, 
   // fewest images per cluster (8 J) with which every cluster is resident at once; beyond 32 images per resident
   // cluster the grid simply takes several waves
   const int resident = max_resident_tail_clusters();
+  if (resident < 1) return false;
   int j = 1;
   while (j < TCL_MAX_J && (m + 8 * j - 1) / (8 * j) > resident) ++j;
   const int clusters = (m + 8 * j - 1) / (8 * j);
