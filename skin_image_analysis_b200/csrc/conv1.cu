@@ -105,6 +105,7 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
   uint64_t* tempty_bar = bars + 2 * C1_NSTAGE + C1_NACC;
   uint64_t* wload_bar = bars + 2 * C1_NSTAGE + 2 * C1_NACC;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C1_NSTAGE + 2 * C1_NACC + 1);
+  volatile uint32_t* issued = tmem_slot + 1;            // [C1_MMA_WARPS] tiles issued per issuing warp (issue_gate)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -119,6 +120,7 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
       mbar_init(&tempty_bar[i], 4);
     }
     mbar_init(wload_bar, 1);
+    for (int i = 0; i < C1_MMA_WARPS; ++i) issued[i] = 0;
     fence_mbar_init();
     tma_prefetch_desc(&tmap_in);
   }
@@ -218,6 +220,13 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
         trace(lt, 1);
         if (++stage == C1_NSTAGE) { stage = 0; phase ^= 1; }
       }
+      // Drain: the tcgen05.commit arrivals on the empty barriers of the last stages are asynchronous and nobody else
+      // waits for them; the CTA must not exit (and hand its shared memory to the next kernel's CTA, which under
+      // programmatic dependent launch is already queued) while one is in flight.
+      for (int i = 0; i < C1_NSTAGE; ++i) {
+        mbar_wait(&empty_bar[stage], phase ^ 1, 35);
+        if (++stage == C1_NSTAGE) { stage = 0; phase ^= 1; }
+      }
       wait_stage.store(0);
     }
   } else if (warp >= 1 && warp <= C1_MMA_WARPS) {
@@ -244,6 +253,8 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
     for (int lt = which; blockIdx.x + (long long)lt * gridDim.x < total_tiles; lt += C1_MMA_WARPS) {
       const int stage = lt % C1_NSTAGE, acc = lt % C1_NACC;
       const uint32_t phase = (uint32_t)(lt / C1_NSTAGE) & 1u, acc_phase = (uint32_t)(lt / C1_NACC) & 1u;
+      issue_gate(issued, lt, C1_NSTAGE, C1_MMA_WARPS, 36);
+      if (C1_NACC != C1_NSTAGE) issue_gate(issued, lt, C1_NACC, C1_MMA_WARPS, 36);
       wait_acc.begin();
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 32);
       wait_acc.end();
@@ -272,6 +283,7 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __restr
         umma_commit(&tfull_bar[acc]);
       }
       __syncwarp();
+      if (lane == 0) issue_done(issued, lt, C1_MMA_WARPS);
       if (lane == 0) trace(lt, 4);
     }
     loop.end();
@@ -418,7 +430,7 @@ extern "C" int sia_conv7x7_c3_relu_pool2_strided(const void* in_nhwc4, int batch
   const int tiles_y = (h + C1_TILE_Y - 1) / C1_TILE_Y, tiles_x = w / C1_TILE_X;
   const int total = tiles_y * tiles_x * batch;
   const int smem = 1024 + C1_B_BYTES + C1_NSTAGE * C1_STAGE_STRIDE + ONES_BYTES + C1_BIAS_BYTES +
-                   (2 * C1_NSTAGE + 2 * C1_NACC + 2) * 8;
+                   (2 * C1_NSTAGE + 2 * C1_NACC + 4) * 8;
   static SmemSlots configured = {};
   if (int rc2 = ensure_dynamic_smem(conv1_kernel, smem, &configured)) return rc2;
   const int grid = total < sm_count() ? total : sm_count();

@@ -129,6 +129,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
   uint64_t* tempty_bar = bars + 2 * NSTAGE + CV_NACC;
   uint64_t* wload_bar = bars + 2 * NSTAGE + 2 * CV_NACC;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 2 * CV_NACC + 1);
+  volatile uint32_t* issued = tmem_slot + 1;            // [CV_MMA_WARPS] tiles issued per issuing warp (issue_gate)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -143,6 +144,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
       mbar_init(&tempty_bar[i], 4);
     }
     mbar_init(wload_bar, 1);
+    for (int i = 0; i < CV_MMA_WARPS; ++i) issued[i] = 0;
     fence_mbar_init();
     tma_prefetch_desc(&tmap_in);
   }
@@ -189,6 +191,13 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
         trace(lt, 1);
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
       }
+      // Drain: the tcgen05.commit arrivals on the empty barriers of the last stages are asynchronous and nobody else
+      // waits for them; the CTA must not exit (and hand its shared memory to the next kernel's CTA, which under
+      // programmatic dependent launch is already queued) while one is in flight.
+      for (int i = 0; i < NSTAGE; ++i) {
+        mbar_wait(&empty_bar[stage], phase ^ 1, 60);
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+      }
       wait_stage.store(0);
     }
   } else if (warp >= 1 && warp <= CV_MMA_WARPS) {
@@ -213,6 +222,8 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
     for (int lt = warp - 1; blockIdx.x + (long long)lt * gridDim.x < total_tiles; lt += CV_MMA_WARPS) {
       const int stage = lt % NSTAGE, acc = lt % CV_NACC;
       const uint32_t phase = (uint32_t)(lt / NSTAGE) & 1u, acc_phase = (uint32_t)(lt / CV_NACC) & 1u;
+      issue_gate(issued, lt, NSTAGE, CV_MMA_WARPS, 61);       // sia_ptx.cuh: parity waits need the previous use issued
+      if (CV_NACC != NSTAGE) issue_gate(issued, lt, CV_NACC, CV_MMA_WARPS, 61);
       wait_acc.begin();
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 22);
       wait_acc.end();
@@ -245,6 +256,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* __res
         umma_commit(&tfull_bar[acc]);     // accumulator complete -> epilogue
       }
       __syncwarp();
+      if (lane == 0) issue_done(issued, lt, CV_MMA_WARPS);
       if (lane == 0) trace(lt, 4);
     }
     loop.end();
@@ -600,6 +612,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* 
   uint64_t* tempty_bar = bars + 2 * CP_NSTAGE + CV_NACC;
   uint64_t* wload_bar = bars + 2 * CP_NSTAGE + 2 * CV_NACC;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * CP_NSTAGE + 2 * CV_NACC + 1);
+  volatile uint32_t* issued = tmem_slot + 1;            // [CP_MMA_WARPS] tiles issued per issuing warp (issue_gate)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -614,6 +627,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* 
       mbar_init(&tempty_bar[i], 4);
     }
     mbar_init(wload_bar, 1);
+    for (int i = 0; i < CP_MMA_WARPS; ++i) issued[i] = 0;
     fence_mbar_init();
     tma_prefetch_desc(&tmap_in);
   }
@@ -647,6 +661,13 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* 
                     t.ty * CP_TILE_Y - 1, t.n);
         if (++stage == CP_NSTAGE) { stage = 0; phase ^= 1; }
       }
+      // Drain: the tcgen05.commit arrivals on the empty barriers of the last stages are asynchronous and nobody else
+      // waits for them; the CTA must not exit (and hand its shared memory to the next kernel's CTA, which under
+      // programmatic dependent launch is already queued) while one is in flight.
+      for (int i = 0; i < CP_NSTAGE; ++i) {
+        mbar_wait(&empty_bar[stage], phase ^ 1, 62);
+        if (++stage == CP_NSTAGE) { stage = 0; phase ^= 1; }
+      }
     }
   } else if (warp >= 1 && warp <= CP_MMA_WARPS) {
     // ================================ MMA issuer ============================================
@@ -663,6 +684,8 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* 
     for (int lt = warp - 1; blockIdx.x + (long long)lt * gridDim.x < total_tiles; lt += CP_MMA_WARPS) {
       const int stage = lt % CP_NSTAGE, acc = lt % CV_NACC;
       const uint32_t phase = (uint32_t)(lt / CP_NSTAGE) & 1u, acc_phase = (uint32_t)(lt / CV_NACC) & 1u;
+      issue_gate(issued, lt, CP_NSTAGE, CP_MMA_WARPS, 63);    // sia_ptx.cuh: parity waits need the previous use issued
+      if (CV_NACC != CP_NSTAGE) issue_gate(issued, lt, CV_NACC, CP_MMA_WARPS, 63);
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 52);
       mbar_wait(&full_bar[stage], phase, 53);
       tc_fence_after_sync();
@@ -684,6 +707,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint8_t* 
         umma_commit(&tfull_bar[acc]);
       }
       __syncwarp();
+      if (lane == 0) issue_done(issued, lt, CP_MMA_WARPS);
     }
   } else if (warp >= 4) {
     // ================================ epilogue ==============================================
@@ -779,7 +803,7 @@ static int launch_conv3x3_pair(const void* in, int batch, int h, int w, const vo
   const int tiles_x = (w / 2 + CP_TILE_XP - 1) / CP_TILE_XP;
   const int total = tiles_y * tiles_x * batch;
   const int smem = 1024 + CP_B_BYTES + CP_NSTAGE * CP_STAGE_STRIDE + ONES_BYTES + CP_BIAS_BYTES +
-                   (2 * CP_NSTAGE + 2 * CV_NACC + 2) * 8;
+                   (2 * CP_NSTAGE + 2 * CV_NACC + 4) * 8;
   static SmemSlots configured = {};
   if (int rc2 = ensure_dynamic_smem(conv3x3_pair_kernel, smem, &configured)) return rc2;
   const int grid = total < sm_count() ? total : sm_count();
@@ -829,7 +853,7 @@ static int launch_conv3x3(const void* in, int batch, int h, int w, const void* w
   const int tiles_x = (w + CV_TILE_X - 1) / CV_TILE_X;      // TMA zero-fills past the image: 'same' padding
   const int total = tiles_y * tiles_x * batch;
   const int smem = 1024 + C::B_BYTES + NSTAGE * C::STAGE_STRIDE + ONES_BYTES + C::BIAS_BYTES +
-                   (2 * NSTAGE + 2 * CV_NACC + 2) * 8;
+                   (2 * NSTAGE + 2 * CV_NACC + 4) * 8;
   auto kern = conv3x3_kernel<CIN, COUT, NSTAGE>;
   static SmemSlots configured = {};
   if (int rc2 = ensure_dynamic_smem(kern, smem, &configured)) return rc2;

@@ -93,6 +93,12 @@ linear_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         tma_load_2d(smem + stage * LN_STAGE_BYTES, &tmap_a, &full_bar[stage], kb * LN_BK, m_blk * LN_BM);
         if (++stage == LN_NSTAGE) { stage = 0; phase ^= 1; }
       }
+      // Drain: the last stages' tcgen05.commit arrivals on the empty barriers are asynchronous and nobody else waits
+      // for them; they must have landed before the CTA exits and its shared memory goes to the next kernel's CTA.
+      for (int i = 0; i < LN_NSTAGE; ++i) {
+        mbar_wait(&empty_bar[stage], phase ^ 1, 43);
+        if (++stage == LN_NSTAGE) { stage = 0; phase ^= 1; }
+      }
     }
   } else if (warp == 1) {
     pdl_wait();

@@ -124,6 +124,38 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32
   }
 }
 
+// ---------------------------------- several MMA-issuing warps ---------------------------------
+// The conv kernels deal their tiles round-robin to W issuing warps.  A warp that handles only every W-th tile sees
+// only every W-th use of a ring slot's barrier, and an mbarrier wait is by PARITY: if that warp runs ahead of the owner
+// of the use in between, a phase completed two uses ago satisfies its wait (ABA) -- it issues on stale operands, the
+// arrival counts drift apart and the CTA deadlocks.  It took a delayed issuer to show (six back-to-back launches of
+// conv1 under programmatic dependent launch; a spinning NCCL kernel sharing the SMs): the watchdog fired in
+// whichever role starved first.  issue_gate() closes it: before waiting for tile lt, the issuer waits until tile
+// lt - ring has been ISSUED by its owner -- who, by induction, saw the previous phase of the same slot complete -- so
+// the slot's barrier is exactly one phase away and the parity is unambiguous.  `issued[w]` = tiles issued by warp w.
+__device__ __forceinline__ void issue_gate(volatile uint32_t* issued, int lt, int ring, int n_warps, uint32_t site) {
+  const int g = lt - ring;
+  if (g < 0 || (g % n_warps) == (lt % n_warps)) return;      // no earlier use, or this warp's own (program order)
+  const uint32_t need = (uint32_t)(g / n_warps) + 1u;
+  uint32_t spins = 0;
+  while (issued[g % n_warps] < need) {
+    if (++spins > 8u * SIA_WATCHDOG_SPINS) {
+      if (g_watchdog_word != nullptr) {
+        *g_watchdog_word = 0x80000000u | (site << 16) | (blockIdx.x & 0xffffu);
+        __threadfence_system();
+      }
+      __trap();
+    }
+  }
+}
+// After the tile's MMAs and commits have been issued (and a __syncwarp), by one lane of the issuing warp.  No fence:
+// the progress word and the barriers live in the same CTA's shared memory, each side touches them in program order
+// (owner: barrier waits, then this store; reader: the load above, then its barrier waits) and a barrier's phase
+// only moves forward.
+__device__ __forceinline__ void issue_done(volatile uint32_t* issued, int lt, int n_warps) {
+  issued[lt % n_warps] = (uint32_t)(lt / n_warps) + 1u;
+}
+
 // ---------------------------------- programmatic dependent launch ---------------------------
 // A kernel launched with the programmatic-stream-serialization attribute may start while its predecessor in the
 // stream is still running: everything before pdl_wait() (barrier init, TMEM allocation, tensor-map prefetch, loads of
