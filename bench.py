@@ -481,7 +481,8 @@ def run_ours(args):
         # Local GPU work first, THEN the collective: an NCCL kernel that spin-waits for a slower peer must not share
         # the GPU with seconds of queued evaluation kernels (observed at N >= 2 with a 2 s region: a conv1 CTA made no
         # progress while the barrier kernel of an early rank was resident, until its mbarrier watchdog fired).
-        torch.cuda.synchronize()
+        if os.environ.get("SIA_BENCH_BARRIER_NOSYNC") != "1":      # (test switch: reproduce the co-residency case)
+            torch.cuda.synchronize()
         if world > 1:
             torch.distributed.barrier()
             torch.cuda.synchronize()
