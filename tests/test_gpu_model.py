@@ -101,6 +101,34 @@ def test_linear_splitk_tiled_weights_bit_identical(m, n, k, splits):
     assert torch.equal(got, want)
 
 
+def test_wide_first_layer_engine_replays_under_dependent_launch():
+    """Regression ("the hole ... and its repair").  tone_bias_optuna.create_best_model's first layer has
+    192 channels = six launches of the 7x7 kernel in a row; in the captured step each may start under its
+    predecessor's tail (programmatic dependent launch).  With the tiles dealt round-robin to three issuing warps a
+    delayed issuer let another one pass a parity wait on a stale phase and the CTA deadlocked (mbarrier watchdog,
+    site 34) within the first replays of `bench.py --workload optuna224`.  Here: the same engine, batch 128, 12
+    replays; every image counted, and the counts of the replays equal those of the same batches run eagerly."""
+    from skin_image_analysis_b200.engine import EvalEngine
+    from skin_image_analysis_b200.synthetic import random_state_dict
+    batch = 128
+    state = random_state_dict("optuna_best", 224, seed=0)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    u8 = [torch.randint(0, 256, (batch, 450, 600, 3), dtype=torch.uint8, device="cuda", generator=g) for _ in range(2)]
+    label = torch.randint(0, 2, (batch,), dtype=torch.uint8, device="cuda", generator=g)
+    groups = torch.randint(0, 6, (3, batch), dtype=torch.uint8, device="cuda", generator=g)
+    results = []
+    for use_graph in (True, False):
+        eng = EvalEngine(state, batch, (450, 600), 224, use_graph=use_graph, n_slots=2)
+        for k in range(12):
+            eng.step(u8[k % 2], label, groups, slot=k % 2)
+        eng.synchronize()
+        counts = eng.read_counts()
+        assert int(counts[0].sum()) == 12 * batch
+        results.append(counts.cpu())
+        del eng
+    assert torch.equal(results[0], results[1])
+
+
 def test_pack_linear_permutes_chw_to_hwc():
     from skin_image_analysis_b200 import ops
     w = torch.arange(4 * 3 * 5, dtype=torch.float32, device="cuda").view(4, 15)
