@@ -37,6 +37,7 @@ import torch  # noqa: E402
 
 SRC_H, SRC_W, OUT = 450, 600, 224
 METRIC, UNIT = "eval_images_per_sec_224", "images/s"
+NOMINAL_BF16_TFLOPS = 2250.0          # dense bf16, B200 (the profiling guide); only used when a stage beats the measured GEMM
 WORKLOAD = ("configs[1]: SkinCancerListModel eval, batch 256 per GPU, bf16, fused resize+normalise from synthetic "
             "600x450 uint8 ISIC-shaped images, per-Fitzpatrick-group confusion counts")
 # --workload: the default is the configuration the metric is quoted on; the others are BASELINE configs[3] / [4]
@@ -611,6 +612,16 @@ def run_ours(args):
     for v in stages.values():
         if v.get("bound") == "tensor":
             v["peak"], v["frac"] = tensor_tflops, v["achieved"] / tensor_tflops
+            if v["frac"] > 1.0:
+                # the measured denominator is a cuBLAS bf16 GEMM on this pool's parts, not a hardware ceiling: a kernel
+                # that beats it is held against the nominal dense peak (2.25 PFLOP/s at the maximum SM clock) instead
+                mx = stage_clock_summary.get("sm_max_mhz") or 1965.0
+                sm = stage_clock_summary.get("sm_mhz") or mx
+                v["peak_measured"], v["frac_of_measured"] = v["peak"], v["frac"]
+                v["peak"] = NOMINAL_BF16_TFLOPS * sm / mx
+                v["frac"] = v["achieved"] / v["peak"]
+                v["peak_note"] = ("achieved exceeds the cuBLAS-measured bf16 GEMM figure; held against the nominal dense "
+                                  "bf16 peak scaled to the observed SM clock")
     dominant = max((k for k in stages if "bound" in stages[k]), key=lambda k: stages[k]["ms"])
     d = stages[dominant]
     step_ms = 1e3 * dt / steps
