@@ -496,7 +496,18 @@ tail_chain_kernel(const float* __restrict__ partial, int splits, int M, int n1, 
     if (m0 + img < M) {
       const float* src = partial + (size_t)(m0 + img) * n1_stride + k;
       const size_t step = (size_t)M * n1_stride;
-      for (int sp = 0; sp < splits; ++sp) s += __ldg(src + (size_t)sp * step);      // split order: deterministic
+      // sixteen loads in flight per round trip; the adds stay in split order: deterministic
+      for (int sp0 = 0; sp0 < splits; sp0 += 16) {
+        float v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          if (sp0 + u < splits) v[u] = __ldg(src + (size_t)(sp0 + u) * step);
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          if (sp0 + u < splits) s += v[u];
+        }
+      }
       s = fmaxf(s + b1[k], 0.f);
     }
     h[0][img][k] = s;
