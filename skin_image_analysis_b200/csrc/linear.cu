@@ -19,7 +19,10 @@ namespace sia {
 
 constexpr int LN_BM = 128, LN_BN = 128, LN_BK = 64;
 constexpr int LN_STAGE_BYTES = (LN_BM + LN_BN) * LN_BK * 2;  // 32 KB
-constexpr int LN_NSTAGE = 6;
+#ifndef SIA_LN_NSTAGE
+#define SIA_LN_NSTAGE 7
+#endif
+constexpr int LN_NSTAGE = SIA_LN_NSTAGE;
 constexpr int LN_OUT_PITCH = LN_BN * 4 + 16;   // epilogue staging: rows 4 words apart modulo the 32 banks
 constexpr int LN_THREADS = 192;  // warp0 TMA, warp1 MMA (+TMEM alloc), warps2-5 epilogue
 
