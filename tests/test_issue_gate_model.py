@@ -120,7 +120,7 @@ def run(n_tiles: int, n_warps: int, n_stage: int, n_acc: int, gate: bool, rng: r
     return "ok"
 
 
-CONFIGS = [(3, 4, 4), (2, 3, 4), (3, 3, 4), (2, 4, 4)]      # (issuing warps, operand stages, accumulators)
+CONFIGS = [(3, 4, 4), (2, 3, 4), (2, 6, 4), (3, 3, 4), (2, 4, 4)]      # (issuing warps, operand stages, accumulators)
 
 
 @pytest.mark.parametrize("n_warps,n_stage,n_acc", CONFIGS)
@@ -150,3 +150,27 @@ def test_two_issuers_over_rings_of_four_never_alias_even_without_the_gate():
     rng = random.Random(5)
     for trial in range(300):
         assert run(60, 2, 4, 4, False, rng, trial % 2) == "ok"
+
+
+def test_the_kernels_use_modelled_configurations_and_call_the_gate():
+    """Ties the model to the sources: the (issuers, stages, accumulators) of every multi-issuer kernel instance are
+    among CONFIGS, and each of their issue loops calls issue_gate / issue_done."""
+    import os
+    import re
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "skin_image_analysis_b200", "csrc")
+    conv1 = open(os.path.join(root, "conv1.cu")).read()
+    conv3 = open(os.path.join(root, "conv3x3.cu")).read()
+
+    def define(text, name):
+        return int(re.search(rf"#define {name} (\d+)", text).group(1))
+
+    def constexpr(text, name):
+        return int(re.search(rf"constexpr int {name} = (\d+);", text).group(1))
+
+    found = {(define(conv1, "SIA_C1_MMA_WARPS"), define(conv1, "SIA_C1_NSTAGE"), define(conv1, "SIA_C1_NACC")),
+             (define(conv3, "SIA_CP_MMA_WARPS"), constexpr(conv3, "CP_NSTAGE"), constexpr(conv3, "CV_NACC"))}
+    for stages in re.findall(r"launch_conv3x3<\d+, \d+, (\d+)>", conv3):
+        found.add((define(conv3, "SIA_CV_MMA_WARPS"), int(stages), constexpr(conv3, "CV_NACC")))
+    assert found and found <= set(CONFIGS), found - set(CONFIGS)
+    assert conv1.count("issue_gate(issued, lt,") >= 1 and conv1.count("issue_done(issued, lt,") == 1
+    assert conv3.count("issue_gate(issued, lt,") >= 2 and conv3.count("issue_done(issued, lt,") == 2
